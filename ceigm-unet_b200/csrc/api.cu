@@ -1,0 +1,277 @@
+// C ABI of libss2d_b200.so: argument validation, parameter packing, variant dispatch. No torch, no allocation.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "scan_params.h"
+#include "ss2d_b200.h"
+
+namespace ss2d {
+cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
+cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
+cudaError_t scan_bwd_finalize(const ScanParams& p, float* dA, float* dD, float* dbias, cudaStream_t stream);
+cudaError_t cross_scan_launch(const void* x, void* xs, int batch, int channels, int H, int W, int K, const int* dirs,
+                              int dtype, cudaStream_t stream);
+cudaError_t cross_merge_launch(const void* ys, void* y, int batch, int channels, int H, int W, int K, const int* dirs,
+                               int dtype, cudaStream_t stream);
+
+cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
+                                int out_dtype, cudaStream_t stream);
+cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
+                                float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
+                                int out_dtype, cudaStream_t stream);
+int epi_bwd_partials(int batch, int L);
+int epi_max_D(bool backward);
+
+thread_local char g_cuda_err[256] = "";
+thread_local int64_t g_launches = 0;
+
+static int cuda_fail(cudaError_t e) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  return SS2D_ERR_CUDA;
+}
+
+static bool dtype_ok(int d) { return d == SS2D_F32 || d == SS2D_F16 || d == SS2D_BF16; }
+static size_t esize(int d) { return d == SS2D_F32 ? 4 : 2; }
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+constexpr int kStatesPerPass = 32;
+
+static int validate(const ss2d_scan_desc* d) {
+  if (!d) return SS2D_ERR_NULL_POINTER;
+  if (d->batch <= 0 || d->dim <= 0 || d->seqlen <= 0 || d->dstate <= 0 || d->n_groups <= 0) return SS2D_ERR_BAD_SHAPE;
+  if (d->dim % d->n_groups != 0) return SS2D_ERR_BAD_SHAPE;      // reference: selective_scan.cpp:190
+  if (d->dstate > SS2D_MAX_DSTATE) return SS2D_ERR_DSTATE;       // reference: selective_scan.cpp:191
+  if (!dtype_ok(d->io_dtype) || !dtype_ok(d->out_dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (d->out_dtype != d->io_dtype && d->out_dtype != SS2D_F32) return SS2D_ERR_BAD_DTYPE;
+  if (d->layout == SS2D_LAYOUT_NATURAL) {
+    if (d->H <= 0 || d->W <= 0 || (int64_t)d->H * d->W != d->seqlen) return SS2D_ERR_BAD_SHAPE;
+    if (d->n_groups > SS2D_MAX_GROUP_DIRS) return SS2D_ERR_BAD_LAYOUT;
+    for (int g = 0; g < d->n_groups; ++g)
+      if (d->dirs[g] < 1 || d->dirs[g] > 4) return SS2D_ERR_BAD_LAYOUT;
+  } else if (d->layout != SS2D_LAYOUT_SCAN) {
+    return SS2D_ERR_BAD_LAYOUT;
+  }
+  if (d->u_dim_modulo < 0) return SS2D_ERR_BAD_SHAPE;
+  return SS2D_OK;
+}
+
+static void pack(const ss2d_scan_desc* d, ScanParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.batch = d->batch; p.dim = d->dim; p.L = d->seqlen; p.N = d->dstate; p.G = d->n_groups;
+  p.dpg = d->dim / d->n_groups;
+  p.io_dtype = d->io_dtype; p.out_dtype = d->out_dtype; p.softplus = d->delta_softplus;
+  p.layout = d->layout; p.H = d->H; p.W = d->W;
+  for (int g = 0; g < SS2D_MAX_GROUP_DIRS; ++g) p.dirs[g] = d->layout == SS2D_LAYOUT_NATURAL ? d->dirs[g] : 0;
+  p.u_mod = d->u_dim_modulo;
+  p.last_il = d->last_state_interleaved;
+  p.nck = (d->seqlen + SS2D_CHUNK - 1) / SS2D_CHUNK;
+  p.A_ld = d->dstate;
+  p.u_bs = d->u_batch_stride; p.u_ds = d->u_dim_stride;
+  p.dl_bs = d->delta_batch_stride; p.dl_ds = d->delta_dim_stride;
+  p.out_bs = d->out_batch_stride; p.out_ds = d->out_dim_stride;
+  p.B_bs = d->B_batch_stride; p.B_gs = d->B_group_stride; p.B_ns = d->B_state_stride;
+  p.C_bs = d->C_batch_stride; p.C_gs = d->C_group_stride; p.C_ns = d->C_state_stride;
+}
+
+// states are processed in passes of <= 32; pass i covers [32 i, 32 i + n_i)
+static int n_passes(int N) { return (N + kStatesPerPass - 1) / kStatesPerPass; }
+static size_t ckpt_floats_pass(const ss2d_scan_desc* d, int n) {
+  const Variant v = pick_variant(n);
+  const size_t nck = (d->seqlen + SS2D_CHUNK - 1) / SS2D_CHUNK;
+  return (size_t)d->batch * d->dim * nck * (size_t)(v.NS * v.R);
+}
+static size_t round4(size_t x) { return (x + 3) & ~(size_t)3; }
+
+}  // namespace ss2d
+
+using namespace ss2d;
+
+extern "C" {
+
+size_t ss2d_scan_ckpt_floats(const ss2d_scan_desc* d) {
+  if (validate(d) != SS2D_OK) return 0;
+  size_t total = 0;
+  for (int i = 0; i < n_passes(d->dstate); ++i) {
+    const int n = d->dstate - i * kStatesPerPass < kStatesPerPass ? d->dstate - i * kStatesPerPass : kStatesPerPass;
+    total += round4(ckpt_floats_pass(d, n));
+  }
+  return total;
+}
+
+size_t ss2d_scan_bwd_workspace_bytes(const ss2d_scan_desc* d, int have_ckpt) {
+  if (validate(d) != SS2D_OK) return 0;
+  const int nmax = d->dstate < kStatesPerPass ? d->dstate : kStatesPerPass;
+  size_t floats = round4((size_t)d->batch * d->dim * (nmax + 2));
+  if (!have_ckpt) floats += ss2d_scan_ckpt_floats(d);
+  return floats * sizeof(float);
+}
+
+int ss2d_scan_fwd(const ss2d_scan_desc* d, const void* u, const void* delta, const float* A, const void* Bmat,
+                  const void* Cmat, const float* Dvec, const float* delta_bias, void* out, float* ckpt,
+                  float* last_state, ss2d_stream_t stream) {
+  int rc = validate(d);
+  if (rc != SS2D_OK) return rc;
+  if (!u || !delta || !A || !Bmat || !Cmat || (!out && !ckpt && !last_state)) return SS2D_ERR_NULL_POINTER;
+  if (!aligned(u, esize(d->io_dtype)) || !aligned(delta, esize(d->io_dtype)) || !aligned(Bmat, esize(d->io_dtype)) ||
+      !aligned(Cmat, esize(d->io_dtype)) || !aligned(A, 4) || (out && !aligned(out, esize(d->out_dtype))) ||
+      (ckpt && !aligned(ckpt, 16)))
+    return SS2D_ERR_ALIGNMENT;
+  ScanParams p;
+  pack(d, p);
+  p.u = u; p.delta = delta; p.Dv = Dvec; p.bias = delta_bias; p.out = out; p.last_state = last_state;
+  size_t ck_off = 0;
+  for (int i = 0; i < n_passes(d->dstate); ++i) {
+    const int n0 = i * kStatesPerPass;
+    const int n = d->dstate - n0 < kStatesPerPass ? d->dstate - n0 : kStatesPerPass;
+    const Variant v = pick_variant(n);
+    p.N = n; p.NP = v.NS * v.R; p.accum = i > 0;
+    p.A = A + n0;
+    p.Bm = static_cast<const char*>(Bmat) + (size_t)n0 * d->B_state_stride * esize(d->io_dtype);
+    p.Cm = static_cast<const char*>(Cmat) + (size_t)n0 * d->C_state_stride * esize(d->io_dtype);
+    p.ckpt = ckpt ? ckpt + ck_off : nullptr;
+    p.last_state = last_state ? last_state + (d->last_state_interleaved ? 2 : 1) * n0 : nullptr;
+    ck_off += round4(ckpt_floats_pass(d, n));
+    cudaError_t e = scan_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e);
+    ++g_launches;
+  }
+  return SS2D_OK;
+}
+
+int ss2d_scan_bwd(const ss2d_scan_desc* d, const void* u, const void* delta, const float* A, const void* Bmat,
+                  const void* Cmat, const float* Dvec, const float* delta_bias, const void* dout, const float* ckpt,
+                  void* du, void* ddelta, float* dA, float* dB, float* dC, float* dD, float* ddelta_bias,
+                  void* workspace, size_t workspace_bytes, ss2d_stream_t stream) {
+  int rc = validate(d);
+  if (rc != SS2D_OK) return rc;
+  if (!u || !delta || !A || !Bmat || !Cmat || !dout || !du || !ddelta || !dA || !dB || !dC) return SS2D_ERR_NULL_POINTER;
+  if ((Dvec && !dD) || (delta_bias && !ddelta_bias)) return SS2D_ERR_NULL_POINTER;
+  if (!workspace || workspace_bytes < ss2d_scan_bwd_workspace_bytes(d, ckpt != nullptr) || !aligned(workspace, 16))
+    return SS2D_ERR_WORKSPACE;
+  if (ckpt && !aligned(ckpt, 16)) return SS2D_ERR_ALIGNMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  const int nmax = d->dstate < kStatesPerPass ? d->dstate : kStatesPerPass;
+  float* part = ws;
+  float* own_ckpt = ws + round4((size_t)d->batch * d->dim * (nmax + 2));
+  if (!ckpt) {   // recompute the chunk states with a forward sweep that writes nothing else
+    rc = ss2d_scan_fwd(d, u, delta, A, Bmat, Cmat, Dvec, delta_bias, nullptr, own_ckpt, nullptr, stream);
+    if (rc != SS2D_OK) return rc;
+    ckpt = own_ckpt;
+  }
+  ScanParams p;
+  pack(d, p);
+  p.u = u; p.delta = delta; p.Dv = Dvec; p.bias = delta_bias; p.dout = dout; p.du = du; p.ddelta = ddelta;
+  p.part = part;
+  size_t ck_off = 0;
+  for (int i = 0; i < n_passes(d->dstate); ++i) {
+    const int n0 = i * kStatesPerPass;
+    const int n = d->dstate - n0 < kStatesPerPass ? d->dstate - n0 : kStatesPerPass;
+    const Variant v = pick_variant(n);
+    p.N = n; p.NP = v.NS * v.R; p.accum = i > 0;
+    p.A = A + n0;
+    p.Bm = static_cast<const char*>(Bmat) + (size_t)n0 * d->B_state_stride * esize(d->io_dtype);
+    p.Cm = static_cast<const char*>(Cmat) + (size_t)n0 * d->C_state_stride * esize(d->io_dtype);
+    p.ckpt_in = ckpt + ck_off;
+    p.dB = dB + (size_t)n0 * d->seqlen;
+    p.dC = dC + (size_t)n0 * d->seqlen;
+    ck_off += round4(ckpt_floats_pass(d, n));
+    cudaError_t e = scan_bwd_dispatch(p, st);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = scan_bwd_finalize(p, dA + n0, dD, ddelta_bias, st);
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches += 2;
+  }
+  return SS2D_OK;
+}
+
+int ss2d_cross_scan(const void* x, void* xs, int32_t batch, int32_t channels, int32_t H, int32_t W, int32_t K,
+                    const int32_t* dirs, int32_t dtype, ss2d_stream_t stream) {
+  if (!x || !xs || !dirs) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0 || K <= 0 || K > SS2D_MAX_GROUP_DIRS) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  for (int k = 0; k < K; ++k) if (dirs[k] < 1 || dirs[k] > 4) return SS2D_ERR_BAD_LAYOUT;
+  cudaError_t e = cross_scan_launch(x, xs, batch, channels, H, W, K, dirs, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int ss2d_cross_merge(const void* ys, void* y, int32_t batch, int32_t channels, int32_t H, int32_t W, int32_t K,
+                     const int32_t* dirs, int32_t dtype, ss2d_stream_t stream) {
+  if (!ys || !y || !dirs) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || channels <= 0 || H <= 0 || W <= 0 || K <= 0 || K > SS2D_MAX_GROUP_DIRS) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  for (int k = 0; k < K; ++k) if (dirs[k] < 1 || dirs[k] > 4) return SS2D_ERR_BAD_LAYOUT;
+  cudaError_t e = cross_merge_launch(ys, y, batch, channels, H, W, K, dirs, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L) {
+  if (batch <= 0 || L <= 0) return 0;
+  return epi_bwd_partials(batch, L);
+}
+
+int ss2d_out_gate_fwd(const float* ys, int32_t K, const float* ln_weight, const float* ln_bias, const void* z,
+                      int64_t z_row_stride, int32_t z_act, void* out, float* mean_rstd, int32_t batch, int32_t D,
+                      int32_t L, float eps, int32_t z_dtype, int32_t out_dtype, ss2d_stream_t stream) {
+  if (!ys || !out) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || D <= 0 || L <= 0 || K <= 0 || K > SS2D_MAX_GROUP_DIRS) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(z_dtype) || !dtype_ok(out_dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (D > epi_max_D(false)) return SS2D_ERR_UNSUPPORTED;
+  cudaError_t e = out_gate_fwd_launch(ys, K, ln_weight, ln_bias, z, z_row_stride, z_act, out, mean_rstd, batch, D, L, eps,
+                                      z_dtype, out_dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const float* ln_bias, const void* z,
+                      int64_t z_row_stride, int32_t z_act, const void* dout, const float* mean_rstd, float* dy,
+                      void* dz, int64_t dz_row_stride, float* dln_weight_partial, float* dln_bias_partial,
+                      int32_t n_partials, int32_t batch, int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype,
+                      ss2d_stream_t stream) {
+  if (!ys || !dout || !mean_rstd || !dy || !dln_weight_partial || !dln_bias_partial) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || D <= 0 || L <= 0 || K <= 0 || K > SS2D_MAX_GROUP_DIRS) return SS2D_ERR_BAD_SHAPE;
+  if (n_partials != epi_bwd_partials(batch, L)) return SS2D_ERR_WORKSPACE;
+  if (!dtype_ok(z_dtype) || !dtype_ok(out_dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (D > epi_max_D(true)) return SS2D_ERR_UNSUPPORTED;
+  cudaError_t e = out_gate_bwd_launch(ys, K, ln_weight, ln_bias, z, z_row_stride, z_act, dout, mean_rstd, dy, dz,
+                                      dz_row_stride, dln_weight_partial, dln_bias_partial, n_partials, batch, D, L,
+                                      z_dtype, out_dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+const char* ss2d_strerror(int status) {
+  switch (status) {
+    case SS2D_OK: return "ok";
+    case SS2D_ERR_NULL_POINTER: return "a required pointer is NULL";
+    case SS2D_ERR_BAD_SHAPE: return "bad shape (sizes must be positive, dim % n_groups == 0, H*W == seqlen)";
+    case SS2D_ERR_BAD_DTYPE: return "bad dtype (fp32/fp16/bf16; out dtype must equal io dtype or be fp32)";
+    case SS2D_ERR_DSTATE: return "selective_scan only supports state dimension <= 256";
+    case SS2D_ERR_BAD_LAYOUT: return "bad layout or scan direction";
+    case SS2D_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+    case SS2D_ERR_CUDA: return "CUDA runtime error (see ss2d_last_cuda_error)";
+    case SS2D_ERR_UNSUPPORTED: return "unsupported combination";
+    case SS2D_ERR_ALIGNMENT: return "pointer not aligned to its element size";
+    default: return "unknown status";
+  }
+}
+
+const char* ss2d_last_cuda_error(void) { return g_cuda_err; }
+const char* ss2d_version(void) { return "ss2d_b200 0.1.0 sm_100a"; }
+int64_t ss2d_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+}  // extern "C"

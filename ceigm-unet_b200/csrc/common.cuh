@@ -1,0 +1,111 @@
+// Shared device helpers for the ss2d_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ss2d_b200.h"
+
+namespace ss2d {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// MUFU.EX2 / MUFU.LG2 (16 lanes/clk/SM measured on B200: tools/ubench/pipes.cu)
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// softplus with PyTorch's default threshold 20 (reference: selective_scan_fwd_kernel.cuh:117 and
+// F.softplus in selective_scan_ref). Small exp(x) uses the log1p series so tiny deltas keep relative accuracy.
+__device__ __forceinline__ float softplus20(float x) {
+  const float e = ex2f(x * kLog2e);
+  const float series = e * (1.f - e * (0.5f - e * 0.33333334f));
+  const float full = kLn2 * lg2f(1.f + e);
+  const float sp = e < 0.0078125f ? series : full;
+  return x > 20.f ? x : sp;
+}
+// d softplus(x) / dx = sigmoid(x) (1 above the threshold)
+__device__ __forceinline__ float softplus20_grad(float x) {
+  const float e = ex2f(-x * kLog2e);
+  return x > 20.f ? 1.f : __fdividef(1.f, 1.f + e);
+}
+
+// ---- dtype-erased 4-element loads/stores (runtime dtype: the math is always fp32 from shared memory) ----
+__device__ __forceinline__ size_t dtype_size(int dt) { return dt == SS2D_F32 ? 4 : 2; }
+
+__device__ __forceinline__ float load1(const void* base, int64_t idx, int dt) {
+  if (dt == SS2D_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  if (dt == SS2D_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(base) + idx));
+  return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+}
+__device__ __forceinline__ void store1(void* base, int64_t idx, int dt, float v) {
+  if (dt == SS2D_F32) reinterpret_cast<float*>(base)[idx] = v;
+  else if (dt == SS2D_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+// true when 4 consecutive elements starting at idx can be moved with one vector access
+__device__ __forceinline__ bool vec4_ok(const void* base, int64_t idx, int dt) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(base) + static_cast<uintptr_t>(idx) * dtype_size(dt);
+  return (a & (4 * dtype_size(dt) - 1)) == 0;
+}
+__device__ __forceinline__ float4 load4(const void* base, int64_t idx, int dt) {
+  if (dt == SS2D_F32) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + idx));
+  float4 r;
+  if (dt == SS2D_F16) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    r = make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    r = make_float4(a.x, a.y, b.x, b.y);
+  }
+  return r;
+}
+__device__ __forceinline__ void store4(void* base, int64_t idx, int dt, float4 v) {
+  if (dt == SS2D_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = v;
+    return;
+  }
+  uint2 raw;
+  if (dt == SS2D_F16) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    raw.x = *reinterpret_cast<const uint32_t*>(&a);
+    raw.y = *reinterpret_cast<const uint32_t*>(&b);
+  } else {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    raw.x = *reinterpret_cast<const uint32_t*>(&a);
+    raw.y = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = raw;
+}
+
+// ---- scan-order addressing: position l of the traversal -> natural offset inside an (H, W) plane ----
+// dir 0: tensors already in scan order (identity). 1: row-major, 2: column-major, 3/4: reversed.
+// (index maps of CrossScan_1.._4, /root/reference/gm-unet/model/gm/csms6s.py:56-206)
+struct ScanOrder {
+  int dir, H, W, L;
+  __device__ __forceinline__ bool contiguous() const { return dir == 0 || dir == 1 || dir == 3; }
+  __device__ __forceinline__ bool reversed() const { return dir == 3 || dir == 4; }
+  __device__ __forceinline__ int natural(int l) const {
+    if (dir == 0 || dir == 1) return l;
+    if (dir == 3) return L - 1 - l;
+    const int t = dir == 2 ? l : L - 1 - l;   // column-major position
+    const int w = t / H, h = t - w * H;
+    return h * W + w;
+  }
+};
+
+__device__ __forceinline__ float& f4_at(float4& v, int e) { return reinterpret_cast<float*>(&v)[e]; }
+
+}  // namespace ss2d

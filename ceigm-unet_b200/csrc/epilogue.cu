@@ -1,0 +1,213 @@
+// Fused SS2D epilogue: cross-merge sum over the K directions + (B,D,L)->(B,L,D) transpose + LayerNorm(D) +
+// SiLU(z) gate, forward and backward. Replaces, per SS2D call, CrossMerge.forward, the transpose copy, out_norm,
+// act(z) and `y * z` of /root/reference/gm-unet/model/gm/ss2d.py:486-498, 506-508, 515-517 (5-6 kernels and as
+// many round trips through HBM) with one pass: read ys (K planes) and z once, write out once.
+// HBM-bound; a CTA owns 32 pixels x all D channels (tile staged in shared memory for the transpose).
+#include "common.cuh"
+
+namespace ss2d {
+
+constexpr int kEpiTL = 32;         // pixels per tile
+constexpr int kEpiThreads = 256;
+constexpr int kEpiMaxDPT = 4;     // channels per thread in the backward: D <= 1024 (shared memory caps D near 860)
+
+__device__ __forceinline__ float merge_k(const float* __restrict__ ys, int K, int64_t plane_stride, int64_t off) {
+  if (K == 4) {   // association of CrossMerge.forward, csms6s.py:38-39
+    const float a = __ldg(ys + off) + __ldg(ys + 2 * plane_stride + off);
+    const float b = __ldg(ys + plane_stride + off) + __ldg(ys + 3 * plane_stride + off);
+    return a + b;
+  }
+  float acc = __ldg(ys + off);
+  for (int k = 1; k < K; ++k) acc += __ldg(ys + k * plane_stride + off);
+  return acc;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + ex2f(-x * kLog2e)); }
+__device__ __forceinline__ float silu_grad_f(float x) {
+  const float s = __fdividef(1.f, 1.f + ex2f(-x * kLog2e));
+  return s * (1.f + x * (1.f - s));
+}
+
+// loads the merged tile y[d][pix] for pixels [l0, l0+32) of batch b into s_y[d * 33 + pix]
+__device__ __forceinline__ void load_merged_tile(float* s_y, const float* __restrict__ ys, int K, int b, int D, int L,
+                                                 int l0) {
+  const int64_t plane = (int64_t)D * L;
+  const float* base = ys + (int64_t)b * K * plane;
+  for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
+    const int d = i / kEpiTL, px = i - d * kEpiTL;
+    const int l = l0 + px;
+    s_y[d * (kEpiTL + 1) + px] = l < L ? merge_k(base, K, plane, (int64_t)d * L + l) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kEpiThreads)
+out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                    const void* __restrict__ z, int64_t z_rs, int z_act, void* __restrict__ out,
+                    float* __restrict__ mean_rstd, int batch, int D, int L, float eps, int z_dtype, int out_dtype,
+                    int tiles_per_batch) {
+  extern __shared__ float s_y[];                 // [D][33]
+  __shared__ float s_stat[kEpiTL][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
+    const int b = tile / tiles_per_batch, l0 = (tile - b * tiles_per_batch) * kEpiTL;
+    __syncthreads();
+    load_merged_tile(s_y, ys, K, b, D, L, l0);
+    __syncthreads();
+    // LayerNorm statistics per pixel (two-pass, fp32): warp w handles pixels w, w+8, ...
+    for (int px = warp; px < kEpiTL; px += kEpiThreads / 32) {
+      float s = 0.f;
+      for (int d = lane; d < D; d += 32) s += s_y[d * (kEpiTL + 1) + px];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / D;
+      float v = 0.f;
+      for (int d = lane; d < D; d += 32) { const float t = s_y[d * (kEpiTL + 1) + px] - mean; v = fmaf(t, t, v); }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const float rstd = rsqrtf(v / D + eps);
+      if (lane == 0) {
+        s_stat[px][0] = mean; s_stat[px][1] = rstd;
+        if (l0 + px < L && mean_rstd) {
+          mean_rstd[((int64_t)b * L + l0 + px) * 2 + 0] = mean;
+          mean_rstd[((int64_t)b * L + l0 + px) * 2 + 1] = rstd;
+        }
+      }
+    }
+    __syncthreads();
+    // normalise, gate, write channels-last (threads run along D: coalesced)
+    for (int i = threadIdx.x; i < kEpiTL * D; i += kEpiThreads) {
+      const int px = i / D, d = i - px * D;
+      const int l = l0 + px;
+      if (l >= L) continue;
+      float o = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
+      o = lnw ? fmaf(o, __ldg(lnw + d), lnb ? __ldg(lnb + d) : 0.f) : o;
+      if (z) {
+        float zz = load1(z, ((int64_t)b * L + l) * z_rs + d, z_dtype);
+        if (z_act) zz = silu_f(zz);
+        o *= zz;
+      }
+      store1(out, ((int64_t)b * L + l) * D + d, out_dtype, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kEpiThreads)
+out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                    const void* __restrict__ z, int64_t z_rs, int z_act, const void* __restrict__ dout,
+                    const float* __restrict__ mean_rstd, float* __restrict__ dy, void* __restrict__ dz, int64_t dz_rs,
+                    float* __restrict__ dw_part, float* __restrict__ db_part, int batch, int D, int L, int z_dtype,
+                    int out_dtype, int tiles_per_batch) {
+  extern __shared__ float smem[];
+  float* s_y = smem;                               // [D][33] merged y, then dy
+  float* s_g = s_y + (size_t)D * (kEpiTL + 1);     // [D][33] d(yn) = dout * gate * w
+  __shared__ float s_stat[kEpiTL][4];              // mean, rstd, mean(g), mean(g * yn)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc_dw[kEpiMaxDPT], acc_db[kEpiMaxDPT];
+#pragma unroll
+  for (int m = 0; m < kEpiMaxDPT; ++m) { acc_dw[m] = 0.f; acc_db[m] = 0.f; }
+  for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
+    const int b = tile / tiles_per_batch, l0 = (tile - b * tiles_per_batch) * kEpiTL;
+    __syncthreads();
+    load_merged_tile(s_y, ys, K, b, D, L, l0);
+    for (int px = threadIdx.x; px < kEpiTL; px += kEpiThreads) {
+      const int l = l0 + px;
+      s_stat[px][0] = l < L ? mean_rstd[((int64_t)b * L + l) * 2 + 0] : 0.f;
+      s_stat[px][1] = l < L ? mean_rstd[((int64_t)b * L + l) * 2 + 1] : 0.f;
+    }
+    __syncthreads();
+    // pass 1 (threads along D, coalesced): gate grads and d(yn). Thread t always meets channels t, t+256, ... so
+    // the LayerNorm weight/bias gradients accumulate in registers, without atomics.
+    for (int px = 0; px < kEpiTL; ++px) {
+      const int l = l0 + px;
+#pragma unroll
+      for (int m = 0; m < kEpiMaxDPT; ++m) {
+        const int d = threadIdx.x + m * kEpiThreads;
+        if (d >= D) break;
+        float g = 0.f;
+        if (l < L) {
+          const float yn = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
+          const float w = lnw ? __ldg(lnw + d) : 1.f;
+          const float lin = lnw ? fmaf(yn, w, lnb ? __ldg(lnb + d) : 0.f) : yn;
+          float go = load1(dout, ((int64_t)b * L + l) * D + d, out_dtype);
+          if (z) {
+            const float zr = load1(z, ((int64_t)b * L + l) * z_rs + d, z_dtype);
+            const float gate = z_act ? silu_f(zr) : zr;
+            if (dz) store1(dz, ((int64_t)b * L + l) * dz_rs + d, z_dtype, go * lin * (z_act ? silu_grad_f(zr) : 1.f));
+            go *= gate;
+          }
+          acc_dw[m] = fmaf(go, yn, acc_dw[m]);
+          acc_db[m] += go;
+          g = go * w;
+        }
+        s_g[d * (kEpiTL + 1) + px] = g;
+      }
+    }
+    __syncthreads();
+    for (int px = warp; px < kEpiTL; px += kEpiThreads / 32) {
+      float s1 = 0.f, s2 = 0.f;
+      const float mean = s_stat[px][0], rstd = s_stat[px][1];
+      for (int d = lane; d < D; d += 32) {
+        const float g = s_g[d * (kEpiTL + 1) + px];
+        s1 += g;
+        s2 = fmaf(g, (s_y[d * (kEpiTL + 1) + px] - mean) * rstd, s2);
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      if (lane == 0) { s_stat[px][2] = s1 / D; s_stat[px][3] = s2 / D; }
+    }
+    __syncthreads();
+    // dy[b][d][l] = rstd * (g - mean(g) - yn * mean(g yn)); threads along pixels: coalesced along L
+    for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
+      const int d = i / kEpiTL, px = i - d * kEpiTL;
+      const int l = l0 + px;
+      if (l >= L) continue;
+      const float mean = s_stat[px][0], rstd = s_stat[px][1];
+      const float yn = (s_y[d * (kEpiTL + 1) + px] - mean) * rstd;
+      dy[((int64_t)b * D + d) * L + l] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kEpiMaxDPT; ++m) {
+    const int d = threadIdx.x + m * kEpiThreads;
+    if (d < D) {
+      dw_part[(int64_t)blockIdx.x * D + d] = acc_dw[m];
+      db_part[(int64_t)blockIdx.x * D + d] = acc_db[m];
+    }
+  }
+}
+
+int epi_bwd_partials(int batch, int L) {
+  const int tiles = batch * ((L + kEpiTL - 1) / kEpiTL);
+  return tiles < 148 * 2 ? tiles : 148 * 2;
+}
+int epi_max_D(bool backward) { return backward ? 832 : 1664; }   // keeps the tile(s) within 227 KB of shared memory
+
+cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
+                                int out_dtype, cudaStream_t stream) {
+  const size_t smem = (size_t)D * (kEpiTL + 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(out_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int tpb = (L + kEpiTL - 1) / kEpiTL;
+  const int tiles = batch * tpb;
+  const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
+  out_gate_fwd_kernel<<<grid, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
+                                                          eps, z_dtype, out_dtype, tpb);
+  return cudaGetLastError();
+}
+
+cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
+                                float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
+                                int out_dtype, cudaStream_t stream) {
+  const size_t smem = (size_t)2 * D * (kEpiTL + 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(out_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int tpb = (L + kEpiTL - 1) / kEpiTL;
+  out_gate_bwd_kernel<<<n_partials, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
+                                                                dz_rs, dw_part, db_part, batch, D, L, z_dtype, out_dtype,
+                                                                tpb);
+  return cudaGetLastError();
+}
+
+}  // namespace ss2d

@@ -1,0 +1,181 @@
+"""autograd.Function surface of the reference (boundary b2), backed by libss2d_b200.so.
+
+Same class names and `.apply` signatures as /root/reference/gm-unet/model/gm/csms6s.py:
+  SelectiveScanCore / SelectiveScanOflex   csms6s.py:347-386
+  CrossScan / CrossMerge (K = 4)           csms6s.py:11-53
+  CrossScan_1.._4 / CrossMerge_1.._4       csms6s.py:56-206
+plus the fused operator `ss2d_core_fused` (cross-scan + scan + cross-merge + out_norm + gate without any
+permuted copy), which `modules.SS2D` uses when it recognises the (CrossScan_k, CrossMerge_k) pair it is given.
+Backward passes of the single-direction scans are the TRUE adjoints (the reference's CrossScan_2/_4.backward
+are only correct for H == W; on square maps the results are identical).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _custom_fwd(fn):
+    return torch.amp.custom_fwd(fn, device_type="cuda")
+
+
+def _custom_bwd(fn):
+    return torch.amp.custom_bwd(fn, device_type="cuda")
+
+
+class SelectiveScanCore(torch.autograd.Function):
+    """out = selective_scan(u, delta, A, B, C, D, delta_bias); output dtype = input dtype (csms6s.py:347-365)."""
+    OUT_FLOAT = False
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1,
+                oflex=True):
+        prob = ops.ScanProblem(u, delta, A, B, C, D, delta_bias, delta_softplus, out_float=False)
+        out, x = prob.forward(want_state=True)
+        ctx.delta_softplus = delta_softplus
+        ctx.out_float = False
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        return out
+
+    @staticmethod
+    @_custom_bwd
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        prob = ops.ScanProblem(u, delta, A, B, C, D, delta_bias, ctx.delta_softplus, out_float=ctx.out_float)
+        du, ddelta, dA, dB, dC, dD, dbias = prob.backward(dout, x)
+        return (du, ddelta, dA, dB, dC, dD, dbias, None, None, None, None)
+
+
+class SelectiveScanOflex(torch.autograd.Function):
+    """Same, but with oflex=True the output (and dout) are fp32 whatever the input dtype (csms6s.py:368-386)."""
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1, backnrows=1,
+                oflex=True):
+        prob = ops.ScanProblem(u, delta, A, B, C, D, delta_bias, delta_softplus, out_float=bool(oflex))
+        out, x = prob.forward(want_state=True)
+        ctx.delta_softplus = delta_softplus
+        ctx.out_float = bool(oflex)
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        return out
+
+    backward = SelectiveScanCore.backward
+
+
+# ---- cross scan / merge ---------------------------------------------------------------------------
+def _make_cross_pair(dirs, suffix):
+    dirs = tuple(dirs)
+    K = len(dirs)
+
+    class _Scan(torch.autograd.Function):
+        DIRS = dirs
+
+        @staticmethod
+        def forward(ctx, x: torch.Tensor):
+            Bn, Cn, H, W = x.shape
+            ctx.shape = (Bn, Cn, H, W)
+            return ops.cross_scan(x, dirs)                              # (B, K, C, L)
+
+        @staticmethod
+        def backward(ctx, ys: torch.Tensor):
+            Bn, Cn, H, W = ctx.shape
+            return ops.cross_merge(ys.contiguous(), (H, W), dirs).view(Bn, Cn, H, W)
+
+    class _Merge(torch.autograd.Function):
+        DIRS = dirs
+
+        @staticmethod
+        def forward(ctx, ys: torch.Tensor):
+            Bn, Kn, D, H, W = ys.shape
+            ctx.shape = (H, W)
+            return ops.cross_merge(ys.reshape(Bn, Kn, D, H * W), (H, W), dirs)     # (B, D, L)
+
+        @staticmethod
+        def backward(ctx, x: torch.Tensor):
+            H, W = ctx.shape
+            Bn, Cn, L = x.shape
+            return ops.cross_scan(x.reshape(Bn, Cn, H, W), dirs).view(Bn, K, Cn, H, W)
+
+    _Scan.__name__ = _Scan.__qualname__ = "CrossScan" + suffix
+    _Merge.__name__ = _Merge.__qualname__ = "CrossMerge" + suffix
+    return _Scan, _Merge
+
+
+CrossScan, CrossMerge = _make_cross_pair((1, 2, 3, 4), "")
+CrossScan_1, CrossMerge_1 = _make_cross_pair((1,), "_1")
+CrossScan_2, CrossMerge_2 = _make_cross_pair((2,), "_2")
+CrossScan_3, CrossMerge_3 = _make_cross_pair((3,), "_3")
+CrossScan_4, CrossMerge_4 = _make_cross_pair((4,), "_4")
+
+
+def directions_of(cross_scan_cls, cross_merge_cls):
+    """Directions encoded by a (CrossScan*, CrossMerge*) class pair — ours or the reference's (matched by class
+    name, since the reference passes the classes themselves into SS2D.forward, groupmamba.py:143-146)."""
+    table = {"CrossScan": (1, 2, 3, 4), "CrossScan_1": (1,), "CrossScan_2": (2,), "CrossScan_3": (3,), "CrossScan_4": (4,)}
+    sname, mname = cross_scan_cls.__name__, cross_merge_cls.__name__
+    if sname not in table or mname != sname.replace("Scan", "Merge"):
+        return None
+    return table[sname]
+
+
+# ---- fused SS2D core ------------------------------------------------------------------------------
+class _SS2DScanNatural(torch.autograd.Function):
+    """Selective scan over K directions in NATURAL layout: x (B, D, L) shared by all directions, delta
+    (B, K*D, L), Bs/Cs (B, K, N, L) all in natural pixel order -> ys (B, K, D, L) natural order, fp32."""
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, x, dts, A, Bs, Cs, Ds, delta_bias, H, W, dirs):
+        D = x.shape[1]
+        prob = ops.ScanProblem(x, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=D)
+        out, st = prob.forward(want_state=True)
+        ctx.meta = (H, W, tuple(dirs), D)
+        ctx.save_for_backward(x, dts, A, Bs, Cs, Ds, delta_bias, st)
+        return out.view(x.shape[0], len(dirs), D, H * W)
+
+    @staticmethod
+    @_custom_bwd
+    def backward(ctx, dys):
+        """dys arrives as (B, K, D, L). When it is a stride-0 expansion over K (what `_OutGate.backward` returns:
+        CrossMerge's adjoint hands every direction the same gradient, csms6s.py:42-53) the kernel reads the single
+        (B, D, L) plane for all directions; otherwise the per-direction planes are used as they are."""
+        x, dts, A, Bs, Cs, Ds, delta_bias, st = ctx.saved_tensors
+        H, W, dirs, D = ctx.meta
+        K = len(dirs)
+        Bn, L = x.shape[0], H * W
+        if K == 1 or dys.stride(1) == 0:
+            prob = ops.ScanProblem(x, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=D)
+            du, ddelta, dA, dB, dC, dD, dbias = prob.backward(dys[:, 0].float(), st)
+        else:
+            prob = ops.ScanProblem(x.repeat(1, K, 1), dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True,
+                                   hw=(H, W), dirs=dirs, u_mod=0)
+            du, ddelta, dA, dB, dC, dD, dbias = prob.backward(dys.reshape(Bn, K * D, L).float().contiguous(), st)
+        dx = du.view(Bn, K, D, L).sum(dim=1) if K > 1 else du.view_as(x)
+        return dx, ddelta, dA, dB, dC, dD, dbias, None, None, None
+
+
+class _OutGate(torch.autograd.Function):
+    """merge over K + transpose + LayerNorm(D) + SiLU(z) gate (ops.out_gate_fwd/bwd)."""
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, ys, ln_w, ln_b, z, z_act, eps, out_dtype):
+        out, stats = ops.out_gate_fwd(ys, ln_w, ln_b, z, z_act, eps, out_dtype)
+        ctx.z_act = z_act
+        ctx.has_z = z is not None
+        ctx.save_for_backward(ys, ln_w, ln_b, z, stats)
+        return out
+
+    @staticmethod
+    @_custom_bwd
+    def backward(ctx, dout):
+        ys, ln_w, ln_b, z, stats = ctx.saved_tensors
+        dz = torch.empty(z.shape, dtype=z.dtype, device=z.device) if ctx.has_z else None
+        dy, dw, db = ops.out_gate_bwd(ys, ln_w, ln_b, z, ctx.z_act, dout, stats, dz)
+        # dy is the gradient of the merged y: hand it to the scan's backward as a shared (B, D, L) dout
+        K = ys.shape[1]
+        return (dy.unsqueeze(1).expand(-1, K, -1, -1), (dw if ln_w is not None else None),
+                (db if ln_b is not None else None), dz, None, None, None)

@@ -1,0 +1,183 @@
+"""nn.Module surface of the reference (boundary b3) on top of the fused B200 operators.
+
+  SS2D             <- /root/reference/gm-unet/model/gm/ss2d.py:521-556 (k_group=1, directions given per call) and
+                      model/vmamba/vmamba.py:992 with forward_type "v2"/"v2_no32" (k_group=4)
+  GroupMambaLayer  <- model/gm/groupmamba.py:85-159
+  mamba_init       <- model/gm/ss2d.py:154-209
+
+Parameter names, shapes, dtypes and the order in which the constructors draw random numbers are those of the
+reference, so `load_state_dict` works in both directions. The forward differs only in WHERE the work happens:
+cross-scan and cross-merge are addressing inside the scan kernels, out_norm + SiLU gate are one fused pass, and
+no permuted or transposed copy is materialised.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as Fn
+
+
+class mamba_init:
+    """Parameter initialisers (ss2d.py:154-209), same RNG consumption."""
+
+    @staticmethod
+    def dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4):
+        dt_proj = nn.Linear(dt_rank, d_inner, bias=True)
+        std = dt_rank ** -0.5 * dt_scale
+        if dt_init == "constant":
+            nn.init.constant_(dt_proj.weight, std)
+        elif dt_init == "random":
+            nn.init.uniform_(dt_proj.weight, -std, std)
+        else:
+            raise NotImplementedError
+        dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(min=dt_init_floor)
+        inv_dt = dt + torch.log(-torch.expm1(-dt))            # softplus^-1
+        with torch.no_grad():
+            dt_proj.bias.copy_(inv_dt)
+        return dt_proj
+
+    @staticmethod
+    def A_log_init(d_state, d_inner, copies=-1, device=None, merge=True):
+        A_log = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32, device=device)).repeat(d_inner, 1).contiguous()
+        if copies > 0:
+            A_log = A_log.unsqueeze(0).repeat(copies, 1, 1)
+            if merge:
+                A_log = A_log.flatten(0, 1)
+        A_log = nn.Parameter(A_log)
+        A_log._no_weight_decay = True
+        return A_log
+
+    @staticmethod
+    def D_init(d_inner, copies=-1, device=None, merge=True):
+        D = torch.ones(d_inner, device=device)
+        if copies > 0:
+            D = D.unsqueeze(0).repeat(copies, 1)
+            if merge:
+                D = D.flatten(0, 1)
+        D = nn.Parameter(D)
+        D._no_weight_decay = True
+        return D
+
+
+class SS2D(nn.Module, mamba_init):
+    """2D selective-scan block: in_proj -> dwconv3x3 -> SiLU -> [K-direction selective scan] -> out_norm ->
+    * SiLU(z) -> out_proj.  forward(x: (B, H, W, C), CrossScan=None, CrossMerge=None) -> (B, H, W, C).
+
+    k_group=1 reproduces model/gm/ss2d.py (the direction comes from the (CrossScan_k, CrossMerge_k) classes passed
+    to forward, as GroupMambaLayer does); k_group=4 reproduces the VMamba SS2D "v2" (four directions, no arguments).
+    """
+
+    def __init__(self, d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU, d_conv=3,
+                 conv_bias=True, dropout=0.0, bias=False, dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0,
+                 dt_init_floor=1e-4, initialize="v0", forward_type="v2", channel_first=False, k_group=1, **kwargs):
+        super().__init__()
+        if channel_first:
+            raise NotImplementedError("channel_first=True is not used by GM-UNet")
+        if act_layer is not nn.SiLU:
+            raise NotImplementedError("only SiLU is fused")
+        if forward_type not in ("v2", "v2_no32"):
+            raise NotImplementedError(f"forward_type {forward_type!r}: only 'v2' and 'v2_no32' are on the hot path")
+        if initialize != "v0":
+            raise NotImplementedError("only initialize='v0'")
+        d_inner = int(ssm_ratio * d_model)
+        dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.d_model, self.d_inner, self.d_state, self.dt_rank, self.k_group = d_model, d_inner, d_state, dt_rank, k_group
+        self.disable_force32 = forward_type.endswith("_no32")
+        self.with_dconv = d_conv > 1
+        self.channel_first = False
+        # construction order = reference (ss2d.py:266-335): out_norm, in_proj, conv2d, x_proj, out_proj, dt_projs, A, D
+        self.out_norm = nn.LayerNorm(d_inner)
+        self.in_proj = nn.Linear(d_model, d_inner * 2, bias=bias)
+        self.act = act_layer()
+        if self.with_dconv:
+            self.conv2d = nn.Conv2d(d_inner, d_inner, groups=d_inner, bias=conv_bias, kernel_size=d_conv,
+                                    padding=(d_conv - 1) // 2)
+        x_proj = [nn.Linear(d_inner, dt_rank + d_state * 2, bias=False) for _ in range(k_group)]
+        self.x_proj_weight = nn.Parameter(torch.stack([t.weight for t in x_proj], dim=0))          # (K, R+2N, D)
+        self.out_proj = nn.Linear(d_inner, d_model, bias=bias)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else nn.Identity()
+        dt_projs = [self.dt_init(dt_rank, d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor) for _ in range(k_group)]
+        self.dt_projs_weight = nn.Parameter(torch.stack([t.weight for t in dt_projs], dim=0))      # (K, D, R)
+        self.dt_projs_bias = nn.Parameter(torch.stack([t.bias for t in dt_projs], dim=0))          # (K, D)
+        self.A_logs = self.A_log_init(d_state, d_inner, copies=k_group, merge=True)                # (K*D, N)
+        self.Ds = self.D_init(d_inner, copies=k_group, merge=True)                                 # (K*D)
+
+    # -- forward_corev2 (ss2d.py:349-500) as ONE fused pipeline ------------------------------------
+    def forward_core(self, x: torch.Tensor, z, dirs):
+        """x: (B, D, H, W) activated conv output; z: (B, H, W, D) raw gate view or None -> (B, H, W, D)."""
+        Bn, D, H, W = x.shape
+        K, _, R = self.dt_projs_weight.shape
+        N = self.A_logs.shape[1]
+        L = H * W
+        assert K == len(dirs), "one direction per k_group"
+        xf = x.reshape(Bn, D, L)
+        # pointwise projections evaluated in natural pixel order (identical values to projecting the permuted xs)
+        x_dbl = torch.matmul(self.x_proj_weight.reshape(K * (R + 2 * N), D).to(xf.dtype), xf).view(Bn, K, R + 2 * N, L)
+        dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = torch.matmul(self.dt_projs_weight.to(dts_r.dtype).unsqueeze(0), dts_r).reshape(Bn, K * D, L)
+        As = -torch.exp(self.A_logs.float())
+        Ds = self.Ds.float()
+        bias = self.dt_projs_bias.reshape(-1).float()
+        if not self.disable_force32:
+            xf, dts, Bs, Cs = xf.float(), dts.float(), Bs.float(), Cs.float()
+        else:
+            dts, Bs, Cs = dts.to(xf.dtype), Bs.to(xf.dtype), Cs.to(xf.dtype)
+        ys = Fn._SS2DScanNatural.apply(xf, dts, As, Bs, Cs, Ds, bias, H, W, tuple(dirs))       # (B, K, D, L) fp32
+        zz = z.reshape(Bn, L, D) if z is not None else None
+        y = Fn._OutGate.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, True,
+                              self.out_norm.eps, x.dtype)
+        return y.view(Bn, H, W, D)
+
+    def forward(self, x: torch.Tensor, CrossScan=None, CrossMerge=None, **kwargs):
+        if CrossScan is None and CrossMerge is None:
+            dirs = (1, 2, 3, 4) if self.k_group == 4 else tuple(range(1, self.k_group + 1))
+        else:
+            dirs = Fn.directions_of(CrossScan, CrossMerge)
+            if dirs is None:
+                raise NotImplementedError("SS2D.forward needs a matching (CrossScan*, CrossMerge*) pair")
+        xz = self.in_proj(x)                                      # ss2d.py:504
+        xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
+        xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
+        if self.with_dconv:
+            xi = self.conv2d(xi)                                  # :512
+        xi = self.act(xi)                                         # :513
+        y = self.forward_core(xi, z, dirs)                        # :514-517 (scan, merge, out_norm, gate)
+        return self.dropout(self.out_proj(y))                     # :518
+
+
+class GroupMambaLayer(nn.Module):
+    """Four single-direction SS2Ds on channel quarters + channel-affinity gating (groupmamba.py:85-159)."""
+
+    def __init__(self, input_dim, output_dim, d_state=1, d_conv=3, expand=1, reduction=16):
+        super().__init__()
+        reduced = input_dim // reduction
+        self.fc1 = nn.Linear(input_dim, reduced, bias=True)
+        self.fc2 = nn.Linear(reduced, output_dim, bias=True)
+        self.relu = nn.ReLU()
+        self.sigmoid = nn.Sigmoid()
+        self.input_dim, self.output_dim = input_dim, output_dim
+        self.norm = nn.LayerNorm(input_dim)
+        for i in range(1, 5):
+            setattr(self, f"mamba_g{i}", SS2D(d_model=input_dim // 4, d_state=d_state, ssm_ratio=expand, d_conv=d_conv))
+        self.proj = nn.Linear(input_dim, output_dim)
+        self.skip_scale = nn.Parameter(torch.ones(1))
+
+    def forward(self, x, H, W):
+        if x.dtype == torch.float16:
+            x = x.type(torch.float32)
+        Bn, L, C = x.shape
+        x = self.norm(x)                                                        # :131
+        aff = self.sigmoid(self.fc2(self.relu(self.fc1(x.mean(dim=1)))))        # :134-137 channel affinity
+        x4 = x.view(Bn, H, W, C)
+        parts = torch.chunk(x4, 4, dim=-1)
+        pairs = ((Fn.CrossScan_1, Fn.CrossMerge_1), (Fn.CrossScan_2, Fn.CrossMerge_2),
+                 (Fn.CrossScan_3, Fn.CrossMerge_3), (Fn.CrossScan_4, Fn.CrossMerge_4))
+        outs = [getattr(self, f"mamba_g{i + 1}")(parts[i], CrossScan=pairs[i][0], CrossMerge=pairs[i][1]) for i in range(4)]
+        xm = torch.cat(outs, dim=-1) * self.skip_scale * x4                     # :149
+        xm = xm.view(Bn, L, C) * aff.unsqueeze(1)                               # :154
+        xm = self.norm(xm)                                                      # :156 (same LayerNorm, shared weights)
+        return self.proj(xm)                                                    # :157

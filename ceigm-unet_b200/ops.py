@@ -1,0 +1,257 @@
+"""Tensor-level wrappers over the C ABI: build a `ss2d_scan_desc` from torch tensors, allocate outputs with
+torch on the current device/stream (exactly what the reference's host code does with ATen,
+kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:217-233) and call libss2d_b200.so.
+
+Error behaviour mirrors the reference's TORCH_CHECKs (selective_scan.cpp:165-215, 251-305): wrong dtype,
+device, stride or shape raises RuntimeError before anything is launched.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.SS2D_F32, torch.float16: _lib.SS2D_F16, torch.bfloat16: _lib.SS2D_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _round4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+class ScanProblem:
+    """Validated view of one selective-scan call.
+
+    SCAN layout (reference extension API): u, delta (B, Dt, L); B, C (B, G, N, L) or (B, N, L).
+    NATURAL layout (fused cross-scan/merge): pass hw=(H, W) and dirs (one direction 1..4 per group); u is
+    (B, Dt | D, H*W) flattened images, u_mod=D shares one input across the K groups.
+    """
+
+    def __init__(self, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, *, out_float=False,
+                 hw: Optional[Tuple[int, int]] = None, dirs: Optional[Sequence[int]] = None, u_mod: int = 0):
+        _require(u.dtype in _DT, "u must be float32, float16 or bfloat16")                     # cpp:167
+        _require(A.dtype == torch.float32, "A must be float32")                                 # cpp:168
+        _require(delta.dtype == u.dtype and B.dtype == u.dtype and C.dtype == u.dtype,
+                 "delta, B and C must have the dtype of u")                                     # cpp:170-172
+        for name, t in (("u", u), ("delta", delta), ("A", A), ("B", B), ("C", C)):
+            _require(t.is_cuda, f"Expected {name}.is_cuda() to be true")                        # cpp:174-178
+        _require(u.dim() == 3 and delta.dim() == 3, "u and delta must be (batch, dim, seqlen)")
+        _require(u.stride(-1) == 1 or u.size(-1) == 1, "u must be contiguous in its last dimension")          # cpp:180
+        _require(delta.stride(-1) == 1 or delta.size(-1) == 1, "delta must be contiguous in its last dimension")
+        self.squeeze_BC = B.dim() == 3
+        if self.squeeze_BC:
+            B, C = B.unsqueeze(1), C.unsqueeze(1)
+        batch, dim, L = delta.shape
+        N, G = A.shape[1], B.shape[1]
+        _require(dim % G == 0, "dims should be dividable by n_groups")                          # cpp:190
+        _require(N <= _lib.MAX_DSTATE, "selective_scan only supports state dimension <= 256")   # cpp:191
+        _require(tuple(A.shape) == (dim, N) and A.is_contiguous(), "A must be a contiguous (dim, dstate) tensor")
+        _require(tuple(B.shape) == (batch, G, N, L), "B must be (batch, n_groups, dstate, seqlen)")           # cpp:196
+        _require(tuple(C.shape) == (batch, G, N, L), "C must be (batch, n_groups, dstate, seqlen)")           # cpp:198
+        _require(B.stride(-1) == 1 or B.size(-1) == 1, "B must be contiguous in its last dimension")          # cpp:197
+        _require(C.stride(-1) == 1 or C.size(-1) == 1, "C must be contiguous in its last dimension")          # cpp:199
+        if u_mod:
+            _require(tuple(u.shape) == (batch, u_mod, L) and dim % u_mod == 0, "u must be (batch, u_mod, seqlen)")
+        else:
+            _require(tuple(u.shape) == (batch, dim, L), "u must be (batch, dim, seqlen)")       # cpp:193
+        for name, t in (("D", D), ("delta_bias", delta_bias)):
+            if t is not None:
+                _require(t.dtype == torch.float32, f"{name} must be float32")                   # cpp:203, 211
+                _require(t.is_cuda, f"Expected {name}.is_cuda() to be true")
+                _require(tuple(t.shape) == (dim,) and t.is_contiguous(), f"{name} must be a contiguous (dim,) tensor")
+        self.u, self.delta, self.A, self.B, self.C, self.D, self.bias = u, delta, A, B, C, D, delta_bias
+        self.batch, self.dim, self.L, self.N, self.G = batch, dim, L, N, G
+        self.out_dtype = torch.float32 if out_float else u.dtype
+        self.softplus = bool(delta_softplus)
+        self.hw, self.dirs, self.u_mod = hw, dirs, int(u_mod)
+        d = _lib.ScanDesc()
+        d.batch, d.dim, d.seqlen, d.dstate, d.n_groups = batch, dim, L, N, G
+        d.io_dtype, d.out_dtype, d.delta_softplus = _DT[u.dtype], _DT[self.out_dtype], int(self.softplus)
+        if hw is not None:
+            _require(dirs is not None and len(dirs) == G and G <= _lib.MAX_GROUP_DIRS, "one direction per group needed")
+            _require(hw[0] * hw[1] == L, "H * W must equal seqlen")
+            d.layout, d.H, d.W = _lib.LAYOUT_NATURAL, hw[0], hw[1]
+            for i, k in enumerate(dirs):
+                d.dirs[i] = int(k)
+        else:
+            d.layout = _lib.LAYOUT_SCAN
+        d.u_batch_stride, d.u_dim_stride = u.stride(0), u.stride(1)
+        d.delta_batch_stride, d.delta_dim_stride = delta.stride(0), delta.stride(1)
+        d.B_batch_stride, d.B_group_stride, d.B_state_stride = B.stride(0), B.stride(1), B.stride(2)
+        d.C_batch_stride, d.C_group_stride, d.C_state_stride = C.stride(0), C.stride(1), C.stride(2)
+        d.u_dim_modulo = self.u_mod
+        self.desc = d
+        self.ckpt_floats = int(_lib.lib().ss2d_scan_ckpt_floats(ctypes.byref(d)))
+
+    # ---- forward ----
+    def forward(self, want_state: bool = True):
+        """-> (out (B, Dt, L), x). `x` has the reference's shape convention (B, Dt, 1, 2N): x[:, :, -1, 1::2] is the
+        final state; the chunk checkpoints for the backward live in front of it in the same storage."""
+        d, dev = self.desc, self.delta.device
+        out = torch.empty((self.batch, self.dim, self.L), dtype=self.out_dtype, device=dev)
+        d.out_batch_stride, d.out_dim_stride = out.stride(0), out.stride(1)
+        x = ckpt = last = None
+        if want_state:
+            head = _round4(self.ckpt_floats)
+            buf = torch.empty(head + self.batch * self.dim * 2 * self.N, dtype=torch.float32, device=dev)
+            ckpt = buf
+            x = buf[head:].view(self.batch, self.dim, 1, 2 * self.N)
+            last = x
+            d.last_state_interleaved = 1
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ss2d_scan_fwd(ctypes.byref(d), _ptr(self.u), _ptr(self.delta), _ptr(self.A), _ptr(self.B),
+                                          _ptr(self.C), _ptr(self.D), _ptr(self.bias), _ptr(out), _ptr(ckpt),
+                                          _ptr(last), _stream(dev))
+        _lib.check(rc, "ss2d_scan_fwd")
+        return out, x
+
+    def _ckpt_from_x(self, x: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Recover the checkpoint buffer that `forward` placed in front of `x` (None if x is foreign)."""
+        if x is None or x.dtype != torch.float32 or not x.is_cuda:
+            return None
+        head = _round4(self.ckpt_floats)
+        total = head + self.batch * self.dim * 2 * self.N
+        if x.storage_offset() != head or x.untyped_storage().nbytes() != total * 4 or not x.is_contiguous():
+            return None
+        return torch.empty(0, dtype=torch.float32, device=x.device).set_(x.untyped_storage(), 0, (head,), (1,))
+
+    # ---- backward ----
+    def backward(self, dout, x=None):
+        """-> [du, ddelta, dA, dB, dC, dD, ddelta_bias] with the reference's dtypes (selective_scan.cpp:319-347):
+        du/ddelta in u's dtype, dA/dD/ddelta_bias fp32, dB/dC accumulated in fp32 then cast to B's dtype."""
+        d, dev = self.desc, self.delta.device
+        dch = self.u_mod if self.u_mod else self.dim
+        _require(dout.is_cuda and dout.dtype == self.out_dtype, "dout must be a CUDA tensor of out's dtype")
+        _require(tuple(dout.shape) == (self.batch, dch, self.L), "dout must be (batch, dim, seqlen)")
+        if dout.stride(-1) != 1:                                  # csms6s.py:360-361 does the same before calling bwd
+            dout = dout.contiguous()
+        d.out_batch_stride, d.out_dim_stride = dout.stride(0), dout.stride(1)
+        # du / ddelta are written with u's / delta's strides: normalise strided views to dense tensors first
+        u, delta = self.u, self.delta
+        if not u.is_contiguous():
+            u = u.contiguous()
+            d.u_batch_stride, d.u_dim_stride = u.stride(0), u.stride(1)
+        if not delta.is_contiguous():
+            delta = delta.contiguous()
+            d.delta_batch_stride, d.delta_dim_stride = delta.stride(0), delta.stride(1)
+        du = torch.empty((self.batch, self.dim, self.L), dtype=u.dtype, device=dev) if self.u_mod else torch.empty_like(u)
+        ddelta = torch.empty_like(delta)
+        dA = torch.empty_like(self.A)
+        dB = torch.zeros((self.batch, self.G, self.N, self.L), dtype=torch.float32, device=dev)
+        dC = torch.zeros_like(dB)
+        dD = torch.empty_like(self.D) if self.D is not None else None
+        dbias = torch.empty_like(self.bias) if self.bias is not None else None
+        ckpt = self._ckpt_from_x(x)
+        L = _lib.lib()
+        ws_bytes = int(L.ss2d_scan_bwd_workspace_bytes(ctypes.byref(d), 1 if ckpt is not None else 0))
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.ss2d_scan_bwd(ctypes.byref(d), _ptr(u), _ptr(delta), _ptr(self.A), _ptr(self.B),
+                                 _ptr(self.C), _ptr(self.D), _ptr(self.bias), _ptr(dout), _ptr(ckpt), _ptr(du),
+                                 _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias), _ptr(ws),
+                                 ctypes.c_size_t(ws_bytes), _stream(dev))
+        _lib.check(rc, "ss2d_scan_bwd")
+        if self.B.dtype != torch.float32:
+            dB, dC = dB.to(self.B.dtype), dC.to(self.C.dtype)
+        if self.squeeze_BC:
+            dB, dC = dB[:, 0], dC[:, 0]
+        return [du, ddelta, dA, dB, dC, dD, dbias]
+
+
+# ---- stand-alone permutations ------------------------------------------------------------------
+def cross_scan(x: torch.Tensor, dirs: Sequence[int]) -> torch.Tensor:
+    """x (B, C, H, W) -> (B, K, C, H*W), plane k traversed in direction dirs[k] (csms6s.py:11-206)."""
+    _require(x.is_cuda and x.dtype in _DT and x.dim() == 4, "x must be a CUDA (B, C, H, W) float tensor")
+    x = x.contiguous()
+    Bn, Cn, H, W = x.shape
+    K = len(dirs)
+    out = torch.empty((Bn, K, Cn, H * W), dtype=x.dtype, device=x.device)
+    arr = (ctypes.c_int32 * K)(*[int(k) for k in dirs])
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_cross_scan(_ptr(x), _ptr(out), Bn, Cn, H, W, K, arr, _DT[x.dtype], _stream(x.device))
+    _lib.check(rc, "ss2d_cross_scan")
+    return out
+
+
+def cross_merge(ys: torch.Tensor, hw: Tuple[int, int], dirs: Sequence[int]) -> torch.Tensor:
+    """ys (B, K, C, L) in scan order -> (B, C, L) natural order, summed over K."""
+    _require(ys.is_cuda and ys.dtype in _DT and ys.dim() == 4, "ys must be a CUDA (B, K, C, L) float tensor")
+    ys = ys.contiguous()
+    Bn, K, Cn, L = ys.shape
+    H, W = hw
+    _require(H * W == L and K == len(dirs), "shape mismatch in cross_merge")
+    out = torch.empty((Bn, Cn, L), dtype=ys.dtype, device=ys.device)
+    arr = (ctypes.c_int32 * K)(*[int(k) for k in dirs])
+    with torch.cuda.device(ys.device):
+        rc = _lib.lib().ss2d_cross_merge(_ptr(ys), _ptr(out), Bn, Cn, H, W, K, arr, _DT[ys.dtype], _stream(ys.device))
+    _lib.check(rc, "ss2d_cross_merge")
+    return out
+
+
+# ---- fused epilogue ----------------------------------------------------------------------------
+def out_gate_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, out_dtype):
+    """ys (B, K, D, L) fp32 natural order; z (B, L, D) view with stride(-1)==1 or None -> out (B, L, D), mean_rstd."""
+    _require(ys.is_cuda and ys.dtype == torch.float32 and ys.is_contiguous(), "ys must be contiguous CUDA fp32")
+    Bn, K, D, L = ys.shape
+    out = torch.empty((Bn, L, D), dtype=out_dtype, device=ys.device)
+    stats = torch.empty((Bn, L, 2), dtype=torch.float32, device=ys.device)
+    zrs, zdt = 0, _lib.SS2D_F32
+    if z is not None:
+        _require(z.stride(-1) == 1 and z.shape[-1] == D and z.dtype in _DT, "z rows must be contiguous (.., D)")
+        zrs, zdt = _row_stride(z, Bn, L), _DT[z.dtype]
+    with torch.cuda.device(ys.device):
+        rc = _lib.lib().ss2d_out_gate_fwd(_ptr(ys), K, _ptr(ln_w), _ptr(ln_b), _ptr(z), zrs, int(z_act), _ptr(out),
+                                          _ptr(stats), Bn, D, L, ctypes.c_float(eps), zdt, _DT[out_dtype],
+                                          _stream(ys.device))
+    _lib.check(rc, "ss2d_out_gate_fwd")
+    return out, stats
+
+
+def _row_stride(z, Bn, L) -> int:
+    """Row stride of a (B, L, D) or (B, H, W, D) view whose rows are uniformly spaced in memory."""
+    flat = z.reshape(Bn * L, z.shape[-1]) if z.is_contiguous() else None
+    if flat is not None:
+        return z.shape[-1]
+    rs = z.stride(-2)
+    # uniform spacing check: every outer stride must be the product of inner extents times rs
+    exp = rs
+    for dim in range(z.dim() - 2, -1, -1):
+        _require(z.stride(dim) == exp, "z must be a uniformly strided view of (rows, D)")
+        exp *= z.shape[dim]
+    return rs
+
+
+def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[torch.Tensor]):
+    """-> dy (B, D, L) fp32, dln_w, dln_b. dz is written into `dz_out` (a (B, L, D) uniformly strided view)."""
+    Bn, K, D, L = ys.shape
+    dout = dout.contiguous()
+    dy = torch.empty((Bn, D, L), dtype=torch.float32, device=ys.device)
+    npart = int(_lib.lib().ss2d_out_gate_bwd_partials(Bn, L))
+    part = torch.empty((2, npart, D), dtype=torch.float32, device=ys.device)
+    zrs, zdt, dzrs = 0, _lib.SS2D_F32, 0
+    if z is not None:
+        zrs, zdt = _row_stride(z, Bn, L), _DT[z.dtype]
+        dzrs = _row_stride(dz_out, Bn, L)
+    with torch.cuda.device(ys.device):
+        rc = _lib.lib().ss2d_out_gate_bwd(_ptr(ys), K, _ptr(ln_w), _ptr(ln_b), _ptr(z), zrs, int(z_act), _ptr(dout),
+                                          _ptr(stats), _ptr(dy), _ptr(dz_out) if z is not None else None, dzrs,
+                                          _ptr(part[0]), _ptr(part[1]), npart, Bn, D, L, zdt, _DT[dout.dtype],
+                                          _stream(ys.device))
+    _lib.check(rc, "ss2d_out_gate_bwd")
+    sums = part.sum(dim=1)
+    return dy, sums[0], sums[1]

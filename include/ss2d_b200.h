@@ -1,0 +1,165 @@
+/* ss2d_b200.h — C ABI of the B200-native SS2D selective-scan library (libss2d_b200.so).
+ *
+ * This is the drop-in boundary for GM-UNet's 2D selective-scan hot path. Every entry point takes
+ * plain device pointers, sizes, element strides and a CUDA stream; nothing here depends on PyTorch.
+ * The library never allocates, never synchronises and keeps no global state: the caller owns all
+ * buffers (the reference's host code allocates its outputs with torch the same way,
+ * kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:217-220, 307-323).
+ *
+ * Reference interfaces replaced (paths under /root/reference/gm-unet/):
+ *   ss2d_scan_fwd        <- selective_scan_cuda_core.fwd / selective_scan_cuda_oflex.fwd
+ *                           kernels/selective_scan/csrc/selective_scan/cus/selective_scan.cpp:157-239
+ *                           kernels/selective_scan/csrc/selective_scan/cusoflex/selective_scan_oflex.cpp (out_float)
+ *   ss2d_scan_bwd        <- selective_scan_cuda_core.bwd / _oflex.bwd       cus/selective_scan.cpp:241-349
+ *   layout NATURAL + dirs <- CrossScan[_1.._4] / CrossMerge[_1.._4] folded into the scan's addressing
+ *                           model/gm/csms6s.py:11-206
+ *   ss2d_cross_scan / ss2d_cross_merge  <- the same classes as stand-alone permutation kernels (b2 API)
+ *   ss2d_out_gate_fwd/bwd <- out_norm LayerNorm + y*SiLU(z) gate   model/gm/ss2d.py:498, 515-517
+ *
+ * All functions return SS2D_OK (0) or a negative ss2d_status; ss2d_strerror() names it. Kernel
+ * launches are asynchronous on `stream`.
+ */
+#ifndef SS2D_B200_H_
+#define SS2D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ss2d_stream_t; /* cudaStream_t */
+
+typedef enum {
+  SS2D_OK = 0,
+  SS2D_ERR_NULL_POINTER = -1,   /* a required pointer is NULL */
+  SS2D_ERR_BAD_SHAPE = -2,      /* non-positive size, dim % n_groups != 0, H*W != seqlen ... */
+  SS2D_ERR_BAD_DTYPE = -3,      /* dtype enum out of range */
+  SS2D_ERR_DSTATE = -4,         /* dstate > SS2D_MAX_DSTATE (reference: MAX_DSTATE 256) */
+  SS2D_ERR_BAD_LAYOUT = -5,     /* layout / direction code invalid */
+  SS2D_ERR_WORKSPACE = -6,      /* workspace missing or too small */
+  SS2D_ERR_CUDA = -7,           /* a CUDA runtime call failed: see ss2d_last_cuda_error() */
+  SS2D_ERR_UNSUPPORTED = -8,    /* combination not implemented */
+  SS2D_ERR_ALIGNMENT = -9       /* a pointer is not aligned to its element size */
+} ss2d_status;
+
+typedef enum { SS2D_F32 = 0, SS2D_F16 = 1, SS2D_BF16 = 2 } ss2d_dtype;
+
+/* SCAN: tensors are already in scan order, (batch, dim, L) — the reference extension's layout.
+ * NATURAL: u/delta/out are (batch, dim, H, W) images and B/C are (batch, group, dstate, H, W); each
+ * group g is traversed in direction dirs[g] (1 row-major, 2 column-major, 3 reversed row-major,
+ * 4 reversed column-major — the CrossScan_1.._4 numbering). No permuted copy is materialised. */
+typedef enum { SS2D_LAYOUT_SCAN = 0, SS2D_LAYOUT_NATURAL = 1 } ss2d_layout;
+
+#define SS2D_MAX_DSTATE 256
+#define SS2D_MAX_GROUP_DIRS 8
+/* checkpoint interval of the chunked scan (elements of L between saved states) */
+#define SS2D_CHUNK 32
+
+/* Problem descriptor shared by forward and backward. Strides are in ELEMENTS; the innermost (L or W)
+ * stride is 1 for every tensor (the reference requires the same: selective_scan.cpp:180-181,197,199). */
+typedef struct ss2d_scan_desc {
+  int32_t batch;          /* B */
+  int32_t dim;            /* Dt = K * D channels (all groups) */
+  int32_t seqlen;         /* L = H * W */
+  int32_t dstate;         /* N */
+  int32_t n_groups;       /* G: B/C are shared by dim / n_groups consecutive channels */
+  int32_t io_dtype;       /* ss2d_dtype of u, delta, B, C, du, ddelta */
+  int32_t out_dtype;      /* ss2d_dtype of out and dout (== io_dtype for "core"; SS2D_F32 allowed for "oflex") */
+  int32_t delta_softplus; /* 1: delta = softplus(delta + delta_bias), threshold 20 */
+  int32_t layout;         /* ss2d_layout */
+  int32_t H, W;           /* NATURAL layout only (H * W == seqlen) */
+  int32_t dirs[SS2D_MAX_GROUP_DIRS]; /* NATURAL layout only: direction (1..4) of group g */
+  /* element strides */
+  int64_t u_batch_stride, u_dim_stride;         /* u_group wrap: see u_dim_modulo */
+  int64_t delta_batch_stride, delta_dim_stride;
+  int64_t out_batch_stride, out_dim_stride;
+  int64_t B_batch_stride, B_group_stride, B_state_stride;
+  int64_t C_batch_stride, C_group_stride, C_state_stride;
+  /* If > 0, channel d reads u at channel (d % u_dim_modulo): lets the K directions of one SS2D share a
+   * single (B, D, H, W) input instead of K copies (CrossScan's 4x duplication, csms6s.py:15-19).
+   * In the backward, dout is then ALSO shared: (batch, u_dim_modulo, L) with out's strides (every direction
+   * receives the merged gradient, csms6s.py:42-53), and du is a dense (batch, dim, L) tensor holding one
+   * gradient plane per direction (the caller sums the K planes: CrossScan.backward, csms6s.py:23-29). */
+  int32_t u_dim_modulo;
+  /* 1: last_state is (batch, dim, 2*dstate) with h in the ODD slots and 0 in the even ones — the layout of
+   * the last chunk row of the reference's `x` output (read as x[:, :, -1, 1::2]). */
+  int32_t last_state_interleaved;
+} ss2d_scan_desc;
+
+/* ---- forward -------------------------------------------------------------------------------
+ * out[b,d,l] = sum_n C[b,g,n,l] * h[l,n] + D[d] * u[b,d,l],  h[l,n] = exp(dt*A[d,n]) h[l-1,n] + dt*u*B[b,g,n,l]
+ * A: (dim, dstate) fp32 contiguous. Dvec, delta_bias: (dim) fp32 or NULL.
+ * ckpt: fp32 buffer of ss2d_scan_ckpt_floats(desc) elements, or NULL when no backward will follow.
+ *       It receives the state at the end of every SS2D_CHUNK-element chunk (the reference's `x`,
+ *       selective_scan.cpp:217-220, at a finer interval) in an internal channel-major order.
+ * last_state: (batch, dim, dstate) fp32 or NULL — h after the last element (reference: x[:, :, -1, 1::2]). */
+int ss2d_scan_fwd(const ss2d_scan_desc* desc, const void* u, const void* delta, const float* A,
+                  const void* Bmat, const void* Cmat, const float* Dvec, const float* delta_bias,
+                  void* out, float* ckpt, float* last_state, ss2d_stream_t stream);
+
+size_t ss2d_scan_ckpt_floats(const ss2d_scan_desc* desc);
+
+/* ---- backward ------------------------------------------------------------------------------
+ * dout has out's dtype/strides; du, ddelta have u's / delta's dtype and strides.
+ * dA (dim, dstate), dD (dim) or NULL, ddelta_bias (dim) or NULL: fp32, fully overwritten.
+ * dB, dC: fp32 (batch, group, dstate, L | H, W) contiguous accumulators that the caller has ZEROED
+ *         (the reference does the same: torch::zeros_like(B, fp32), selective_scan.cpp:322-323).
+ * ckpt: the buffer written by ss2d_scan_fwd for the same inputs, or NULL: the states are then
+ *       recomputed by an extra forward sweep into `workspace`.
+ * workspace: ss2d_scan_bwd_workspace_bytes(desc, ckpt != NULL) bytes, 16-byte aligned. */
+int ss2d_scan_bwd(const ss2d_scan_desc* desc, const void* u, const void* delta, const float* A,
+                  const void* Bmat, const void* Cmat, const float* Dvec, const float* delta_bias,
+                  const void* dout, const float* ckpt, void* du, void* ddelta, float* dA, float* dB,
+                  float* dC, float* dD, float* ddelta_bias, void* workspace, size_t workspace_bytes,
+                  ss2d_stream_t stream);
+
+size_t ss2d_scan_bwd_workspace_bytes(const ss2d_scan_desc* desc, int have_ckpt);
+
+/* ---- stand-alone cross-scan / cross-merge (exact permutations; model/gm/csms6s.py:11-206) ----
+ * cross_scan : x (batch, channels, H, W) -> xs (batch, K, channels, L), xs[:,k] in direction dirs[k].
+ * cross_merge: ys (batch, K, channels, L) in scan order -> y (batch, channels, L) natural order,
+ *              summed over k in the reference's association ((k0 + k2) + (k1 + k3)) when K == 4.
+ * With transpose_adjoint != 0 the same kernels compute the adjoints (backward of merge = scan,
+ * backward of scan = merge). */
+int ss2d_cross_scan(const void* x, void* xs, int32_t batch, int32_t channels, int32_t H, int32_t W,
+                    int32_t K, const int32_t* dirs, int32_t dtype, ss2d_stream_t stream);
+int ss2d_cross_merge(const void* ys, void* y, int32_t batch, int32_t channels, int32_t H, int32_t W,
+                     int32_t K, const int32_t* dirs, int32_t dtype, ss2d_stream_t stream);
+
+/* ---- fused epilogue: merge over K + (B,D,L)->(B,L,D) + LayerNorm(D) + SiLU gate ------------------
+ * Replaces CrossMerge + the transpose copy + out_norm + act(z) + `y * z` of model/gm/ss2d.py:486-498,
+ * 506-508, 515-517 with one pass over HBM.
+ * ys: (batch, K, D, L) fp32 per-direction scan outputs in NATURAL pixel order (what ss2d_scan_fwd writes
+ *     in NATURAL layout); the K planes are summed on the fly ((k0+k2)+(k1+k3) when K == 4).
+ * z:  gate rows, element (b, l, d) at z[(b*L + l) * z_row_stride + d] (a strided view of in_proj's output),
+ *     or NULL for no gate; z_act != 0 applies SiLU to z inside the kernel.
+ * out: (batch, L, D) channels-last. mean_rstd: (batch, L, 2) fp32 saved for the backward (may be NULL).
+ * ln_weight / ln_bias: (D) fp32 or NULL (no affine). D <= 1664 forward, <= 832 backward. */
+int ss2d_out_gate_fwd(const float* ys, int32_t K, const float* ln_weight, const float* ln_bias,
+                      const void* z, int64_t z_row_stride, int32_t z_act, void* out, float* mean_rstd,
+                      int32_t batch, int32_t D, int32_t L, float eps, int32_t z_dtype, int32_t out_dtype,
+                      ss2d_stream_t stream);
+/* dy: (batch, D, L) fp32 gradient of the MERGED y (every direction receives the same gradient: pass it to
+ *     ss2d_scan_bwd as a shared dout through u_dim_modulo). dz: gradient of the RAW z when z_act != 0, rows
+ *     strided by dz_row_stride, or NULL. dln_*_partial: (n_partials, D) fp32, n_partials =
+ *     ss2d_out_gate_bwd_partials(batch, L); the caller sums over the first axis. */
+int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const float* ln_bias,
+                      const void* z, int64_t z_row_stride, int32_t z_act, const void* dout,
+                      const float* mean_rstd, float* dy, void* dz, int64_t dz_row_stride,
+                      float* dln_weight_partial, float* dln_bias_partial, int32_t n_partials, int32_t batch,
+                      int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, ss2d_stream_t stream);
+int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+const char* ss2d_strerror(int status);
+const char* ss2d_last_cuda_error(void);   /* thread-local text of the last SS2D_ERR_CUDA */
+const char* ss2d_version(void);           /* "ss2d_b200 <semver> sm_100a" */
+/* number of this library's kernel launches issued by the calling thread since the last reset */
+int64_t ss2d_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SS2D_B200_H_ */
