@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the SS2D selective-scan hot path on B200 (contract: task statement ④).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward + one backward pass of the selective scan over one batch of synthetic input
+(the reference test's seeded recipe, kernels/selective_scan/test_selective_scan.py:406-441), called through
+the reference-facing drop-in API `selective_scan_cuda_core.fwd / .bwd`.
+
+Metric (BASELINE.json): selective-scan algorithmic HBM GB/s (fwd+bwd), whole job over all ranks.
+Algorithmic bytes (level 1): fwd s(3 B Dt L + 2 B K N L), bwd s(5 B Dt L + 4 B K N L).
+
+Workloads (`--workload`):
+  vm_d192 (default)  K=4 directions, d_state N=16, D=192 (Dt=768), L=56^2, batch 24, fp32 — the north-star
+                     SS2D regime on the stage-1 map of a 224^2 Synapse slice at the config-2 batch.
+  vm_d96 / vm_d384 / vm_d768_l112 ... other points of BASELINE config 4.
+  gm_live            the 104 single-direction N=1 scan calls of one GM-UNet forward+backward at batch 24.
+Multi-GPU: the batch is sharded, every rank runs an independent replica of the per-GPU workload (weak scaling,
+no data-path collective — SURVEY.md §8e); the timed region is bracketed by barrier + synchronize and the
+slowest rank's device time is used.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# name -> list of (count, batch, Dt, L, N, G) scan calls making up one step
+WORKLOADS = {
+    "vm_d96": [(1, 24, 384, 3136, 16, 4)],
+    "vm_d192": [(1, 24, 768, 3136, 16, 4)],
+    "vm_d384": [(1, 24, 1536, 3136, 16, 4)],
+    "vm_d192_l80": [(1, 24, 768, 6400, 16, 4)],
+    "vm_d192_l112": [(1, 24, 768, 12544, 16, 4)],
+    "vm_d768_l112": [(1, 24, 3072, 12544, 16, 4)],
+    # live GM-UNet census: per forward 20/24/48/12 calls on the four stages
+    "gm_live": [(20, 24, 16, 3136, 1, 1), (24, 24, 32, 784, 1, 1), (48, 24, 87, 196, 1, 1), (12, 24, 112, 49, 1, 1)],
+}
+DEFAULT_WORKLOAD = "vm_d192"
+
+
+def alg_bytes(calls, esize=4):
+    fwd = sum(c * esize * (3 * b * dt * L + 2 * b * g * n * L) for c, b, dt, L, n, g in calls)
+    bwd = sum(c * esize * (5 * b * dt * L + 4 * b * g * n * L) for c, b, dt, L, n, g in calls)
+    return fwd, bwd
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_inputs(calls, device):
+    """One input set per distinct shape (reused across the `count` repetitions of that shape)."""
+    sets = []
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    for count, b, dt, L, n, g in calls:
+        A = (-0.5 * torch.rand(dt, n, generator=gen)).float()
+        inp = dict(A=A, B=torch.randn(b, g, n, L, generator=gen), C=torch.randn(b, g, n, L, generator=gen),
+                   D=torch.randn(dt, generator=gen), delta_bias=0.5 * torch.rand(dt, generator=gen),
+                   u=torch.randn(b, dt, L, generator=gen), delta=0.5 * torch.rand(b, dt, L, generator=gen),
+                   dout=torch.randn(b, dt, L, generator=gen))
+        sets.append((count, inp))
+    return sets
+
+
+def run_ours(args, rank, world, local_rank):
+    import ceigm_unet_b200 as pkg
+    from ceigm_unet_b200.dropin import selective_scan_cuda_core as core
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    calls = WORKLOADS[args.workload]
+    fwd_b, bwd_b = alg_bytes(calls)
+    host_sets = build_inputs(calls, device)
+    dev_sets = [(c, {k: v.to(device) for k, v in inp.items()}) for c, inp in host_sets]
+    resident = sum(v.numel() * 4 for _, inp in dev_sets for v in inp.values())
+
+    def step(record=None):
+        for count, t in dev_sets:
+            for _ in range(count):
+                if record is not None:
+                    record[0].record()
+                out, x = core.fwd(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], t["delta_bias"], True, 1)
+                if record is not None:
+                    record[1].record()
+                core.bwd(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], t["delta_bias"], t["dout"], x, True, 1)
+                if record is not None:
+                    record[2].record()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- timed region: K steps, device time via CUDA events on the launching (current) stream ----
+    single_call = len(calls) == 1 and calls[0][0] == 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)] if single_call else None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    pkg.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(evs[i] if evs else None)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = pkg.launch_count()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9
+
+    peak, peak_src = load_peaks()
+    roofline = None
+    extra = {}
+    if evs:
+        fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+        bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+        ach = bwd_b / (bwd_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "scan_bwd_kernel (+ finalize and dB/dC memsets inside the bwd call)",
+                    "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                    "traffic": None, "peak_source": peak_src,
+                    "note": "d_state=16 is MUFU.EX2/FMA-bound on B200, not HBM-bound: see DESIGN.md"}
+        extra = {"fwd_ms": round(fwd_ms, 4), "bwd_ms": round(bwd_ms, 4),
+                 "fwd_GBps": round(fwd_b / (fwd_ms * 1e-3) / 1e9, 1), "bwd_GBps": round(ach, 1),
+                 "fwd_frac_of_peak": round(fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, 4)}
+
+    # ---- end to end: host buffers in pinned memory, H2D of every input and D2H of every result, each step ----
+    pinned = [(c, {k: v.pin_memory() for k, v in inp.items()}) for c, inp in host_sets]
+    h2d = sum(c * sum(v.numel() * 4 for v in inp.values()) for c, inp in pinned)
+    res_host = {}
+
+    def e2e_step():
+        d2h = 0
+        for ci, (count, inp) in enumerate(pinned):
+            for _ in range(count):
+                t_ = {k: v.to(device, non_blocking=True) for k, v in inp.items()}
+                out, x = core.fwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"], True, 1)
+                grads = core.bwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"], t_["dout"],
+                                 x, True, 1)
+                outs = [out] + list(grads)
+                if ci not in res_host:
+                    res_host[ci] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                for hbuf, o in zip(res_host[ci], outs):
+                    hbuf.copy_(o, non_blocking=True)
+                    d2h += o.numel() * o.element_size()
+        torch.cuda.synchronize(device)
+        return d2h
+
+    d2h = e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(dt_e2e, op=torch.distributed.ReduceOp.MAX)
+    e2e_val = world * (fwd_b + bwd_b) * e2e_steps / float(dt_e2e.item()) / 1e9
+
+    line = {
+        "metric": "selective-scan fwd+bwd algorithmic HBM GB/s", "value": round(value, 1), "unit": "GB/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "calls_per_step": [list(c) for c in calls],
+                   "call_fields": ["count", "batch", "Dt=K*D", "L", "d_state", "groups"],
+                   "api": "selective_scan_cuda_core.fwd/bwd drop-in -> C ABI ss2d_scan_fwd/bwd",
+                   "l2_policy": "inputs larger than L2 (resident working set %.0f MB vs 126 MB L2)" % (resident / 1e6),
+                   "alg_bytes_fwd": fwd_b, "alg_bytes_bwd": bwd_b, "per_gpu_batch": calls[0][1]},
+        "frac_of_hbm_peak": round(value / world / peak, 4),
+        "e2e": {"value": round(e2e_val, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "note": "pinned host buffers; every input copied in and every result copied out per step"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+    line.update(extra)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_port(args.workload)
+    return line
+
+
+def cpu_baseline_port(workload, sample_batch=4):
+    """The C oracle (oracle/scan_oracle.c, OpenMP, f64 accumulate) on a bounded sample of the same workload."""
+    from oracle import c_oracle
+    calls = WORKLOADS[workload]
+    count, b, dt, L, n, g = max(calls, key=lambda c: c[0] * c[1] * c[2] * c[3] * c[4])
+    sb = min(sample_batch, b)
+    gen = torch.Generator().manual_seed(0)
+    A = (-0.5 * torch.rand(dt, n, generator=gen)).numpy()
+    Bm, Cm = torch.randn(sb, g, n, L, generator=gen).numpy(), torch.randn(sb, g, n, L, generator=gen).numpy()
+    Dv, bias = torch.randn(dt, generator=gen).numpy(), (0.5 * torch.rand(dt, generator=gen)).numpy()
+    u, dl = torch.randn(sb, dt, L, generator=gen).numpy(), (0.5 * torch.rand(sb, dt, L, generator=gen)).numpy()
+    dy = torch.randn(sb, dt, L, generator=gen).numpy()
+    c_oracle.scan_fwd(u[:1], dl[:1], A, Bm[:1], Cm[:1], Dv, bias, True)          # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    c_oracle.scan_fwd(u, dl, A, Bm, Cm, Dv, bias, True, acc="f64")
+    c_oracle.scan_bwd(u, dl, A, Bm, Cm, Dv, bias, dy, True, acc="f64")
+    dt_s = time.perf_counter() - t0
+    fwd_b, bwd_b = alg_bytes([(1, sb, dt, L, n, g)])
+    return {"value": round((fwd_b + bwd_b) / dt_s / 1e9, 4), "unit": "GB/s", "cores": c_oracle.num_threads(),
+            "kind": "port", "seconds": round(dt_s, 2),
+            "sample": f"C oracle (OpenMP) fwd+bwd on batch {sb} of {b} of the largest call of '{workload}' "
+                      f"(Dt={dt}, L={L}, N={n}, G={g})"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU path for the scan — its pure-PyTorch `selective_scan_ref`
+    (kernels/selective_scan/test_selective_scan.py:168-234) forward + autograd backward, restated in
+    oracle/selective_scan_ref.py (the reference tree does not travel to the GPU box). Bounded sample per step."""
+    from oracle.selective_scan_ref import selective_scan_ref
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    calls = WORKLOADS[args.workload]
+    count, b, dt, L, n, g = max(calls, key=lambda c: c[0] * c[1] * c[2] * c[3] * c[4])
+    dpg = dt // g
+
+    def make(rows):
+        gen = torch.Generator().manual_seed(0)
+        t = dict(u=torch.randn(1, rows, L, generator=gen), delta=0.5 * torch.rand(1, rows, L, generator=gen),
+                 A=-0.5 * torch.rand(rows, n, generator=gen), B=torch.randn(1, 1, n, L, generator=gen),
+                 C=torch.randn(1, 1, n, L, generator=gen), D=torch.randn(rows, generator=gen),
+                 delta_bias=0.5 * torch.rand(rows, generator=gen))
+        for v in t.values():
+            v.requires_grad_(True)
+        t["dout"] = torch.randn(1, rows, L, generator=gen)
+        return t
+
+    def one(t):
+        for k, v in t.items():
+            if k != "dout":
+                v.grad = None
+        out = selective_scan_ref(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], None, t["delta_bias"], True)
+        out.backward(t["dout"])
+
+    # calibrate on 2 rows, then size the sample so that (steps + warmup) steps take about two minutes
+    probe = make(2)
+    t0 = time.perf_counter(); one(probe); per_row = (time.perf_counter() - t0) / 2
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    rows = int(max(1, min(dpg, budget / max(per_row, 1e-6))))
+    t = make(rows)
+    for _ in range(args.warmup):
+        one(t)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one(t)
+    sec = (time.perf_counter() - t0) / args.steps
+    fwd_b, bwd_b = alg_bytes([(1, 1, rows, L, n, 1)])
+    val = (fwd_b + bwd_b) / sec / 1e9
+    sample = (f"selective_scan_ref fwd + autograd bwd on {rows} of the {b * dt} (batch x channel) rows of '{args.workload}' "
+              f"(1 batch, 1 group, L={L}, N={n}) per step")
+    return {
+        "impl": "reference", "metric": "selective-scan fwd+bwd algorithmic HBM GB/s", "value": round(val, 6),
+        "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "calls_per_step": [list(c) for c in calls], "sample_rows": rows},
+        "cpu_baseline": {"value": round(val, 6), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 6), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args)), flush=True)
+        return 0
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        line = run_ours(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

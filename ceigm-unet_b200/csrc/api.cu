@@ -77,6 +77,17 @@ static void pack(const ss2d_scan_desc* d, ScanParams& p) {
   p.C_bs = d->C_batch_stride; p.C_gs = d->C_group_stride; p.C_ns = d->C_state_stride;
 }
 
+// TMA bulk copies need 16-byte aligned fp32 rows: every stride a multiple of 4 elements, bases 16-byte aligned
+static bool tma_eligible(const ss2d_scan_desc* d, const void* u, const void* delta, const void* B, const void* C,
+                         const void* extra) {
+  if (d->io_dtype != SS2D_F32 || (d->seqlen & 3)) return false;
+  const int64_t strides[] = {d->u_batch_stride, d->u_dim_stride, d->delta_batch_stride, d->delta_dim_stride,
+                             d->B_batch_stride, d->B_group_stride, d->B_state_stride,
+                             d->C_batch_stride, d->C_group_stride, d->C_state_stride};
+  for (int64_t s : strides) if (s & 3) return false;
+  return aligned(u, 16) && aligned(delta, 16) && aligned(B, 16) && aligned(C, 16) && (!extra || aligned(extra, 16));
+}
+
 // states are processed in passes of <= 32; pass i covers [32 i, 32 i + n_i)
 static int n_passes(int N) { return (N + kStatesPerPass - 1) / kStatesPerPass; }
 static size_t ckpt_floats_pass(const ss2d_scan_desc* d, int n) {
@@ -123,6 +134,7 @@ int ss2d_scan_fwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
   ScanParams p;
   pack(d, p);
   p.u = u; p.delta = delta; p.Dv = Dvec; p.bias = delta_bias; p.out = out; p.last_state = last_state;
+  p.tma_ok = tma_eligible(d, u, delta, Bmat, Cmat, nullptr);
   size_t ck_off = 0;
   for (int i = 0; i < n_passes(d->dstate); ++i) {
     const int n0 = i * kStatesPerPass;

@@ -32,26 +32,30 @@ struct BwdShape {
 // Reduce-scatter of CNT per-lane values over LANES lanes spaced STRIDE apart (lane bits consumed MSB first).
 // If CNT >= LANES each lane ends with CNT/LANES totals (slice index = its lane id among LANES); otherwise the
 // value index is given by the top log2(CNT) lane bits and the remaining lanes hold replicas.
-template <int LANES, int STRIDE, int CNT>
-__device__ __forceinline__ void lane_reduce_scatter(float* v, int lane_id) {
-  int cnt = CNT;
+template <int STRIDE, int CNT, int S>
+struct LaneReduceScatter {
+  static __device__ __forceinline__ void run(float* v, int lane_id) {
+    if constexpr (S >= 1) {
+      if constexpr (CNT > 1) {
+        constexpr int HALF = CNT / 2;
+        const bool up = (lane_id & S) != 0;
 #pragma unroll
-  for (int s = LANES / 2; s >= 1; s >>= 1) {
-    if (cnt > 1) {
-      const int half = cnt / 2;
-      const bool up = (lane_id & s) != 0;
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        const float lo = v[i], hi = v[i + half];
-        const float send = up ? lo : hi;
-        const float keep = up ? hi : lo;
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s * STRIDE);
+        for (int i = 0; i < HALF; ++i) {
+          const float send = up ? v[i] : v[i + HALF];
+          const float keep = up ? v[i + HALF] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, S * STRIDE);
+        }
+        LaneReduceScatter<STRIDE, HALF, S / 2>::run(v, lane_id);
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], S * STRIDE);
+        LaneReduceScatter<STRIDE, 1, S / 2>::run(v, lane_id);
       }
-      cnt = half;
-    } else {
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], s * STRIDE);
     }
   }
+};
+template <int LANES, int STRIDE, int CNT>
+__device__ __forceinline__ void lane_reduce_scatter(float* v, int lane_id) {
+  LaneReduceScatter<STRIDE, CNT, LANES / 2>::run(v, lane_id);
 }
 
 template <int NS>

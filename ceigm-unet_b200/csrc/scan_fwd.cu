@@ -22,21 +22,27 @@ struct FwdShape {
   static constexpr int RPW = RL * RPT;       // rows per warp
   static constexpr int CH = 4 * RPW;         // rows per CTA
   static constexpr int NP = NS * R;          // padded states
-  static constexpr size_t smem_bytes = (size_t)(3 * CH + 2 * NP) * kFwdLTP * 4 + 2 * CH * 4;
+  static constexpr int stage_floats = (2 * CH + 2 * NP) * kFwdLTP;     // delta, u, B, C tiles of one pipeline stage
+  static constexpr size_t smem_bytes = (size_t)(2 * stage_floats + CH * kFwdLTP + 2 * CH) * 4 + 16;
 };
 
+// Tile pipeline: two shared-memory stages. When the operands are fp32 rows that are contiguous along the scan
+// (SCAN layout or direction 1) and 16-byte aligned, warp 0 fetches tile t+1 with TMA bulk copies (UBLKCP, one per
+// row, completing on the stage's mbarrier) while all four warps compute tile t. Any other case (16-bit dtypes,
+// transposed or reversed traversal, ragged tails) goes through the synchronous, index-mapped stage_rows().
 template <int NS, int R, int RPT>
 __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) {
   using S = FwdShape<NS, R, RPT>;
   constexpr int LT = kFwdLT, LTP = kFwdLTP, CH = S::CH, NP = S::NP, RL = S::RL;
   extern __shared__ __align__(16) float smem[];
-  float* s_dl = smem;                 // delta (raw, then activated)   [CH][LTP]
-  float* s_u = s_dl + CH * LTP;       // u                              [CH][LTP]
-  float* s_du = s_u + CH * LTP;       // delta * u                      [CH][LTP]
-  float* s_B = s_du + CH * LTP;       // [NP][LTP]
-  float* s_C = s_B + NP * LTP;        // [NP][LTP]
-  float* s_bias = s_C + NP * LTP;     // [CH]
-  float* s_D = s_bias + CH;           // [CH]
+  float* s_du = smem + 2 * S::stage_floats;   // delta * u                      [CH][LTP]
+  float* s_bias = s_du + CH * LTP;            // [CH]
+  float* s_D = s_bias + CH;                   // [CH]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_D + CH);   // [2]
+  auto st_dl = [&](int s) { return smem + s * S::stage_floats; };              // delta (raw, then activated) [CH][LTP]
+  auto st_u = [&](int s) { return smem + s * S::stage_floats + CH * LTP; };    // u                            [CH][LTP]
+  auto st_B = [&](int s) { return smem + s * S::stage_floats + 2 * CH * LTP; };            // [NP][LTP]
+  auto st_C = [&](int s) { return smem + s * S::stage_floats + (2 * CH + NP) * LTP; };     // [NP][LTP]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = lane % R, rl = lane / R;
@@ -48,11 +54,18 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
   ScanOrder so;
   so.dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
   so.H = p.H; so.W = p.W; so.L = L;
+  const bool tma = p.tma_ok && (so.dir == 0 || so.dir == 1);
 
   for (int r = tid; r < CH; r += kThreads) {
     const bool ok = r < rows_valid;
     s_bias[r] = (ok && p.bias) ? p.bias[d0 + r] : 0.f;
     s_D[r] = (ok && p.Dv && !p.accum) ? p.Dv[d0 + r] : 0.f;
+  }
+  if (tma) {
+    // rows that TMA never writes must not hold garbage that could turn into NaN * 0: padded states and idle rows
+    for (int i = tid; i < 2 * S::stage_floats; i += kThreads) smem[i] = 0.f;
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
+    fence_proxy_async();
   }
 
   int rk[RPT];
@@ -76,28 +89,60 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
   auto B_off = [&](int n) { return B_base + (int64_t)n * p.B_ns; };
   auto C_off = [&](int n) { return C_base + (int64_t)n * p.C_ns; };
 
-  for (int l0 = 0; l0 < L; l0 += LT) {
-    const int len = min(LT, L - l0);
-    __syncthreads();   // previous tile fully consumed
-    stage_rows<LT, LTP>(s_u, p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so);
-    stage_rows<LT, LTP>(s_dl, p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so);
-    stage_rows<LT, LTP>(s_B, p.Bm, p.io_dtype, B_off, NP, p.N, l0, len, so);
-    stage_rows<LT, LTP>(s_C, p.Cm, p.io_dtype, C_off, NP, p.N, l0, len, so);
-    __syncthreads();
+  // warp 0: one bulk copy per operand row of tile `t` into stage `s`
+  auto issue_tile = [&](int t, int s) {
+    const int l0 = t * LT;
+    const int nrow = 2 * rows_valid + 2 * p.N;
+    if (lane == 0) mbar_arrive_expect_tx(&mbar[s], (uint32_t)nrow * LT * 4);
+    __syncwarp();
+    const float* gu = reinterpret_cast<const float*>(p.u);
+    const float* gd = reinterpret_cast<const float*>(p.delta);
+    const float* gB = reinterpret_cast<const float*>(p.Bm);
+    const float* gC = reinterpret_cast<const float*>(p.Cm);
+    for (int i = lane; i < nrow; i += 32) {
+      if (i < rows_valid) tma_load_1d(st_u(s) + i * LTP, gu + u_off(i) + l0, LT * 4, &mbar[s]);
+      else if (i < 2 * rows_valid) tma_load_1d(st_dl(s) + (i - rows_valid) * LTP, gd + dl_off(i - rows_valid) + l0, LT * 4, &mbar[s]);
+      else if (i < 2 * rows_valid + p.N) tma_load_1d(st_B(s) + (i - 2 * rows_valid) * LTP, gB + B_off(i - 2 * rows_valid) + l0, LT * 4, &mbar[s]);
+      else tma_load_1d(st_C(s) + (i - 2 * rows_valid - p.N) * LTP, gC + C_off(i - 2 * rows_valid - p.N) + l0, LT * 4, &mbar[s]);
+    }
+  };
+
+  const int ntiles = (L + LT - 1) / LT;
+  auto tile_is_tma = [&](int t) { return tma && (t + 1) * LT <= L; };
+  __syncthreads();
+  if (warp == 0 && tile_is_tma(0)) issue_tile(0, 0);
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int l0 = t * LT, len = min(LT, L - l0), s = t & 1;
+    float* s_dl = st_dl(s);
+    float* s_u = st_u(s);
+    float* s_B = st_B(s);
+    float* s_C = st_C(s);
+    // prefetch the next tile into the other stage (its previous tile was released by the barrier ending iteration t-1)
+    if (warp == 0 && t + 1 < ntiles && tile_is_tma(t + 1)) issue_tile(t + 1, s ^ 1);
+    if (tile_is_tma(t)) {
+      mbar_wait(&mbar[s], (t >> 1) & 1);
+    } else {
+      stage_rows<LT, LTP>(s_u, p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so);
+      stage_rows<LT, LTP>(s_dl, p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so);
+      stage_rows<LT, LTP>(s_B, p.Bm, p.io_dtype, B_off, NP, p.N, l0, len, so);
+      stage_rows<LT, LTP>(s_C, p.Cm, p.io_dtype, C_off, NP, p.N, l0, len, so);
+      __syncthreads();
+    }
     // activate delta once per element (not once per state lane): delta = softplus(raw + bias); du = delta * u
     for (int i = tid; i < CH * (LT / 4); i += kThreads) {
       const int r = i / (LT / 4), c = (i - r * (LT / 4)) * 4;
       float4 dv = *reinterpret_cast<const float4*>(s_dl + r * LTP + c);
-      const float4 uv = *reinterpret_cast<const float4*>(s_u + r * LTP + c);
+      float4 uv = *reinterpret_cast<const float4*>(s_u + r * LTP + c);
       const float bias = s_bias[r];
       float4 du;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float x = f4_at(dv, e) + bias;
         if (p.softplus) x = softplus20(x);
-        if (c + e >= len) x = 0.f;          // frozen state beyond the end of the sequence (a = 1, b = 0)
-        f4_at(dv, e) = x;
-        f4_at(du, e) = x * f4_at(const_cast<float4&>(uv), e);
+        const bool live = c + e < len;       // beyond the end of the sequence the state is frozen (a = 1, b = 0)
+        f4_at(dv, e) = live ? x : 0.f;
+        f4_at(du, e) = live ? x * f4_at(uv, e) : 0.f;
       }
       *reinterpret_cast<float4*>(s_dl + r * LTP + c) = dv;
       *reinterpret_cast<float4*>(s_du + r * LTP + c) = du;
@@ -165,6 +210,9 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
         }
       }
     }
+    // this stage was written through the generic proxy (activated delta); order that before the TMA that refills it
+    if (tma) fence_proxy_async();
+    __syncthreads();
   }
   if (p.last_state != nullptr) {
 #pragma unroll

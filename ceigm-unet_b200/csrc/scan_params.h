@@ -13,6 +13,7 @@ struct ScanParams {
   int dirs[SS2D_MAX_GROUP_DIRS];     // 0 in SCAN layout
   int u_mod;                         // 0 or the channel modulo for u (and for dout in the backward)
   int last_il;                       // last_state interleaved (h in odd slots)
+  int tma_ok;                        // fp32 operands, 16-byte aligned rows: TMA bulk staging allowed
   int nck;                           // number of SS2D_CHUNK checkpoints per row
   int NP;                            // padded state count of the kernel variant (ckpt row length)
   int A_ld;                          // row stride of A / dA / last_state (total dstate); N is this pass's count
