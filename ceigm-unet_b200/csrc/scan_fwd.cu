@@ -13,39 +13,43 @@
 
 namespace ss2d {
 
-constexpr int kFwdLT = 64;
-constexpr int kFwdLTP = kFwdLT + 4;
+constexpr int kConsumerWarps = 4;
+constexpr int kFwdThreads = 32 * (kConsumerWarps + 1);     // + 1 producer warp
 
-template <int NS, int R, int RPT>
+template <int NS, int R, int RPT, int LT, int STAGES>
 struct FwdShape {
+  static constexpr int LTP = LT + 4;
   static constexpr int RL = 32 / R;          // rows per warp per RPT slot
   static constexpr int RPW = RL * RPT;       // rows per warp
-  static constexpr int CH = 4 * RPW;         // rows per CTA
+  static constexpr int CH = kConsumerWarps * RPW;   // rows per CTA
   static constexpr int NP = NS * R;          // padded states
-  static constexpr int stage_floats = (2 * CH + 2 * NP) * kFwdLTP;     // delta, u, B, C tiles of one pipeline stage
-  static constexpr size_t smem_bytes = (size_t)(2 * stage_floats + CH * kFwdLTP + 2 * CH) * 4 + 16;
+  static constexpr int stage_floats = (2 * CH + 2 * NP) * LTP;     // delta, u, B, C tiles of one pipeline stage
+  static constexpr size_t smem_bytes = (size_t)(STAGES * stage_floats + CH * LTP + 2 * CH) * 4 + 16 * STAGES + 16;
 };
 
-// Tile pipeline: two shared-memory stages. When the operands are fp32 rows that are contiguous along the scan
-// (SCAN layout or direction 1) and 16-byte aligned, warp 0 fetches tile t+1 with TMA bulk copies (UBLKCP, one per
-// row, completing on the stage's mbarrier) while all four warps compute tile t. Any other case (16-bit dtypes,
-// transposed or reversed traversal, ragged tails) goes through the synchronous, index-mapped stage_rows().
-template <int NS, int R, int RPT>
-__global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) {
-  using S = FwdShape<NS, R, RPT>;
-  constexpr int LT = kFwdLT, LTP = kFwdLTP, CH = S::CH, NP = S::NP, RL = S::RL;
+// Warp-specialised tile pipeline, no CTA-wide barrier inside the loop:
+//   warp 4 (producer) fills stage t % STAGES with the delta / u / B / C tiles of scan positions [t LT, (t+1) LT):
+//     - fp32 operands whose rows are contiguous along the scan (SCAN layout or direction 1) and 16-byte aligned:
+//       one TMA bulk copy per row (cp.async.bulk -> UBLKCP) completing on the stage's `full` mbarrier;
+//     - anything else (16-bit dtypes, transposed / reversed traversal, unaligned views): index-mapped stage_rows().
+//   warps 0-3 (consumers) own RPW channel rows each: wait `full`, activate delta for their own rows, run the
+//   recurrence over the tile, then release the stage through its `empty` mbarrier. B/C are read-only and shared.
+template <int NS, int R, int RPT, int LT, int STAGES>
+__global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams p) {
+  using S = FwdShape<NS, R, RPT, LT, STAGES>;
+  constexpr int LTP = S::LTP, CH = S::CH, NP = S::NP, RL = S::RL, RPW = S::RPW;
   extern __shared__ __align__(16) float smem[];
-  float* s_du = smem + 2 * S::stage_floats;   // delta * u                      [CH][LTP]
-  float* s_bias = s_du + CH * LTP;            // [CH]
-  float* s_D = s_bias + CH;                   // [CH]
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_D + CH);   // [2]
+  float* s_du = smem + STAGES * S::stage_floats;   // delta * u                      [CH][LTP]
+  float* s_bias = s_du + CH * LTP;                 // [CH]
+  float* s_D = s_bias + CH;                        // [CH]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_D + CH);   // [STAGES]
+  uint64_t* empty = full + STAGES;                          // [STAGES]
   auto st_dl = [&](int s) { return smem + s * S::stage_floats; };              // delta (raw, then activated) [CH][LTP]
   auto st_u = [&](int s) { return smem + s * S::stage_floats + CH * LTP; };    // u                            [CH][LTP]
   auto st_B = [&](int s) { return smem + s * S::stage_floats + 2 * CH * LTP; };            // [NP][LTP]
   auto st_C = [&](int s) { return smem + s * S::stage_floats + (2 * CH + NP) * LTP; };     // [NP][LTP]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane % R, rl = lane / R;
   const int b = blockIdx.z, g = blockIdx.y;
   const int row0 = blockIdx.x * CH;                        // first channel of this CTA inside the group
   const int rows_valid = min(CH, p.dpg - row0);
@@ -55,31 +59,21 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
   so.dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
   so.H = p.H; so.W = p.W; so.L = L;
   const bool tma = p.tma_ok && (so.dir == 0 || so.dir == 1);
+  const int ntiles = (L + LT - 1) / LT;
 
-  for (int r = tid; r < CH; r += kThreads) {
+  for (int r = tid; r < CH; r += kFwdThreads) {
     const bool ok = r < rows_valid;
     s_bias[r] = (ok && p.bias) ? p.bias[d0 + r] : 0.f;
     s_D[r] = (ok && p.Dv && !p.accum) ? p.Dv[d0 + r] : 0.f;
   }
-  if (tma) {
-    // rows that TMA never writes must not hold garbage that could turn into NaN * 0: padded states and idle rows
-    for (int i = tid; i < 2 * S::stage_floats; i += kThreads) smem[i] = 0.f;
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_mbar_init(); }
-    fence_proxy_async();
+  // rows / tails that the producer never writes must hold finite values (they only ever meet multiplications by 0)
+  for (int i = tid; i < STAGES * S::stage_floats; i += kFwdThreads) smem[i] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    fence_mbar_init();
   }
-
-  int rk[RPT];
-  float A2[RPT][NS], h[RPT][NS];
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    rk[k] = warp * S::RPW + k * RL + rl;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const int n = j * R + q;
-      A2[k][j] = (rk[k] < rows_valid && n < p.N) ? p.A[(int64_t)(d0 + rk[k]) * p.A_ld + n] * kLog2e : 0.f;
-      h[k][j] = 0.f;
-    }
-  }
+  fence_proxy_async();
+  __syncthreads();
 
   const int64_t u_boff = (int64_t)b * p.u_bs, dl_boff = (int64_t)b * p.dl_bs, out_boff = (int64_t)b * p.out_bs;
   auto u_off = [&](int r) { const int d = d0 + r; return u_boff + (int64_t)(p.u_mod > 0 ? d % p.u_mod : d) * p.u_ds; };
@@ -89,49 +83,65 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
   auto B_off = [&](int n) { return B_base + (int64_t)n * p.B_ns; };
   auto C_off = [&](int n) { return C_base + (int64_t)n * p.C_ns; };
 
-  // warp 0: one bulk copy per operand row of tile `t` into stage `s`
-  auto issue_tile = [&](int t, int s) {
-    const int l0 = t * LT;
-    const int nrow = 2 * rows_valid + 2 * p.N;
-    if (lane == 0) mbar_arrive_expect_tx(&mbar[s], (uint32_t)nrow * LT * 4);
-    __syncwarp();
+  if (warp == kConsumerWarps) {
+    // =============================== producer warp ===============================
     const float* gu = reinterpret_cast<const float*>(p.u);
     const float* gd = reinterpret_cast<const float*>(p.delta);
     const float* gB = reinterpret_cast<const float*>(p.Bm);
     const float* gC = reinterpret_cast<const float*>(p.Cm);
-    for (int i = lane; i < nrow; i += 32) {
-      if (i < rows_valid) tma_load_1d(st_u(s) + i * LTP, gu + u_off(i) + l0, LT * 4, &mbar[s]);
-      else if (i < 2 * rows_valid) tma_load_1d(st_dl(s) + (i - rows_valid) * LTP, gd + dl_off(i - rows_valid) + l0, LT * 4, &mbar[s]);
-      else if (i < 2 * rows_valid + p.N) tma_load_1d(st_B(s) + (i - 2 * rows_valid) * LTP, gB + B_off(i - 2 * rows_valid) + l0, LT * 4, &mbar[s]);
-      else tma_load_1d(st_C(s) + (i - 2 * rows_valid - p.N) * LTP, gC + C_off(i - 2 * rows_valid - p.N) + l0, LT * 4, &mbar[s]);
+    const int nrow = 2 * rows_valid + 2 * p.N;
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t % STAGES, use = t / STAGES;
+      const int l0 = t * LT, len = min(LT, L - l0);
+      mbar_wait(&empty[s], (use & 1) ^ 1);            // passes immediately the first time a stage is used
+      if (tma) {
+        const uint32_t bytes = (uint32_t)len * 4;
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)nrow * bytes);
+        __syncwarp();
+        for (int i = lane; i < nrow; i += 32) {
+          if (i < rows_valid) tma_load_1d(st_u(s) + i * LTP, gu + u_off(i) + l0, bytes, &full[s]);
+          else if (i < 2 * rows_valid) tma_load_1d(st_dl(s) + (i - rows_valid) * LTP, gd + dl_off(i - rows_valid) + l0, bytes, &full[s]);
+          else if (i < 2 * rows_valid + p.N) tma_load_1d(st_B(s) + (i - 2 * rows_valid) * LTP, gB + B_off(i - 2 * rows_valid) + l0, bytes, &full[s]);
+          else tma_load_1d(st_C(s) + (i - 2 * rows_valid - p.N) * LTP, gC + C_off(i - 2 * rows_valid - p.N) + l0, bytes, &full[s]);
+        }
+      } else {
+        stage_rows<LT, LTP>(st_u(s), p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<LT, LTP>(st_dl(s), p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<LT, LTP>(st_B(s), p.Bm, p.io_dtype, B_off, NP, p.N, l0, len, so, lane, 32);
+        stage_rows<LT, LTP>(st_C(s), p.Cm, p.io_dtype, C_off, NP, p.N, l0, len, so, lane, 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);         // release: the tile is visible to whoever acquires `full`
+      }
     }
-  };
+    return;
+  }
 
-  const int ntiles = (L + LT - 1) / LT;
-  auto tile_is_tma = [&](int t) { return tma && (t + 1) * LT <= L; };
-  __syncthreads();
-  if (warp == 0 && tile_is_tma(0)) issue_tile(0, 0);
+  // =============================== consumer warps ===============================
+  const int q = lane % R, rl = lane / R;
+  int rk[RPT];
+  float A2[RPT][NS], h[RPT][NS];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    rk[k] = warp * RPW + k * RL + rl;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int n = j * R + q;
+      A2[k][j] = (rk[k] < rows_valid && n < p.N) ? p.A[(int64_t)(d0 + rk[k]) * p.A_ld + n] * kLog2e : 0.f;
+      h[k][j] = 0.f;
+    }
+  }
 
   for (int t = 0; t < ntiles; ++t) {
-    const int l0 = t * LT, len = min(LT, L - l0), s = t & 1;
+    const int s = t % STAGES, use = t / STAGES;
+    const int l0 = t * LT, len = min(LT, L - l0);
     float* s_dl = st_dl(s);
-    float* s_u = st_u(s);
-    float* s_B = st_B(s);
-    float* s_C = st_C(s);
-    // prefetch the next tile into the other stage (its previous tile was released by the barrier ending iteration t-1)
-    if (warp == 0 && t + 1 < ntiles && tile_is_tma(t + 1)) issue_tile(t + 1, s ^ 1);
-    if (tile_is_tma(t)) {
-      mbar_wait(&mbar[s], (t >> 1) & 1);
-    } else {
-      stage_rows<LT, LTP>(s_u, p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so);
-      stage_rows<LT, LTP>(s_dl, p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so);
-      stage_rows<LT, LTP>(s_B, p.Bm, p.io_dtype, B_off, NP, p.N, l0, len, so);
-      stage_rows<LT, LTP>(s_C, p.Cm, p.io_dtype, C_off, NP, p.N, l0, len, so);
-      __syncthreads();
-    }
-    // activate delta once per element (not once per state lane): delta = softplus(raw + bias); du = delta * u
-    for (int i = tid; i < CH * (LT / 4); i += kThreads) {
-      const int r = i / (LT / 4), c = (i - r * (LT / 4)) * 4;
+    const float* s_u = st_u(s);
+    const float* s_B = st_B(s);
+    const float* s_C = st_C(s);
+    mbar_wait(&full[s], use & 1);
+    // activate delta once per element, for this warp's own rows: delta = softplus(raw + bias); du = delta * u
+    for (int i = lane; i < RPW * (LT / 4); i += 32) {
+      const int r = warp * RPW + i / (LT / 4), c = (i % (LT / 4)) * 4;
       float4 dv = *reinterpret_cast<const float4*>(s_dl + r * LTP + c);
       float4 uv = *reinterpret_cast<const float4*>(s_u + r * LTP + c);
       const float bias = s_bias[r];
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
       *reinterpret_cast<float4*>(s_dl + r * LTP + c) = dv;
       *reinterpret_cast<float4*>(s_du + r * LTP + c) = du;
     }
-    __syncthreads();
+    __syncwarp();
 
     for (int i4 = 0; i4 < LT / 4; i4 += R) {
       float yacc[RPT][R * 4];
@@ -164,17 +174,27 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
         for (int k = 0; k < RPT; ++k) {
           float4 dv = *reinterpret_cast<const float4*>(s_dl + rk[k] * LTP + c);
           float4 du = *reinterpret_cast<const float4*>(s_du + rk[k] * LTP + c);
+          // two scan positions per packed instruction (FMUL2 / FFMA2 halve the issue slots of the products and of
+          // the C.h accumulation); only the recurrence itself is inherently sequential and stays scalar
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float de = f4_at(dv, e), ue = f4_at(du, e);
-            float y = 0.f;
+          for (int ep = 0; ep < 2; ++ep) {
+            const float2 d2 = ep == 0 ? make_float2(dv.x, dv.y) : make_float2(dv.z, dv.w);
+            const float2 u2 = ep == 0 ? make_float2(du.x, du.y) : make_float2(du.z, du.w);
+            float2 y2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-              const float a = ex2f(de * A2[k][j]);
-              h[k][j] = fmaf(a, h[k][j], ue * f4_at(Bv[j], e));
-              y = fmaf(h[k][j], f4_at(Cv[j], e), y);
+              const float2 arg = __fmul2_rn(d2, make_float2(A2[k][j], A2[k][j]));
+              const float a0 = ex2f(arg.x), a1 = ex2f(arg.y);
+              const float2 b2 = ep == 0 ? make_float2(Bv[j].x, Bv[j].y) : make_float2(Bv[j].z, Bv[j].w);
+              const float2 c2 = ep == 0 ? make_float2(Cv[j].x, Cv[j].y) : make_float2(Cv[j].z, Cv[j].w);
+              const float2 bu = __fmul2_rn(u2, b2);
+              const float h0 = fmaf(a0, h[k][j], bu.x);
+              const float h1 = fmaf(a1, h0, bu.y);
+              h[k][j] = h1;
+              y2 = __ffma2_rn(make_float2(h0, h1), c2, y2);
             }
-            yacc[k][gq * 4 + e] = y;
+            yacc[k][gq * 4 + 2 * ep] = y2.x;
+            yacc[k][gq * 4 + 2 * ep + 1] = y2.y;
           }
         }
       }
@@ -210,9 +230,10 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
         }
       }
     }
-    // this stage was written through the generic proxy (activated delta); order that before the TMA that refills it
-    if (tma) fence_proxy_async();
-    __syncthreads();
+    // release the stage: this warp's generic-proxy writes (activated delta) are ordered before the TMA that refills it
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
   if (p.last_state != nullptr) {
 #pragma unroll
@@ -229,25 +250,25 @@ __global__ void __launch_bounds__(kThreads) scan_fwd_kernel(const ScanParams p) 
   }
 }
 
-template <int NS, int R, int RPT>
+template <int NS, int R, int RPT, int LT, int STAGES>
 static cudaError_t launch_fwd(const ScanParams& p, cudaStream_t stream) {
-  using S = FwdShape<NS, R, RPT>;
-  auto kern = scan_fwd_kernel<NS, R, RPT>;
+  using S = FwdShape<NS, R, RPT, LT, STAGES>;
+  auto kern = scan_fwd_kernel<NS, R, RPT, LT, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
   if (e != cudaSuccess) return e;
   dim3 grid((p.dpg + S::CH - 1) / S::CH, p.G, p.batch);
-  kern<<<grid, kThreads, S::smem_bytes, stream>>>(p);
+  kern<<<grid, kFwdThreads, S::smem_bytes, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream) {
   const Variant v = pick_variant(p.N);
-  if (v.NS == 1) return launch_fwd<1, 1, 1>(p, stream);
-  if (v.NS == 2) return launch_fwd<2, 1, 1>(p, stream);
-  if (v.R == 1) return launch_fwd<4, 1, 1>(p, stream);
-  if (v.R == 2) return launch_fwd<4, 2, 1>(p, stream);
-  if (v.R == 4) return launch_fwd<4, 4, 1>(p, stream);
-  return launch_fwd<4, 8, 1>(p, stream);
+  if (v.NS == 1) return launch_fwd<1, 1, 1, 32, 3>(p, stream);
+  if (v.NS == 2) return launch_fwd<2, 1, 1, 32, 3>(p, stream);
+  if (v.R == 1) return launch_fwd<4, 1, 1, 32, 3>(p, stream);
+  if (v.R == 2) return launch_fwd<4, 2, 1, 32, 3>(p, stream);
+  if (v.R == 4) return launch_fwd<4, 4, 1, 32, 3>(p, stream);
+  return launch_fwd<4, 8, 1, 32, 3>(p, stream);
 }
 
 }  // namespace ss2d

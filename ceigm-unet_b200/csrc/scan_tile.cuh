@@ -14,13 +14,14 @@ constexpr int kThreads = 128;
 
 // dst[r][0..LT) <- row r of `src` at scan positions [l0, l0+len), zero-filled beyond len / rows_valid.
 // row_off(r) gives the element offset of row r's plane/sequence start.
+// The copy is shared by `nthr` threads; `thr` is this thread's index among them.
 template <int LT, int LTP, typename RowOff>
 __device__ __forceinline__ void stage_rows(float* __restrict__ dst, const void* __restrict__ src, int dt,
                                            RowOff row_off, int rows_total, int rows_valid, int l0, int len,
-                                           const ScanOrder so) {
+                                           const ScanOrder so, int thr = threadIdx.x, int nthr = kThreads) {
   constexpr int G4 = LT / 4;
   const bool vecL = (so.L & 3) == 0;
-  for (int i = threadIdx.x; i < rows_total * G4; i += kThreads) {
+  for (int i = thr; i < rows_total * G4; i += nthr) {
     const int r = i / G4, c = (i - r * G4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows_valid && c < len) {
