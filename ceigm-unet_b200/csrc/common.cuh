@@ -137,6 +137,32 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                : "memory");
 }
 
+// tiled TMA loads through a tensor map (UTMALDG): box lands densely in shared memory, 128-byte swizzled
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// Shared-memory tile layout: rows of 32 floats (128 bytes) with the 16-byte chunks XOR-swizzled by the row index —
+// exactly what TMA's SWIZZLE_128B produces for a 1024-byte aligned tile — so that 8 consecutive rows read at the
+// same column (the scan's access pattern) hit 8 different bank groups without any padding.
+constexpr int kTileL = 32;
+__device__ __forceinline__ int swz(int r, int c) { return r * kTileL + ((((c >> 2) ^ r) & 7) << 2) + (c & 3); }
+
 __device__ __forceinline__ float& f4_at(float4& v, int e) { return reinterpret_cast<float*>(&v)[e]; }
 
 }  // namespace ss2d

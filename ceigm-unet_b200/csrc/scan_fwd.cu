@@ -8,46 +8,56 @@
 // row combine their partial y with warp shuffles, and B/C tiles are staged once per CTA and broadcast from
 // shared memory to all rows. At d_state = 16 the kernel is bound by MUFU.EX2 (16/clk/SM), not by HBM —
 // see DESIGN.md.
+#include <cstdlib>
+#include <cstring>
+
 #include "scan_params.h"
 #include "scan_tile.cuh"
+#include "tma_host.h"
 
 namespace ss2d {
 
 constexpr int kConsumerWarps = 4;
 constexpr int kFwdThreads = 32 * (kConsumerWarps + 1);     // + 1 producer warp
+constexpr int LT = kTileL;                                  // scan positions per tile (= SS2D_CHUNK)
+static_assert(LT == SS2D_CHUNK, "one checkpoint per tile");
 
-template <int NS, int R, int RPT, int LT, int STAGES>
+template <int NS, int R, int RPT, int STAGES>
 struct FwdShape {
-  static constexpr int LTP = LT + 4;
   static constexpr int RL = 32 / R;          // rows per warp per RPT slot
   static constexpr int RPW = RL * RPT;       // rows per warp
   static constexpr int CH = kConsumerWarps * RPW;   // rows per CTA
   static constexpr int NP = NS * R;          // padded states
-  static constexpr int stage_floats = (2 * CH + 2 * NP) * LTP;     // delta, u, B, C tiles of one pipeline stage
-  static constexpr size_t smem_bytes = (size_t)(STAGES * stage_floats + CH * LTP + 2 * CH) * 4 + 16 * STAGES + 16;
+  static constexpr int NPB = (NP + 7) / 8 * 8;      // B/C tile rows (tiles are multiples of 1024 bytes)
+  static constexpr int stage_floats = (2 * CH + 2 * NPB) * LT;     // delta, u, B, C tiles of one pipeline stage
+  static constexpr size_t smem_bytes = (size_t)(STAGES * stage_floats + CH * LT + 2 * CH) * 4 + 16 * STAGES + 1024;
 };
 
 // Warp-specialised tile pipeline, no CTA-wide barrier inside the loop:
 //   warp 4 (producer) fills stage t % STAGES with the delta / u / B / C tiles of scan positions [t LT, (t+1) LT):
 //     - fp32 operands whose rows are contiguous along the scan (SCAN layout or direction 1) and 16-byte aligned:
-//       one TMA bulk copy per row (cp.async.bulk -> UBLKCP) completing on the stage's `full` mbarrier;
-//     - anything else (16-bit dtypes, transposed / reversed traversal, unaligned views): index-mapped stage_rows().
+//       four tiled TMA loads through tensor maps (cp.async.bulk.tensor -> UTMALDG, 128-byte swizzle, out-of-bounds
+//       rows / tails zero-filled by the hardware), completing on the stage's `full` mbarrier;
+//     - anything else (16-bit dtypes, transposed / reversed traversal, unaligned views): index-mapped stage_rows()
+//       writing the same swizzled layout.
 //   warps 0-3 (consumers) own RPW channel rows each: wait `full`, activate delta for their own rows, run the
 //   recurrence over the tile, then release the stage through its `empty` mbarrier. B/C are read-only and shared.
-template <int NS, int R, int RPT, int LT, int STAGES>
-__global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams p) {
-  using S = FwdShape<NS, R, RPT, LT, STAGES>;
-  constexpr int LTP = S::LTP, CH = S::CH, NP = S::NP, RL = S::RL, RPW = S::RPW;
-  extern __shared__ __align__(16) float smem[];
-  float* s_du = smem + STAGES * S::stage_floats;   // delta * u                      [CH][LTP]
-  float* s_bias = s_du + CH * LTP;                 // [CH]
+template <int NS, int R, int RPT, int STAGES>
+__global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams p, const __grid_constant__ TmaMaps maps) {
+  using S = FwdShape<NS, R, RPT, STAGES>;
+  constexpr int CH = S::CH, NP = S::NP, NPB = S::NPB, RL = S::RL, RPW = S::RPW;
+  extern __shared__ __align__(16) float smem_raw[];
+  // tiles must be 1024-byte aligned in the shared window for the 128-byte swizzle pattern
+  float* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023) / 4;
+  float* s_du = smem + STAGES * S::stage_floats;   // delta * u (consumer-written), swizzled   [CH][LT]
+  float* s_bias = s_du + CH * LT;                  // [CH]
   float* s_D = s_bias + CH;                        // [CH]
   uint64_t* full = reinterpret_cast<uint64_t*>(s_D + CH);   // [STAGES]
   uint64_t* empty = full + STAGES;                          // [STAGES]
-  auto st_dl = [&](int s) { return smem + s * S::stage_floats; };              // delta (raw, then activated) [CH][LTP]
-  auto st_u = [&](int s) { return smem + s * S::stage_floats + CH * LTP; };    // u                            [CH][LTP]
-  auto st_B = [&](int s) { return smem + s * S::stage_floats + 2 * CH * LTP; };            // [NP][LTP]
-  auto st_C = [&](int s) { return smem + s * S::stage_floats + (2 * CH + NP) * LTP; };     // [NP][LTP]
+  auto st_dl = [&](int s) { return smem + s * S::stage_floats; };              // delta (raw, then activated) [CH][LT]
+  auto st_u = [&](int s) { return smem + s * S::stage_floats + CH * LT; };     // u                            [CH][LT]
+  auto st_B = [&](int s) { return smem + s * S::stage_floats + 2 * CH * LT; };             // [NPB][LT]
+  auto st_C = [&](int s) { return smem + s * S::stage_floats + (2 * CH + NPB) * LT; };     // [NPB][LT]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, g = blockIdx.y;
@@ -66,13 +76,10 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
     s_bias[r] = (ok && p.bias) ? p.bias[d0 + r] : 0.f;
     s_D[r] = (ok && p.Dv && !p.accum) ? p.Dv[d0 + r] : 0.f;
   }
-  // rows / tails that the producer never writes must hold finite values (they only ever meet multiplications by 0)
-  for (int i = tid; i < STAGES * S::stage_floats; i += kFwdThreads) smem[i] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
     fence_mbar_init();
   }
-  fence_proxy_async();
   __syncthreads();
 
   const int64_t u_boff = (int64_t)b * p.u_bs, dl_boff = (int64_t)b * p.dl_bs, out_boff = (int64_t)b * p.out_bs;
@@ -85,30 +92,27 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
 
   if (warp == kConsumerWarps) {
     // =============================== producer warp ===============================
-    const float* gu = reinterpret_cast<const float*>(p.u);
-    const float* gd = reinterpret_cast<const float*>(p.delta);
-    const float* gB = reinterpret_cast<const float*>(p.Bm);
-    const float* gC = reinterpret_cast<const float*>(p.Cm);
-    const int nrow = 2 * rows_valid + 2 * p.N;
+    if (tma && lane == 0) {
+      tma_prefetch_desc(&maps.u); tma_prefetch_desc(&maps.dl); tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.C);
+    }
+    const int urow0 = p.u_mod > 0 ? d0 % p.u_mod : d0;
     for (int t = 0; t < ntiles; ++t) {
       const int s = t % STAGES, use = t / STAGES;
       const int l0 = t * LT, len = min(LT, L - l0);
       mbar_wait(&empty[s], (use & 1) ^ 1);            // passes immediately the first time a stage is used
       if (tma) {
-        const uint32_t bytes = (uint32_t)len * 4;
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)nrow * bytes);
-        __syncwarp();
-        for (int i = lane; i < nrow; i += 32) {
-          if (i < rows_valid) tma_load_1d(st_u(s) + i * LTP, gu + u_off(i) + l0, bytes, &full[s]);
-          else if (i < 2 * rows_valid) tma_load_1d(st_dl(s) + (i - rows_valid) * LTP, gd + dl_off(i - rows_valid) + l0, bytes, &full[s]);
-          else if (i < 2 * rows_valid + p.N) tma_load_1d(st_B(s) + (i - 2 * rows_valid) * LTP, gB + B_off(i - 2 * rows_valid) + l0, bytes, &full[s]);
-          else tma_load_1d(st_C(s) + (i - 2 * rows_valid - p.N) * LTP, gC + C_off(i - 2 * rows_valid - p.N) + l0, bytes, &full[s]);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_floats * 4);
+          tma_load_3d(st_u(s), &maps.u, l0, urow0, b, &full[s]);
+          tma_load_3d(st_dl(s), &maps.dl, l0, d0, b, &full[s]);
+          tma_load_4d(st_B(s), &maps.B, l0, 0, g, b, &full[s]);
+          tma_load_4d(st_C(s), &maps.C, l0, 0, g, b, &full[s]);
         }
       } else {
-        stage_rows<LT, LTP>(st_u(s), p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so, lane, 32);
-        stage_rows<LT, LTP>(st_dl(s), p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so, lane, 32);
-        stage_rows<LT, LTP>(st_B(s), p.Bm, p.io_dtype, B_off, NP, p.N, l0, len, so, lane, 32);
-        stage_rows<LT, LTP>(st_C(s), p.Cm, p.io_dtype, C_off, NP, p.N, l0, len, so, lane, 32);
+        stage_rows<LT, LT>(st_u(s), p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<LT, LT>(st_dl(s), p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<LT, LT>(st_B(s), p.Bm, p.io_dtype, B_off, NPB, p.N, l0, len, so, lane, 32);
+        stage_rows<LT, LT>(st_C(s), p.Cm, p.io_dtype, C_off, NPB, p.N, l0, len, so, lane, 32);
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);         // release: the tile is visible to whoever acquires `full`
       }
@@ -142,8 +146,9 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
     // activate delta once per element, for this warp's own rows: delta = softplus(raw + bias); du = delta * u
     for (int i = lane; i < RPW * (LT / 4); i += 32) {
       const int r = warp * RPW + i / (LT / 4), c = (i % (LT / 4)) * 4;
-      float4 dv = *reinterpret_cast<const float4*>(s_dl + r * LTP + c);
-      float4 uv = *reinterpret_cast<const float4*>(s_u + r * LTP + c);
+      const int o = swz(r, c);
+      float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
+      float4 uv = *reinterpret_cast<const float4*>(s_u + o);
       const float bias = s_bias[r];
       float4 du;
 #pragma unroll
@@ -154,8 +159,8 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         f4_at(dv, e) = live ? x : 0.f;
         f4_at(du, e) = live ? x * f4_at(uv, e) : 0.f;
       }
-      *reinterpret_cast<float4*>(s_dl + r * LTP + c) = dv;
-      *reinterpret_cast<float4*>(s_du + r * LTP + c) = du;
+      *reinterpret_cast<float4*>(s_dl + o) = dv;
+      *reinterpret_cast<float4*>(s_du + o) = du;
     }
     __syncwarp();
 
@@ -167,13 +172,13 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         float4 Bv[NS], Cv[NS];
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          Bv[j] = *reinterpret_cast<const float4*>(s_B + (j * R + q) * LTP + c);
-          Cv[j] = *reinterpret_cast<const float4*>(s_C + (j * R + q) * LTP + c);
+          Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
+          Cv[j] = *reinterpret_cast<const float4*>(s_C + swz(j * R + q, c));
         }
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          float4 dv = *reinterpret_cast<const float4*>(s_dl + rk[k] * LTP + c);
-          float4 du = *reinterpret_cast<const float4*>(s_du + rk[k] * LTP + c);
+          const float4 dv = *reinterpret_cast<const float4*>(s_dl + swz(rk[k], c));
+          const float4 du = *reinterpret_cast<const float4*>(s_du + swz(rk[k], c));
           // two scan positions per packed instruction (FMUL2 / FFMA2 halve the issue slots of the products and of
           // the C.h accumulation); only the recurrence itself is inherently sequential and stays scalar
 #pragma unroll
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         reduce_scatter_groups<R>(yacc[k], q);
         const int c = (i4 + q) * 4;                 // this lane owns group q of the R groups just finished
         if (p.out != nullptr && rk[k] < rows_valid && c < len) {
-          const float4 uv = *reinterpret_cast<const float4*>(s_u + rk[k] * LTP + c);
+          const float4 uv = *reinterpret_cast<const float4*>(s_u + swz(rk[k], c));
           const float Dd = s_D[rk[k]];
           const float4 y4 = make_float4(fmaf(Dd, uv.x, yacc[k][0]), fmaf(Dd, uv.y, yacc[k][1]),
                                         fmaf(Dd, uv.z, yacc[k][2]), fmaf(Dd, uv.w, yacc[k][3]));
@@ -211,21 +216,18 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
                       p.accum != 0);
         }
       }
-      // state checkpoint at the end of every SS2D_CHUNK elements (for the backward's recompute)
-      if (p.ckpt != nullptr && ((i4 + R) & (SS2D_CHUNK / 4 - 1)) == 0) {
-        const int chunk = (l0 + (i4 + R) * 4) / SS2D_CHUNK - 1;
-        if (chunk < p.nck) {
+    }
+    // state checkpoint at the end of the tile (= SS2D_CHUNK scan positions), for the backward's recompute
+    if (p.ckpt != nullptr) {
 #pragma unroll
-          for (int k = 0; k < RPT; ++k) {
-            if (rk[k] < rows_valid) {
-              float* dst = p.ckpt + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + chunk) * NP + q * NS;
-              if (NS == 4) {
-                *reinterpret_cast<float4*>(dst) = make_float4(h[k][0], h[k][1 % NS], h[k][2 % NS], h[k][3 % NS]);
-              } else {
+      for (int k = 0; k < RPT; ++k) {
+        if (rk[k] < rows_valid) {
+          float* dst = p.ckpt + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + t) * NP + q * NS;
+          if (NS == 4) {
+            *reinterpret_cast<float4*>(dst) = make_float4(h[k][0], h[k][1 % NS], h[k][2 % NS], h[k][3 % NS]);
+          } else {
 #pragma unroll
-                for (int j = 0; j < NS; ++j) dst[j] = h[k][j];
-              }
-            }
+            for (int j = 0; j < NS; ++j) dst[j] = h[k][j];
           }
         }
       }
@@ -250,25 +252,38 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
   }
 }
 
-template <int NS, int R, int RPT, int LT, int STAGES>
-static cudaError_t launch_fwd(const ScanParams& p, cudaStream_t stream) {
-  using S = FwdShape<NS, R, RPT, LT, STAGES>;
-  auto kern = scan_fwd_kernel<NS, R, RPT, LT, STAGES>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
-  if (e != cudaSuccess) return e;
+template <int NS, int R, int RPT, int STAGES>
+static cudaError_t launch_fwd(ScanParams p, cudaStream_t stream) {
+  using S = FwdShape<NS, R, RPT, STAGES>;
+  auto kern = scan_fwd_kernel<NS, R, RPT, STAGES>;
+  static bool configured = false;     // per instantiation; the attribute is per-function and sticky
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  TmaMaps maps;
+  if (p.tma_ok && !(p.u_mod == 0 || p.u_mod == p.dpg)) p.tma_ok = 0;
+  if (p.tma_ok && !make_scan_maps(p, S::CH, S::NPB, false, &maps)) p.tma_ok = 0;
+  if (!p.tma_ok) memset(&maps, 0, sizeof(maps));
   dim3 grid((p.dpg + S::CH - 1) / S::CH, p.G, p.batch);
-  kern<<<grid, kFwdThreads, S::smem_bytes, stream>>>(p);
+  kern<<<grid, kFwdThreads, S::smem_bytes, stream>>>(p, maps);
   return cudaGetLastError();
 }
 
 cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream) {
   const Variant v = pick_variant(p.N);
-  if (v.NS == 1) return launch_fwd<1, 1, 1, 32, 3>(p, stream);
-  if (v.NS == 2) return launch_fwd<2, 1, 1, 32, 3>(p, stream);
-  if (v.R == 1) return launch_fwd<4, 1, 1, 32, 3>(p, stream);
-  if (v.R == 2) return launch_fwd<4, 2, 1, 32, 3>(p, stream);
-  if (v.R == 4) return launch_fwd<4, 4, 1, 32, 3>(p, stream);
-  return launch_fwd<4, 8, 1, 32, 3>(p, stream);
+  if (v.NS == 1) return launch_fwd<1, 1, 1, 3>(p, stream);
+  if (v.NS == 2) return launch_fwd<2, 1, 1, 3>(p, stream);
+  if (v.R == 1) return launch_fwd<4, 1, 1, 3>(p, stream);
+  if (v.R == 2) return launch_fwd<4, 2, 1, 3>(p, stream);
+  if (v.R == 4) {
+    static const int rpt = getenv("SS2D_FWD_RPT") ? atoi(getenv("SS2D_FWD_RPT")) : 1;     // tuning knob
+    static const int stg = getenv("SS2D_FWD_STAGES") ? atoi(getenv("SS2D_FWD_STAGES")) : 3;
+    if (rpt == 2) return stg == 2 ? launch_fwd<4, 4, 2, 2>(p, stream) : launch_fwd<4, 4, 2, 3>(p, stream);
+    return stg == 2 ? launch_fwd<4, 4, 1, 2>(p, stream) : stg == 4 ? launch_fwd<4, 4, 1, 4>(p, stream) : launch_fwd<4, 4, 1, 3>(p, stream);
+  }
+  return launch_fwd<4, 8, 1, 3>(p, stream);
 }
 
 }  // namespace ss2d

@@ -40,6 +40,11 @@ struct ScanParams {
   float* part;          // workspace: [batch][dim][N + 2] per-batch partial sums of dA, dD, dbias
 };
 
+// Opaque 128-byte TMA tensor-map descriptors (CUtensorMap), filled on the host by cuTensorMapEncodeTiled and passed
+// to the kernels as a __grid_constant__ parameter.
+struct alignas(64) TMap { unsigned long long v[16]; };
+struct TmaMaps { TMap u, dl, B, C, dy; };
+
 // Kernel variant for a state count: NS states per thread, R lanes per row. NS * R >= N.
 struct Variant { int NS, R; };
 inline Variant pick_variant(int N) {

@@ -46,7 +46,7 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ dst, const void* 
           if (c + e < len) f4_at(v, e) = load1(src, ro + so.natural(l0 + c + e), dt);
       }
     }
-    *reinterpret_cast<float4*>(dst + r * LTP + c) = v;
+    *reinterpret_cast<float4*>(dst + (LTP == LT ? swz(r, c) : r * LTP + c)) = v;
   }
 }
 
