@@ -91,9 +91,8 @@ static bool tma_eligible(const ss2d_scan_desc* d, const void* u, const void* del
 // states are processed in passes of <= 32; pass i covers [32 i, 32 i + n_i)
 static int n_passes(int N) { return (N + kStatesPerPass - 1) / kStatesPerPass; }
 static size_t ckpt_floats_pass(const ss2d_scan_desc* d, int n) {
-  const Variant v = pick_variant(n);
   const size_t nck = (d->seqlen + SS2D_CHUNK - 1) / SS2D_CHUNK;
-  return (size_t)d->batch * d->dim * nck * (size_t)(v.NS * v.R);
+  return (size_t)d->batch * d->dim * nck * (size_t)n;
 }
 static size_t round4(size_t x) { return (x + 3) & ~(size_t)3; }
 
@@ -178,6 +177,8 @@ int ss2d_scan_bwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
   ScanParams p;
   pack(d, p);
   p.u = u; p.delta = delta; p.Dv = Dvec; p.bias = delta_bias; p.dout = dout; p.du = du; p.ddelta = ddelta;
+  p.tma_ok = tma_eligible(d, u, delta, Bmat, Cmat, dout) && d->out_dtype == SS2D_F32 && !(d->out_batch_stride & 3) &&
+             !(d->out_dim_stride & 3);
   p.part = part;
   size_t ck_off = 0;
   for (int i = 0; i < n_passes(d->dstate); ++i) {

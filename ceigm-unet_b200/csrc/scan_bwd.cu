@@ -2,36 +2,51 @@
 //
 // Replaces selective_scan_bwd_kernel (/root/reference/gm-unet/kernels/selective_scan/csrc/selective_scan/cus/
 // selective_scan_bwd_kernel.cuh:66-273) and, in NATURAL layout, the backward of CrossScan*/CrossMerge*
-// (model/gm/csms6s.py). Same work decomposition as scan_fwd.cu. Tiles of SS2D_CHUNK scan positions are
-// visited last-to-first; inside a tile the states h are RECOMPUTED from the chunk checkpoint written by the
-// forward (never stored in HBM per element), kept in shared memory, and consumed by the reverse adjoint
-// recurrence  g_l = C_l dy_l + a_(l+1) g_(l+1).  dB/dC are summed over the rows of the CTA in registers /
-// shuffles / per-warp slabs before they touch global memory (the reference issues one fp32 atomic per row
-// and element); dA, dD, d(delta_bias) go through a per-batch partial buffer and a deterministic second pass.
+// (model/gm/csms6s.py). Not a port: the reference runs one CTA per (batch, channel) row, two CUB block scans per
+// state and chunk, and one fp32 global atomic per row and element for dB/dC.
+//
+// Here a CTA owns CH channel rows of one (batch, group) and walks the tiles of 32 scan positions LAST TO FIRST:
+//   * warp 4 (producer) streams the u / delta / dout / B / C tiles through a 2-stage shared-memory ring with tiled
+//     TMA loads (or the index-mapped generic copy for 16-bit / transposed / reversed operands), and — being idle
+//     otherwise — also folds the consumers' per-warp dB/dC slabs together and sends them to global memory;
+//   * warps 0-3 (consumers) each own RPW rows, NS states per lane. Per tile: (1) recompute the states h forward from
+//     the forward pass' chunk checkpoint, keeping only one state vector per 4 positions in shared memory;
+//     (2) for each group of 4 positions, last to first, re-expand h and a = exp(delta A) into registers and run the
+//     adjoint recurrence g_l = C_l dy_l + a_(l+1) g_(l+1). Nothing per-element is ever stored in HBM.
+//   * dB/dC partials are summed over the thread's rows in registers, over the warp's row lanes with a shuffle
+//     reduce-scatter, and over the CTA's warps by the producer: one vector reduction per (state, 4 positions) and
+//     CTA reaches global memory (plain stores when the CTA covers the whole group: deterministic).
+//   * dA, dD, d(delta_bias) leave through a per-batch partial buffer and a deterministic second pass.
+#include <cstdlib>
+#include <cstring>
+
 #include "scan_params.h"
 #include "scan_tile.cuh"
+#include "tma_host.h"
 
 namespace ss2d {
 
-constexpr int kBwdLT = SS2D_CHUNK;
-constexpr int kBwdLTP = kBwdLT + 4;
+constexpr int kBwdConsumerWarps = 4;
+constexpr int kBwdThreads = 32 * (kBwdConsumerWarps + 1);
+constexpr int BLT = kTileL;                 // scan positions per tile (= SS2D_CHUNK)
+constexpr int kBwdStages = 2;
+constexpr int kHalf = BLT / 2;              // slab hand-off granularity (scan positions)
 
 template <int NS, int R, int RPT>
 struct BwdShape {
   static constexpr int RL = 32 / R;
   static constexpr int RPW = RL * RPT;
-  static constexpr int CH = 4 * RPW;
+  static constexpr int CH = kBwdConsumerWarps * RPW;
   static constexpr int NP = NS * R;
-  static constexpr int CNT = 2 * NS * 4;                 // dB/dC partials per thread and 4-element group
-  static constexpr size_t tile_floats = (size_t)(4 * CH + 2 * NP) * kBwdLTP;
-  static constexpr size_t slab_floats = (size_t)4 * 2 * NP * kBwdLTP;
-  static constexpr size_t h_floats = (size_t)kBwdLT * RPT * kThreads * NS;
-  static constexpr size_t smem_bytes = (tile_floats + slab_floats + h_floats + 2 * CH) * 4;
+  static constexpr int NPB = (NP + 7) / 8 * 8;
+  static constexpr int CNT = 2 * NS * 4;                      // dB/dC partials per thread and 4-position group
+  static constexpr int stage_floats = (3 * CH + 2 * NPB) * BLT;
+  static constexpr int slab_floats = 2 * NP * kHalf;          // one warp, one half tile: [dB | dC][NP][16]
+  static constexpr int hs_floats = (BLT / 4) * RPT * 32 * NS; // one warp: state at the end of each group
+  static constexpr size_t smem_bytes =
+      (size_t)(kBwdStages * stage_floats + kBwdConsumerWarps * (2 * slab_floats + hs_floats) + 2 * CH) * 4 + 128 + 1024;
 };
 
-// Reduce-scatter of CNT per-lane values over LANES lanes spaced STRIDE apart (lane bits consumed MSB first).
-// If CNT >= LANES each lane ends with CNT/LANES totals (slice index = its lane id among LANES); otherwise the
-// value index is given by the top log2(CNT) lane bits and the remaining lanes hold replicas.
 template <int STRIDE, int CNT, int S>
 struct LaneReduceScatter {
   static __device__ __forceinline__ void run(float* v, int lane_id) {
@@ -53,6 +68,9 @@ struct LaneReduceScatter {
     }
   }
 };
+// Reduce-scatter of CNT per-lane values over LANES lanes spaced STRIDE apart (lane bits consumed MSB first).
+// If CNT >= LANES each lane ends with CNT/LANES totals (slice index = its lane id among LANES); otherwise the
+// value index is given by the top log2(CNT) lane bits and the remaining lanes hold replicas.
 template <int LANES, int STRIDE, int CNT>
 __device__ __forceinline__ void lane_reduce_scatter(float* v, int lane_id) {
   LaneReduceScatter<STRIDE, CNT, LANES / 2>::run(v, lane_id);
@@ -60,35 +78,44 @@ __device__ __forceinline__ void lane_reduce_scatter(float* v, int lane_id) {
 
 template <int NS>
 __device__ __forceinline__ void load_states(const float* __restrict__ src, float* dst) {
-  if (NS == 4) {
+  if constexpr (NS == 4) {
     const float4 v = *reinterpret_cast<const float4*>(src);
-    dst[0] = v.x; dst[1 % NS] = v.y; dst[2 % NS] = v.z; dst[3 % NS] = v.w;
-  } else if (NS == 2) {
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+  } else if constexpr (NS == 2) {
     const float2 v = *reinterpret_cast<const float2*>(src);
-    dst[0] = v.x; dst[1 % NS] = v.y;
+    dst[0] = v.x; dst[1] = v.y;
   } else {
     dst[0] = src[0];
   }
 }
+template <int NS>
+__device__ __forceinline__ void store_states(float* __restrict__ dst, const float* src) {
+  if constexpr (NS == 4) *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
+  else if constexpr (NS == 2) *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
+  else dst[0] = src[0];
+}
 
 template <int NS, int R, int RPT>
-__global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams p, const __grid_constant__ TmaMaps maps) {
   using S = BwdShape<NS, R, RPT>;
-  constexpr int LT = kBwdLT, LTP = kBwdLTP, CH = S::CH, NP = S::NP, RL = S::RL, CNT = S::CNT;
-  extern __shared__ __align__(16) float smem[];
-  float* s_dl = smem;                    // delta (activated); reused for the d(delta) tile   [CH][LTP]
-  float* s_u = s_dl + CH * LTP;          // u
-  float* s_du = s_u + CH * LTP;          // delta * u
-  float* s_dy = s_du + CH * LTP;         // dout; reused for the du tile
-  float* s_B = s_dy + CH * LTP;          // [NP][LTP]
-  float* s_C = s_B + NP * LTP;
-  float* s_slab = s_C + NP * LTP;        // [4 warps][2][NP][LTP] per-warp dB / dC sums
-  float* s_h = s_slab + S::slab_floats;  // [LT][RPT][128][NS] recomputed states
-  float* s_bias = s_h + S::h_floats;     // [CH]
-  float* s_D = s_bias + CH;              // [CH]
+  constexpr int CH = S::CH, NP = S::NP, NPB = S::NPB, RL = S::RL, RPW = S::RPW, CNT = S::CNT, NW = kBwdConsumerWarps;
+  extern __shared__ __align__(16) float smem_raw[];
+  float* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023) / 4;
+  float* s_slab = smem + kBwdStages * S::stage_floats;             // [2 buffers][NW][2][NP][16]
+  float* s_hs = s_slab + 2 * NW * S::slab_floats;                  // [NW][8 groups][RPT][32 lanes][NS]
+  float* s_bias = s_hs + NW * S::hs_floats;                        // [CH]
+  float* s_D = s_bias + CH;                                        // [CH]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_D + CH);          // [stages]
+  uint64_t* empty = full + kBwdStages;                             // [stages]
+  uint64_t* slab_full = empty + kBwdStages;                        // [2]
+  uint64_t* slab_empty = slab_full + 2;                            // [2]
+  auto st_dl = [&](int s) { return smem + s * S::stage_floats; };                          // delta -> d(delta)
+  auto st_u = [&](int s) { return smem + s * S::stage_floats + CH * BLT; };                // u
+  auto st_dy = [&](int s) { return smem + s * S::stage_floats + 2 * CH * BLT; };           // dout -> du
+  auto st_B = [&](int s) { return smem + s * S::stage_floats + 3 * CH * BLT; };            // [NPB][32]
+  auto st_C = [&](int s) { return smem + s * S::stage_floats + (3 * CH + NPB) * BLT; };    // [NPB][32]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane % R, rl = lane / R;
   const int b = blockIdx.z, g = blockIdx.y;
   const int row0 = blockIdx.x * CH;
   const int rows_valid = min(CH, p.dpg - row0);
@@ -97,28 +124,20 @@ __global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const ScanParams p) 
   ScanOrder so;
   so.dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
   so.H = p.H; so.W = p.W; so.L = L;
+  const bool tma = p.tma_ok && (so.dir == 0 || so.dir == 1);
+  const int ntiles = (L + BLT - 1) / BLT;
 
-  for (int r = tid; r < CH; r += kThreads) {
+  for (int r = tid; r < CH; r += kBwdThreads) {
     const bool ok = r < rows_valid;
     s_bias[r] = (ok && p.bias) ? p.bias[d0 + r] : 0.f;
     s_D[r] = (ok && p.Dv && !p.accum) ? p.Dv[d0 + r] : 0.f;
   }
-
-  int rk[RPT];
-  float A1[RPT][NS], A2[RPT][NS], carry[RPT][NS], dA[RPT][NS], dDacc[RPT], dbacc[RPT];
-#pragma unroll
-  for (int k = 0; k < RPT; ++k) {
-    rk[k] = warp * S::RPW + k * RL + rl;
-    dDacc[k] = 0.f; dbacc[k] = 0.f;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const int n = j * R + q;
-      A1[k][j] = (rk[k] < rows_valid && n < p.N) ? p.A[(int64_t)(d0 + rk[k]) * p.A_ld + n] : 0.f;
-      A2[k][j] = A1[k][j] * kLog2e;
-      carry[k][j] = 0.f;     // a_(l+1) * g_(l+1), zero past the end of the sequence
-      dA[k][j] = 0.f;
-    }
+  if (tid == 0) {
+    for (int s = 0; s < kBwdStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&slab_full[s], NW); mbar_init(&slab_empty[s], 1); }
+    fence_mbar_init();
   }
+  __syncthreads();
 
   const int64_t u_boff = (int64_t)b * p.u_bs, dl_boff = (int64_t)b * p.dl_bs, out_boff = (int64_t)b * p.out_bs;
   auto u_off = [&](int r) { const int d = d0 + r; return u_boff + (int64_t)(p.u_mod > 0 ? d % p.u_mod : d) * p.u_ds; };
@@ -132,47 +151,139 @@ __global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const ScanParams p) 
   const int64_t C_base = (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
   auto B_off = [&](int n) { return B_base + (int64_t)n * p.B_ns; };
   auto C_off = [&](int n) { return C_base + (int64_t)n * p.C_ns; };
-  const bool single_cta_group = gridDim.x == 1;
-  const int ntiles = (L + LT - 1) / LT;
 
-  for (int t = ntiles - 1; t >= 0; --t) {
-    const int l0 = t * LT, len = min(LT, L - l0);
-    __syncthreads();
-    stage_rows<LT, LTP>(s_u, p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so);
-    stage_rows<LT, LTP>(s_dl, p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so);
-    stage_rows<LT, LTP>(s_dy, p.dout, p.out_dtype, dy_off, CH, rows_valid, l0, len, so);
-    stage_rows<LT, LTP>(s_B, p.Bm, p.io_dtype, B_off, NP, p.N, l0, len, so);
-    stage_rows<LT, LTP>(s_C, p.Cm, p.io_dtype, C_off, NP, p.N, l0, len, so);
-    __syncthreads();
-    for (int i = tid; i < CH * (LT / 4); i += kThreads) {
-      const int r = i / (LT / 4), c = (i - r * (LT / 4)) * 4;
-      float4 dv = *reinterpret_cast<const float4*>(s_dl + r * LTP + c);
-      float4 uv = *reinterpret_cast<const float4*>(s_u + r * LTP + c);
+  if (warp == NW) {
+    // =============================== producer warp ===============================
+    if (tma && lane == 0) {
+      tma_prefetch_desc(&maps.u); tma_prefetch_desc(&maps.dl); tma_prefetch_desc(&maps.dy);
+      tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.C);
+    }
+    const int urow0 = p.u_mod > 0 ? d0 % p.u_mod : d0;
+    const bool single_cta_group = gridDim.x == 1;
+    // fold the NW per-warp slabs of half tile `hc` (processing order) and send the sums to dB / dC
+    auto flush_half = [&](int hc) {
+      const int buf = hc & 1;
+      mbar_wait(&slab_full[buf], (hc >> 1) & 1);
+      const int it = hc >> 1, t = ntiles - 1 - it;              // tile index along the scan
+      const int half = (hc & 1) ? 0 : 1;                        // the upper half of a tile is processed first
+      const int l_base = t * BLT + half * kHalf;
+      const float* base = s_slab + (size_t)buf * NW * S::slab_floats;
+      for (int i = lane; i < 2 * NP * (kHalf / 4); i += 32) {
+        const int which = i / (NP * (kHalf / 4)), rem = i - which * NP * (kHalf / 4);
+        const int n = rem / (kHalf / 4), c = (rem - n * (kHalf / 4)) * 4;
+        float4 acc = *reinterpret_cast<const float4*>(base + (which * NP + n) * kHalf + c);
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+          const float4 v = *reinterpret_cast<const float4*>(base + w * S::slab_floats + (which * NP + n) * kHalf + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const int l = l_base + c;
+        if (n < p.N && l < L) {
+          float* dst = (which == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + n) * L;
+          if (so.dir <= 1 && l + 3 < L && (L & 3) == 0) {
+            float4* q4 = reinterpret_cast<float4*>(dst + l);
+            if (single_cta_group) *q4 = acc;
+            else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q4), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (l + e < L) {
+                float* q1 = dst + so.natural(l + e);
+                if (single_cta_group) *q1 = f4_at(acc, e);
+                else atomicAdd(q1, f4_at(acc, e));
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slab_empty[buf]);
+    };
+    for (int it = 0; it < ntiles; ++it) {
+      const int t = ntiles - 1 - it;
+      const int s = it % kBwdStages, use = it / kBwdStages;
+      const int l0 = t * BLT, len = min(BLT, L - l0);
+      mbar_wait(&empty[s], (use & 1) ^ 1);
+      if (tma) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_floats * 4);
+          tma_load_3d(st_u(s), &maps.u, l0, urow0, b, &full[s]);
+          tma_load_3d(st_dl(s), &maps.dl, l0, d0, b, &full[s]);
+          tma_load_3d(st_dy(s), &maps.dy, l0, urow0, b, &full[s]);
+          tma_load_4d(st_B(s), &maps.B, l0, 0, g, b, &full[s]);
+          tma_load_4d(st_C(s), &maps.C, l0, 0, g, b, &full[s]);
+        }
+      } else {
+        stage_rows<BLT, BLT>(st_u(s), p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<BLT, BLT>(st_dl(s), p.delta, p.io_dtype, dl_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<BLT, BLT>(st_dy(s), p.dout, p.out_dtype, dy_off, CH, rows_valid, l0, len, so, lane, 32);
+        stage_rows<BLT, BLT>(st_B(s), p.Bm, p.io_dtype, B_off, NPB, p.N, l0, len, so, lane, 32);
+        stage_rows<BLT, BLT>(st_C(s), p.Cm, p.io_dtype, C_off, NPB, p.N, l0, len, so, lane, 32);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+      // the stage just refilled was released by the consumers finishing tile it - kBwdStages: its slabs are complete
+      if (it >= kBwdStages) { flush_half(2 * (it - kBwdStages)); flush_half(2 * (it - kBwdStages) + 1); }
+    }
+    for (int it = max(0, ntiles - kBwdStages); it < ntiles; ++it) { flush_half(2 * it); flush_half(2 * it + 1); }
+    return;
+  }
+
+  // =============================== consumer warps ===============================
+  const int q = lane % R, rl = lane / R;
+  float* my_hs = s_hs + warp * S::hs_floats;
+  int rk[RPT];
+  float A1[RPT][NS], A2[RPT][NS], carry[RPT][NS], dA[RPT][NS], dDacc[RPT], dbacc[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    rk[k] = warp * RPW + k * RL + rl;
+    dDacc[k] = 0.f; dbacc[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int n = j * R + q;
+      A1[k][j] = (rk[k] < rows_valid && n < p.N) ? p.A[(int64_t)(d0 + rk[k]) * p.A_ld + n] : 0.f;
+      A2[k][j] = A1[k][j] * kLog2e;
+      carry[k][j] = 0.f;     // a_(l+1) * g_(l+1), zero past the end of the sequence
+      dA[k][j] = 0.f;
+    }
+  }
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int t = ntiles - 1 - it;
+    const int s = it % kBwdStages, use = it / kBwdStages;
+    const int l0 = t * BLT, len = min(BLT, L - l0);
+    float* s_dl = st_dl(s);
+    const float* s_u = st_u(s);
+    float* s_dy = st_dy(s);
+    const float* s_B = st_B(s);
+    const float* s_C = st_C(s);
+    mbar_wait(&full[s], use & 1);
+    // activate delta for this warp's own rows, in place
+    for (int i = lane; i < RPW * (BLT / 4); i += 32) {
+      const int r = warp * RPW + i / (BLT / 4), c = (i % (BLT / 4)) * 4;
+      const int o = swz(r, c);
+      float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
       const float bias = s_bias[r];
-      float4 du;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float x = f4_at(dv, e) + bias;
         if (p.softplus) x = softplus20(x);
-        if (c + e >= len) x = 0.f;
-        f4_at(dv, e) = x;
-        f4_at(du, e) = x * f4_at(uv, e);
+        f4_at(dv, e) = (c + e < len && r < rows_valid) ? x : 0.f;   // idle rows may hold a neighbour group's data (TMA)
       }
-      *reinterpret_cast<float4*>(s_dl + r * LTP + c) = dv;
-      *reinterpret_cast<float4*>(s_du + r * LTP + c) = du;
+      *reinterpret_cast<float4*>(s_dl + o) = dv;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- forward recompute of h over the tile, from the checkpoint at the end of the previous chunk ----
+    // ---- (1) forward recompute of h over the tile from the checkpoint at the end of the previous chunk;
+    //          only the state after each group of 4 positions is kept (shared memory, private to the thread) ----
     float h0[RPT][NS];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
 #pragma unroll
-      for (int j = 0; j < NS; ++j) h0[k][j] = 0.f;
-      if (t > 0 && rk[k] < rows_valid) {
-        const float* src = p.ckpt_in + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + (t - 1)) * NP + q * NS;
-#pragma unroll
-        for (int j = 0; j < NS; ++j) h0[k][j] = __ldg(src + j);
+      for (int j = 0; j < NS; ++j) {
+        const int n = j * R + q;
+        h0[k][j] = (t > 0 && rk[k] < rows_valid && n < p.N)
+                       ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + (t - 1)) * p.N + n) : 0.f;
       }
     }
     {
@@ -181,149 +292,160 @@ __global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const ScanParams p) 
       for (int k = 0; k < RPT; ++k)
 #pragma unroll
         for (int j = 0; j < NS; ++j) h[k][j] = h0[k][j];
-      for (int i4 = 0; i4 < LT / 4; ++i4) {
-        const int c = i4 * 4;
+#pragma unroll 2
+      for (int gi = 0; gi < BLT / 4 - 1; ++gi) {       // the state after the last group is never needed
+        const int c = gi * 4;
         float4 Bv[NS];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) Bv[j] = *reinterpret_cast<const float4*>(s_B + (j * R + q) * LTP + c);
+        for (int j = 0; j < NS; ++j) Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          float4 dv = *reinterpret_cast<const float4*>(s_dl + rk[k] * LTP + c);
-          float4 du = *reinterpret_cast<const float4*>(s_du + rk[k] * LTP + c);
+          const float4 dv = *reinterpret_cast<const float4*>(s_dl + swz(rk[k], c));
+          const float4 uv = *reinterpret_cast<const float4*>(s_u + swz(rk[k], c));
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float de = f4_at(dv, e), ue = f4_at(du, e);
-            float* hs = s_h + ((size_t)((c + e) * RPT + k) * kThreads + tid) * NS;
+          for (int ep = 0; ep < 2; ++ep) {
+            const float2 d2 = ep == 0 ? make_float2(dv.x, dv.y) : make_float2(dv.z, dv.w);
+            const float2 u2 = __fmul2_rn(d2, ep == 0 ? make_float2(uv.x, uv.y) : make_float2(uv.z, uv.w));
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-              const float a = ex2f(de * A2[k][j]);
-              h[k][j] = fmaf(a, h[k][j], ue * f4_at(Bv[j], e));
+              const float2 arg = __fmul2_rn(d2, make_float2(A2[k][j], A2[k][j]));
+              const float2 bu = __fmul2_rn(u2, ep == 0 ? make_float2(Bv[j].x, Bv[j].y) : make_float2(Bv[j].z, Bv[j].w));
+              h[k][j] = fmaf(ex2f(arg.x), h[k][j], bu.x);
+              h[k][j] = fmaf(ex2f(arg.y), h[k][j], bu.y);
             }
-            if (NS == 4) *reinterpret_cast<float4*>(hs) = make_float4(h[k][0], h[k][1 % NS], h[k][2 % NS], h[k][3 % NS]);
-            else if (NS == 2) *reinterpret_cast<float2*>(hs) = make_float2(h[k][0], h[k][1 % NS]);
-            else hs[0] = h[k][0];
           }
+          store_states<NS>(my_hs + ((gi * RPT + k) * 32 + lane) * NS, h[k]);
         }
       }
     }
-    // each thread re-reads only what it wrote itself: no barrier needed before the reverse sweep
 
-    // ---- reverse adjoint sweep ----
-    for (int i4 = LT / 4 - 1; i4 >= 0; --i4) {
-      const int c = i4 * 4;
+    // ---- (2) groups of 4 positions, last to first: re-expand h and a, then the adjoint recurrence ----
+#pragma unroll 1
+    for (int gi = BLT / 4 - 1; gi >= 0; --gi) {
+      const int c = gi * 4;
       float4 Bv[NS], Cv[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        Bv[j] = *reinterpret_cast<const float4*>(s_B + (j * R + q) * LTP + c);
-        Cv[j] = *reinterpret_cast<const float4*>(s_C + (j * R + q) * LTP + c);
+        Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
+        Cv[j] = *reinterpret_cast<const float4*>(s_C + swz(j * R + q, c));
       }
       float part[CNT];     // [dB | dC][NS][4], summed over this thread's RPT rows
 #pragma unroll
       for (int i = 0; i < CNT; ++i) part[i] = 0.f;
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        float4 dv = *reinterpret_cast<const float4*>(s_dl + rk[k] * LTP + c);
-        float4 du = *reinterpret_cast<const float4*>(s_du + rk[k] * LTP + c);
-        float4 dy = *reinterpret_cast<const float4*>(s_dy + rk[k] * LTP + c);
+        const int o = swz(rk[k], c);
+        const float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
+        const float4 uv = *reinterpret_cast<const float4*>(s_u + o);
+        const float4 dy = *reinterpret_cast<const float4*>(s_dy + o);
+        const float dl[4] = {dv.x, dv.y, dv.z, dv.w};
+        const float dye[4] = {dy.x, dy.y, dy.z, dy.w};
+        const float dU[4] = {dv.x * uv.x, dv.y * uv.y, dv.z * uv.z, dv.w * uv.w};
+        float hin[NS];
+        if (gi > 0) load_states<NS>(my_hs + (((gi - 1) * RPT + k) * 32 + lane) * NS, hin);
+        else {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) hin[j] = h0[k][j];
+        }
+        float sB[4] = {0.f, 0.f, 0.f, 0.f}, sA[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const float Bj[4] = {Bv[j].x, Bv[j].y, Bv[j].z, Bv[j].w};
+          const float Cj[4] = {Cv[j].x, Cv[j].y, Cv[j].z, Cv[j].w};
+          float a[4], hh[4];
+          float hprev = hin[j];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            a[e] = ex2f(dl[e] * A2[k][j]);
+            hh[e] = fmaf(a[e], hprev, dU[e] * Bj[e]);
+            hprev = hh[e];
+          }
+          float cj = carry[k][j];
+#pragma unroll
+          for (int e = 3; e >= 0; --e) {
+            const float gj = fmaf(Cj[e], dye[e], cj);
+            part[(0 * NS + j) * 4 + e] = fmaf(gj, dU[e], part[(0 * NS + j) * 4 + e]);
+            part[(1 * NS + j) * 4 + e] = fmaf(dye[e], hh[e], part[(1 * NS + j) * 4 + e]);
+            sB[e] = fmaf(gj, Bj[e], sB[e]);
+            cj = gj * a[e];
+            const float w = cj * (e > 0 ? hh[e - 1] : hin[j]);
+            sA[e] = fmaf(w, A1[k][j], sA[e]);
+            dA[k][j] = fmaf(w, dl[e], dA[k][j]);
+          }
+          carry[k][j] = cj;
+        }
         float sums[8];     // [e][sB | sA]
 #pragma unroll
-        for (int e = 3; e >= 0; --e) {
-          const float de = f4_at(dv, e), ue = f4_at(du, e), dye = f4_at(dy, e);
-          float hc[NS], hp[NS];
-          load_states<NS>(s_h + ((size_t)((c + e) * RPT + k) * kThreads + tid) * NS, hc);
-          if (c + e > 0) {
-            load_states<NS>(s_h + ((size_t)((c + e - 1) * RPT + k) * kThreads + tid) * NS, hp);
-          } else {
-#pragma unroll
-            for (int j = 0; j < NS; ++j) hp[j] = h0[k][j];
-          }
-          float sB = 0.f, sA = 0.f;
-#pragma unroll
-          for (int j = 0; j < NS; ++j) {
-            const float a = ex2f(de * A2[k][j]);
-            const float gj = fmaf(f4_at(Cv[j], e), dye, carry[k][j]);
-            part[(0 * NS + j) * 4 + e] = fmaf(gj, ue, part[(0 * NS + j) * 4 + e]);
-            part[(1 * NS + j) * 4 + e] = fmaf(dye, hc[j], part[(1 * NS + j) * 4 + e]);
-            sB = fmaf(gj, f4_at(Bv[j], e), sB);
-            const float tj = gj * a;
-            carry[k][j] = tj;
-            const float w = tj * hp[j];
-            sA = fmaf(w, A1[k][j], sA);
-            dA[k][j] = fmaf(w, de, dA[k][j]);
-          }
-          sums[e * 2 + 0] = sB;
-          sums[e * 2 + 1] = sA;
-        }
-        // combine the R state lanes of the row; afterwards lane q owns 4/R elements (or half of one for R = 8)
+        for (int e = 0; e < 4; ++e) { sums[e * 2] = sB[e]; sums[e * 2 + 1] = sA[e]; }
+        // combine the R state lanes of the row; afterwards lane q owns 4/R positions (or half of one for R = 8)
         lane_reduce_scatter<R, 1, 8>(sums, q);
         constexpr int PER = (8 / R) > 0 ? (8 / R) : 1;
         float other = 0.f;
         if (R == 8) other = __shfl_xor_sync(0xffffffffu, sums[0], 1);
         if (R < 8 || (q & 1) == 0) {
-          constexpr int NE = R == 8 ? 1 : PER / 2;     // elements owned
+          constexpr int NE = R == 8 ? 1 : PER / 2;     // positions owned
           const int e0 = R == 8 ? (q >> 1) : q * NE;
 #pragma unroll
           for (int ee = 0; ee < NE; ++ee) {
             const int e = e0 + ee;
-            const float sB = sums[ee * 2 + 0];
-            const float sA = R == 8 ? other : sums[ee * 2 + 1];
-            const int idx = rk[k] * LTP + c + e;
-            const float de = s_dl[idx], uu = s_u[idx], dye = s_dy[idx];
-            const float du_out = fmaf(s_D[rk[k]], dye, de * sB);
-            float ddl = fmaf(uu, sB, sA);
+            const float sBe = sums[ee * 2 + 0];
+            const float sAe = R == 8 ? other : sums[ee * 2 + 1];
+            const int idx = swz(rk[k], c + e);
+            const float de = s_dl[idx], uu = s_u[idx], dyv = s_dy[idx];
+            const float du_out = fmaf(s_D[rk[k]], dyv, de * sBe);
+            float ddl = fmaf(uu, sBe, sAe);
             if (p.softplus) {   // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
               const float sig = de < 0.015625f ? de * (1.f - de * (0.5f - de * 0.16666667f)) : 1.f - ex2f(-de * kLog2e);
               ddl *= sig;
             }
             if (c + e >= len) ddl = 0.f;
-            dDacc[k] = fmaf(dye, uu, dDacc[k]);
+            dDacc[k] = fmaf(dyv, uu, dDacc[k]);
             dbacc[k] += ddl;
-            // the row's lanes are done with dy/delta of this group (the shuffles above ordered them): reuse the tiles
+            // every lane of the row has consumed dy / delta of this group (the shuffles above ordered them): reuse the tiles
             s_dy[idx] = du_out;
             s_dl[idx] = ddl;
           }
         }
       }
-      // dB/dC: sum over the RL row lanes of the warp, then park the warp's totals in its slab
+      // dB/dC: sum over the RL row lanes of the warp, then park the warp's totals in its slab for this half tile
       lane_reduce_scatter<RL, R, CNT>(part, rl);
       {
+        const int hc = 2 * it + (gi >= BLT / 8 ? 0 : 1);       // half tiles in processing order
+        const int buf = hc & 1;
+        if (gi == BLT / 4 - 1 || gi == BLT / 8 - 1) mbar_wait(&slab_empty[buf], ((hc >> 1) & 1) ^ 1);   // first group of a half
         constexpr int PER = CNT >= RL ? CNT / RL : 1;
         constexpr int REP = CNT >= RL ? 1 : RL / CNT;          // replicas when there are fewer values than lanes
         if ((rl % REP) == 0) {
           const int slice = rl / REP;
-          float* slab = s_slab + (size_t)warp * 2 * NP * LTP;
+          float* slab = s_slab + ((size_t)buf * NW + warp) * S::slab_floats;
+          const int ch = c & (kHalf - 1);
 #pragma unroll
           for (int i = 0; i < PER; ++i) {
             const int vi = slice * PER + i;                     // index into [dB | dC][NS][4]
             const int which = vi / (NS * 4), j = (vi / 4) % NS, e = vi & 3;
-            slab[(which * NP + j * R + q) * LTP + c + e] = part[i];
+            slab[(which * NP + j * R + q) * kHalf + ch + e] = part[i];
           }
+        }
+        if (gi == BLT / 8 || gi == 0) {                        // last group of a half: hand the slab to the producer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slab_full[buf]);
         }
       }
     }
-    __syncthreads();
-    // ---- tile epilogue: du / d(delta) tiles and the CTA's dB / dC sums go to global memory ----
-    for (int i = tid; i < CH * (LT / 4); i += kThreads) {
-      const int r = i / (LT / 4), c = (i - r * (LT / 4)) * 4;
+    __syncwarp();
+    // ---- tile epilogue: this warp's rows of du / d(delta) go to global memory, then the stage is released ----
+    for (int i = lane; i < RPW * (BLT / 4); i += 32) {
+      const int r = warp * RPW + i / (BLT / 4), c = (i % (BLT / 4)) * 4;
       if (r < rows_valid && c < len) {
-        const float4 a = *reinterpret_cast<const float4*>(s_dy + r * LTP + c);
-        const float4 d = *reinterpret_cast<const float4*>(s_dl + r * LTP + c);
+        const float4 a = *reinterpret_cast<const float4*>(s_dy + swz(r, c));
+        const float4 d = *reinterpret_cast<const float4*>(s_dl + swz(r, c));
         store_scan4(p.du, p.io_dtype, du_off(r), l0 + c, l0 + len, a, so, p.accum != 0);
         store_scan4(p.ddelta, p.io_dtype, dl_off(r), l0 + c, l0 + len, d, so, p.accum != 0);
       }
     }
-    for (int i = tid; i < 2 * NP * LT; i += kThreads) {
-      const int which = i / (NP * LT), n = (i / LT) % NP, c = i % LT;
-      if (n < p.N && c < len) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) v += s_slab[((size_t)(w * 2 + which) * NP + n) * LTP + c];
-        float* dst = which == 0 ? p.dB : p.dC;
-        const int64_t idx = ((int64_t)(b * p.G + g) * p.A_ld + n) * L + so.natural(l0 + c);
-        if (single_cta_group) dst[idx] = v;
-        else atomicAdd(dst + idx, v);
-      }
-    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
 
   // ---- per-(batch, channel) partials of dA, dD, d(delta_bias) ----
@@ -331,9 +453,9 @@ __global__ void __launch_bounds__(kThreads) scan_bwd_kernel(const ScanParams p) 
   for (int k = 0; k < RPT; ++k) {
     float dd = dDacc[k], db = dbacc[k];
 #pragma unroll
-    for (int s = R / 2; s >= 1; s >>= 1) {
-      dd += __shfl_xor_sync(0xffffffffu, dd, s);
-      db += __shfl_xor_sync(0xffffffffu, db, s);
+    for (int sft = R / 2; sft >= 1; sft >>= 1) {
+      dd += __shfl_xor_sync(0xffffffffu, dd, sft);
+      db += __shfl_xor_sync(0xffffffffu, db, sft);
     }
     if (rk[k] < rows_valid) {
       float* dst = p.part + ((int64_t)b * p.dim + d0 + rk[k]) * (p.N + 2);
@@ -361,23 +483,31 @@ __global__ void scan_bwd_finalize_kernel(const float* __restrict__ part, float* 
 }
 
 template <int NS, int R, int RPT>
-static cudaError_t launch_bwd(const ScanParams& p, cudaStream_t stream) {
+static cudaError_t launch_bwd(ScanParams p, cudaStream_t stream) {
   using S = BwdShape<NS, R, RPT>;
   auto kern = scan_bwd_kernel<NS, R, RPT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
-  if (e != cudaSuccess) return e;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  TmaMaps maps;
+  if (p.tma_ok && !(p.u_mod == 0 || p.u_mod == p.dpg)) p.tma_ok = 0;
+  if (p.tma_ok && !make_scan_maps(p, S::CH, S::NPB, true, &maps)) p.tma_ok = 0;
+  if (!p.tma_ok) memset(&maps, 0, sizeof(maps));
   dim3 grid((p.dpg + S::CH - 1) / S::CH, p.G, p.batch);
-  kern<<<grid, kThreads, S::smem_bytes, stream>>>(p);
+  kern<<<grid, kBwdThreads, S::smem_bytes, stream>>>(p, maps);
   return cudaGetLastError();
 }
 
 cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream) {
-  const Variant v = pick_variant(p.N);
-  if (v.NS == 1) return launch_bwd<1, 1, 1>(p, stream);
-  if (v.NS == 2) return launch_bwd<2, 1, 1>(p, stream);
-  if (v.R == 1) return launch_bwd<4, 1, 1>(p, stream);
-  if (v.R == 2) return launch_bwd<4, 2, 1>(p, stream);
-  if (v.R == 4) return launch_bwd<4, 4, 1>(p, stream);
+  const int N = p.N;
+  if (N <= 1) return launch_bwd<1, 1, 1>(p, stream);
+  if (N <= 2) return launch_bwd<2, 1, 1>(p, stream);
+  if (N <= 4) return launch_bwd<2, 2, 1>(p, stream);
+  if (N <= 8) return launch_bwd<2, 4, 2>(p, stream);
+  if (N <= 16) return launch_bwd<2, 8, 2>(p, stream);
   return launch_bwd<4, 8, 1>(p, stream);
 }
 

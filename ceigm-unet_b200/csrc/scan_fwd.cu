@@ -217,18 +217,16 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         }
       }
     }
-    // state checkpoint at the end of the tile (= SS2D_CHUNK scan positions), for the backward's recompute
+    // state checkpoint at the end of the tile (= SS2D_CHUNK scan positions), for the backward's recompute:
+    // ckpt[b][d][tile][n], states in natural order so that forward and backward may split them over lanes differently
     if (p.ckpt != nullptr) {
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         if (rk[k] < rows_valid) {
-          float* dst = p.ckpt + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + t) * NP + q * NS;
-          if (NS == 4) {
-            *reinterpret_cast<float4*>(dst) = make_float4(h[k][0], h[k][1 % NS], h[k][2 % NS], h[k][3 % NS]);
-          } else {
+          float* dst = p.ckpt + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + t) * p.N;
 #pragma unroll
-            for (int j = 0; j < NS; ++j) dst[j] = h[k][j];
-          }
+          for (int j = 0; j < NS; ++j)
+            if (j * R + q < p.N) dst[j * R + q] = h[k][j];
         }
       }
     }
