@@ -41,7 +41,8 @@ struct BwdShape {
   static constexpr int NPB = (NP + 7) / 8 * 8;
   static constexpr int CNT = 2 * NS * 4;                      // dB/dC partials per thread and 4-position group
   static constexpr int stage_floats = (3 * CH + 2 * NPB) * BLT;
-  static constexpr int slab_floats = 2 * NP * kHalf;          // one warp, one half tile: [dB | dC][NP][16]
+  static constexpr int kSlabPitch = kHalf + 4;               // 20 floats: consecutive states land in different bank groups
+  static constexpr int slab_floats = 2 * NP * kSlabPitch;     // one warp, one half tile: [dB | dC][NP][16 (+4)]
   static constexpr int hs_floats = (BLT / 4) * RPT * 32 * NS; // one warp: state at the end of each group
   static constexpr size_t smem_bytes =
       (size_t)(kBwdStages * stage_floats + kBwdConsumerWarps * (2 * slab_floats + hs_floats) + 2 * CH) * 4 + 128 + 1024;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void store_states(float* __restrict__ dst, const floa
 }
 
 template <int NS, int R, int RPT>
-__global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams p, const __grid_constant__ TmaMaps maps) {
+__global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanParams p, const __grid_constant__ TmaMaps maps) {
   using S = BwdShape<NS, R, RPT>;
   constexpr int CH = S::CH, NP = S::NP, NPB = S::NPB, RL = S::RL, RPW = S::RPW, CNT = S::CNT, NW = kBwdConsumerWarps;
   extern __shared__ __align__(16) float smem_raw[];
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams 
     // fold the NW per-warp slabs of half tile `hc` (processing order) and send the sums to dB / dC
     auto flush_half = [&](int hc) {
       const int buf = hc & 1;
-      mbar_wait(&slab_full[buf], (hc >> 1) & 1);
+      mbar_wait_relaxed(&slab_full[buf], (hc >> 1) & 1);
       const int it = hc >> 1, t = ntiles - 1 - it;              // tile index along the scan
       const int half = (hc & 1) ? 0 : 1;                        // the upper half of a tile is processed first
       const int l_base = t * BLT + half * kHalf;
@@ -171,10 +172,10 @@ __global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams 
       for (int i = lane; i < 2 * NP * (kHalf / 4); i += 32) {
         const int which = i / (NP * (kHalf / 4)), rem = i - which * NP * (kHalf / 4);
         const int n = rem / (kHalf / 4), c = (rem - n * (kHalf / 4)) * 4;
-        float4 acc = *reinterpret_cast<const float4*>(base + (which * NP + n) * kHalf + c);
+        float4 acc = *reinterpret_cast<const float4*>(base + (which * NP + n) * S::kSlabPitch + c);
 #pragma unroll
         for (int w = 1; w < NW; ++w) {
-          const float4 v = *reinterpret_cast<const float4*>(base + w * S::slab_floats + (which * NP + n) * kHalf + c);
+          const float4 v = *reinterpret_cast<const float4*>(base + w * S::slab_floats + (which * NP + n) * S::kSlabPitch + c);
           acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         const int l = l_base + c;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams 
       const int t = ntiles - 1 - it;
       const int s = it % kBwdStages, use = it / kBwdStages;
       const int l0 = t * BLT, len = min(BLT, L - l0);
-      mbar_wait(&empty[s], (use & 1) ^ 1);
+      mbar_wait_relaxed(&empty[s], (use & 1) ^ 1);
       if (tma) {
         if (lane == 0) {
           mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_floats * 4);
@@ -248,6 +249,16 @@ __global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams 
     }
   }
 
+  float h0_next[RPT][NS];     // checkpoint (state before the tile) of the tile processed next
+#pragma unroll
+  for (int k = 0; k < RPT; ++k)
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int n = j * R + q;
+      h0_next[k][j] = (ntiles > 1 && rk[k] < rows_valid && n < p.N)
+                          ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + (ntiles - 2)) * p.N + n) : 0.f;
+    }
+
   for (int it = 0; it < ntiles; ++it) {
     const int t = ntiles - 1 - it;
     const int s = it % kBwdStages, use = it / kBwdStages;
@@ -275,17 +286,18 @@ __global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams 
     __syncwarp();
 
     // ---- (1) forward recompute of h over the tile from the checkpoint at the end of the previous chunk;
-    //          only the state after each group of 4 positions is kept (shared memory, private to the thread) ----
+    //          only the state after each group of 4 positions is kept (shared memory, private to the thread).
+    //          The checkpoint of the tile processed NEXT is fetched now, a whole tile ahead of its use. ----
     float h0[RPT][NS];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
+    for (int k = 0; k < RPT; ++k)
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
+        h0[k][j] = h0_next[k][j];
         const int n = j * R + q;
-        h0[k][j] = (t > 0 && rk[k] < rows_valid && n < p.N)
-                       ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + (t - 1)) * p.N + n) : 0.f;
+        h0_next[k][j] = (t > 1 && rk[k] < rows_valid && n < p.N)
+                            ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + (t - 2)) * p.N + n) : 0.f;
       }
-    }
     {
       float h[RPT][NS];
 #pragma unroll
@@ -419,11 +431,21 @@ __global__ void __launch_bounds__(kBwdThreads) scan_bwd_kernel(const ScanParams 
           const int slice = rl / REP;
           float* slab = s_slab + ((size_t)buf * NW + warp) * S::slab_floats;
           const int ch = c & (kHalf - 1);
+          if constexpr (PER >= 4) {      // each lane holds whole 4-position vectors of one (tensor, state): vector stores
 #pragma unroll
-          for (int i = 0; i < PER; ++i) {
-            const int vi = slice * PER + i;                     // index into [dB | dC][NS][4]
-            const int which = vi / (NS * 4), j = (vi / 4) % NS, e = vi & 3;
-            slab[(which * NP + j * R + q) * kHalf + ch + e] = part[i];
+            for (int i = 0; i < PER; i += 4) {
+              const int vi = slice * PER + i;                   // index into [dB | dC][NS][4]
+              const int which = vi / (NS * 4), j = (vi / 4) % NS;
+              *reinterpret_cast<float4*>(slab + (which * NP + j * R + q) * S::kSlabPitch + ch) =
+                  make_float4(part[i], part[i + 1], part[i + 2], part[i + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+              const int vi = slice * PER + i;
+              const int which = vi / (NS * 4), j = (vi / 4) % NS, e = vi & 3;
+              slab[(which * NP + j * R + q) * S::kSlabPitch + ch + e] = part[i];
+            }
           }
         }
         if (gi == BLT / 8 || gi == 0) {                        // last group of a half: hand the slab to the producer

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
     for (int t = 0; t < ntiles; ++t) {
       const int s = t % STAGES, use = t / STAGES;
       const int l0 = t * LT, len = min(LT, L - l0);
-      mbar_wait(&empty[s], (use & 1) ^ 1);            // passes immediately the first time a stage is used
+      mbar_wait_relaxed(&empty[s], (use & 1) ^ 1);    // passes immediately the first time a stage is used
       if (tma) {
         if (lane == 0) {
           mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_floats * 4);
