@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanPara
   const int q = lane % R, rl = lane / R;
   float* my_hs = s_hs + warp * S::hs_floats;
   int rk[RPT];
-  float A1[RPT][NS], A2[RPT][NS], carry[RPT][NS], dA[RPT][NS], dDacc[RPT], dbacc[RPT];
+  float A1[RPT][NS], A2[RPT][NS], carry[RPT][NS], dDacc[RPT], dbacc[RPT];
+  float2 dA2[RPT][NS];     // dA accumulated separately on even / odd positions (packed FFMA2), summed at the end
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
     rk[k] = warp * RPW + k * RL + rl;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanPara
       A1[k][j] = (rk[k] < rows_valid && n < p.N) ? p.A[(int64_t)(d0 + rk[k]) * p.A_ld + n] : 0.f;
       A2[k][j] = A1[k][j] * kLog2e;
       carry[k][j] = 0.f;     // a_(l+1) * g_(l+1), zero past the end of the sequence
-      dA[k][j] = 0.f;
+      dA2[k][j] = make_float2(0.f, 0.f);
     }
   }
 
@@ -341,51 +342,64 @@ __global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanPara
         Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
         Cv[j] = *reinterpret_cast<const float4*>(s_C + swz(j * R + q, c));
       }
-      float part[CNT];     // [dB | dC][NS][4], summed over this thread's RPT rows
+      // dB / dC partials [NS][2 position pairs], summed over this thread's RPT rows; packed f32x2 arithmetic throughout:
+      // only the two recurrences (h forward, g backward) are inherently scalar chains
+      float2 pB[NS][2], pC[NS][2];
 #pragma unroll
-      for (int i = 0; i < CNT; ++i) part[i] = 0.f;
+      for (int j = 0; j < NS; ++j) { pB[j][0] = pB[j][1] = pC[j][0] = pC[j][1] = make_float2(0.f, 0.f); }
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
         const int o = swz(rk[k], c);
         const float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
         const float4 uv = *reinterpret_cast<const float4*>(s_u + o);
         const float4 dy = *reinterpret_cast<const float4*>(s_dy + o);
-        const float dl[4] = {dv.x, dv.y, dv.z, dv.w};
-        const float dye[4] = {dy.x, dy.y, dy.z, dy.w};
-        const float dU[4] = {dv.x * uv.x, dv.y * uv.y, dv.z * uv.z, dv.w * uv.w};
+        const float2 dl01 = make_float2(dv.x, dv.y), dl23 = make_float2(dv.z, dv.w);
+        const float2 dy01 = make_float2(dy.x, dy.y), dy23 = make_float2(dy.z, dy.w);
+        const float2 dU01 = __fmul2_rn(dl01, make_float2(uv.x, uv.y)), dU23 = __fmul2_rn(dl23, make_float2(uv.z, uv.w));
         float hin[NS];
         if (gi > 0) load_states<NS>(my_hs + (((gi - 1) * RPT + k) * 32 + lane) * NS, hin);
         else {
 #pragma unroll
           for (int j = 0; j < NS; ++j) hin[j] = h0[k][j];
         }
-        float sB[4] = {0.f, 0.f, 0.f, 0.f}, sA[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 sB01 = make_float2(0.f, 0.f), sB23 = sB01, sA01 = sB01, sA23 = sB01;
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          const float Bj[4] = {Bv[j].x, Bv[j].y, Bv[j].z, Bv[j].w};
-          const float Cj[4] = {Cv[j].x, Cv[j].y, Cv[j].z, Cv[j].w};
-          float a[4], hh[4];
-          float hprev = hin[j];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            a[e] = ex2f(dl[e] * A2[k][j]);
-            hh[e] = fmaf(a[e], hprev, dU[e] * Bj[e]);
-            hprev = hh[e];
-          }
-          float cj = carry[k][j];
-#pragma unroll
-          for (int e = 3; e >= 0; --e) {
-            const float gj = fmaf(Cj[e], dye[e], cj);
-            part[(0 * NS + j) * 4 + e] = fmaf(gj, dU[e], part[(0 * NS + j) * 4 + e]);
-            part[(1 * NS + j) * 4 + e] = fmaf(dye[e], hh[e], part[(1 * NS + j) * 4 + e]);
-            sB[e] = fmaf(gj, Bj[e], sB[e]);
-            cj = gj * a[e];
-            const float w = cj * (e > 0 ? hh[e - 1] : hin[j]);
-            sA[e] = fmaf(w, A1[k][j], sA[e]);
-            dA[k][j] = fmaf(w, dl[e], dA[k][j]);
-          }
-          carry[k][j] = cj;
+          const float2 B01 = make_float2(Bv[j].x, Bv[j].y), B23 = make_float2(Bv[j].z, Bv[j].w);
+          const float2 A2p = make_float2(A2[k][j], A2[k][j]), A1p = make_float2(A1[k][j], A1[k][j]);
+          // re-expand a = exp(delta A) and h over the 4 positions
+          const float2 e01 = __fmul2_rn(dl01, A2p), e23 = __fmul2_rn(dl23, A2p);
+          const float a0 = ex2f(e01.x), a1 = ex2f(e01.y), a2 = ex2f(e23.x), a3 = ex2f(e23.y);
+          const float2 bu01 = __fmul2_rn(dU01, B01), bu23 = __fmul2_rn(dU23, B23);
+          const float hh0 = fmaf(a0, hin[j], bu01.x);
+          const float hh1 = fmaf(a1, hh0, bu01.y);
+          const float hh2 = fmaf(a2, hh1, bu23.x);
+          const float hh3 = fmaf(a3, hh2, bu23.y);
+          // adjoint chain, last position first: g_e = C_e dy_e + a_(e+1) g_(e+1);  t_e = a_e g_e
+          const float g3 = fmaf(Cv[j].w, dy.w, carry[k][j]);
+          const float t3 = g3 * a3;
+          const float g2 = fmaf(Cv[j].z, dy.z, t3);
+          const float t2 = g2 * a2;
+          const float g1 = fmaf(Cv[j].y, dy.y, t2);
+          const float t1 = g1 * a1;
+          const float g0 = fmaf(Cv[j].x, dy.x, t1);
+          const float t0 = g0 * a0;
+          carry[k][j] = t0;
+          const float2 g01 = make_float2(g0, g1), g23 = make_float2(g2, g3);
+          pB[j][0] = __ffma2_rn(g01, dU01, pB[j][0]);
+          pB[j][1] = __ffma2_rn(g23, dU23, pB[j][1]);
+          pC[j][0] = __ffma2_rn(dy01, make_float2(hh0, hh1), pC[j][0]);
+          pC[j][1] = __ffma2_rn(dy23, make_float2(hh2, hh3), pC[j][1]);
+          sB01 = __ffma2_rn(g01, B01, sB01);
+          sB23 = __ffma2_rn(g23, B23, sB23);
+          const float2 w01 = __fmul2_rn(make_float2(t0, t1), make_float2(hin[j], hh0));   // t_e h_(e-1)
+          const float2 w23 = __fmul2_rn(make_float2(t2, t3), make_float2(hh1, hh2));
+          sA01 = __ffma2_rn(w01, A1p, sA01);
+          sA23 = __ffma2_rn(w23, A1p, sA23);
+          dA2[k][j] = __ffma2_rn(w01, dl01, dA2[k][j]);
+          dA2[k][j] = __ffma2_rn(w23, dl23, dA2[k][j]);
         }
+        const float sB[4] = {sB01.x, sB01.y, sB23.x, sB23.y}, sA[4] = {sA01.x, sA01.y, sA23.x, sA23.y};
         float sums[8];     // [e][sB | sA]
 #pragma unroll
         for (int e = 0; e < 4; ++e) { sums[e * 2] = sB[e]; sums[e * 2 + 1] = sA[e]; }
@@ -420,6 +434,14 @@ __global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanPara
         }
       }
       // dB/dC: sum over the RL row lanes of the warp, then park the warp's totals in its slab for this half tile
+      float part[CNT];     // [dB | dC][NS][4]
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        part[(0 * NS + j) * 4 + 0] = pB[j][0].x; part[(0 * NS + j) * 4 + 1] = pB[j][0].y;
+        part[(0 * NS + j) * 4 + 2] = pB[j][1].x; part[(0 * NS + j) * 4 + 3] = pB[j][1].y;
+        part[(1 * NS + j) * 4 + 0] = pC[j][0].x; part[(1 * NS + j) * 4 + 1] = pC[j][0].y;
+        part[(1 * NS + j) * 4 + 2] = pC[j][1].x; part[(1 * NS + j) * 4 + 3] = pC[j][1].y;
+      }
       lane_reduce_scatter<RL, R, CNT>(part, rl);
       {
         const int hc = 2 * it + (gi >= BLT / 8 ? 0 : 1);       // half tiles in processing order
@@ -484,7 +506,7 @@ __global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanPara
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
         const int n = j * R + q;
-        if (n < p.N) dst[n] = dA[k][j];
+        if (n < p.N) dst[n] = dA2[k][j].x + dA2[k][j].y;
       }
       if (q == 0) { dst[p.N] = dd; dst[p.N + 1] = db; }
     }
