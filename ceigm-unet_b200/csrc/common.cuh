@@ -139,7 +139,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(200);
+    __nanosleep(1000);
   }
 }
 // global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned)
