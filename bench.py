@@ -66,8 +66,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe). The sampler is started
+    before the warm-up (nvidia-smi takes a few hundred ms to produce its first line); samples are time-stamped and the
+    ones inside the timed region are used, falling back to every sample of the run when the region was too short."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -76,12 +78,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,21 +93,23 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), [n for n, v in zip(names, f[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        used, scope = (inside, "timed region") if len(inside) >= 2 else (rows, "whole run (timed region shorter than the sampling period)")
+        sm = [r[1] for r in used]
+        reasons = sorted({n for r in used for n in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in used), default=None),
+                "samples": len(sm), "scope": scope, "reasons": reasons}
 
 
 def build_inputs(calls, device):
@@ -123,6 +128,7 @@ def build_inputs(calls, device):
 
 def run_ours(args, rank, world, local_rank):
     import ceigm_unet_b200 as pkg
+    from ceigm_unet_b200 import dist as D
     from ceigm_unet_b200.dropin import selective_scan_cuda_core as core
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (impl ours) needs a CUDA device: there is no CPU fallback")
@@ -151,29 +157,26 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize(device)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     # ---- timed region: K steps, device time via CUDA events on the launching (current) stream ----
     single_call = len(calls) == 1 and calls[0][0] == 1
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)] if single_call else None
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     pkg.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     e0.record()
     for i in range(args.steps):
         step(evs[i] if evs else None)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, time.time())
     launches = pkg.launch_count()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = D.max_over_ranks(e0.elapsed_time(e1), device)      # slowest rank's device time
     ms_per_step = ms / args.steps
     value = world * (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9
 
@@ -192,26 +195,38 @@ def run_ours(args, rank, world, local_rank):
                  "fwd_GBps": round(fwd_b / (fwd_ms * 1e-3) / 1e9, 1), "bwd_GBps": round(ach, 1),
                  "fwd_frac_of_peak": round(fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, 4)}
 
-    # ---- end to end: host buffers in pinned memory, H2D of every input and D2H of every result, each step ----
+    # ---- end to end: host buffers in pinned memory; every step copies every input host->device and every result
+    #      device->host. The batch is cut into chunks that are pipelined over two streams so that H2D, the scan
+    #      kernels and D2H of different chunks overlap (samples are independent; dA/dD/dbias are summed on the host).
     pinned = [(c, {k: v.pin_memory() for k, v in inp.items()}) for c, inp in host_sets]
     h2d = sum(c * sum(v.numel() * 4 for v in inp.values()) for c, inp in pinned)
+    streams = [torch.cuda.Stream(device) for _ in range(2)]
     res_host = {}
+    BATCHED = ("u", "delta", "B", "C", "dout")
 
     def e2e_step():
         d2h = 0
         for ci, (count, inp) in enumerate(pinned):
-            for _ in range(count):
-                t_ = {k: v.to(device, non_blocking=True) for k, v in inp.items()}
-                out, x = core.fwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"], True, 1)
-                grads = core.bwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"], t_["dout"],
-                                 x, True, 1)
-                outs = [out] + list(grads)
-                if ci not in res_host:
-                    res_host[ci] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-                for hbuf, o in zip(res_host[ci], outs):
-                    hbuf.copy_(o, non_blocking=True)
-                    d2h += o.numel() * o.element_size()
-        torch.cuda.synchronize(device)
+            nb = inp["u"].shape[0]
+            nchunk = 4 if nb >= 8 else 1
+            for rep in range(count):
+                for ch in range(nchunk):
+                    a, bnd = D.shard_batch(nb, ch, nchunk)
+                    st = streams[ch % 2]
+                    with torch.cuda.stream(st):
+                        t_ = {k: (v[a:bnd] if k in BATCHED else v).to(device, non_blocking=True) for k, v in inp.items()}
+                        out, x = core.fwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"], True, 1)
+                        grads = core.bwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"],
+                                         t_["dout"], x, True, 1)
+                        outs = [out] + list(grads)
+                        key = (ci, ch)
+                        if key not in res_host:
+                            res_host[key] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+                        for hbuf, o in zip(res_host[key], outs):
+                            hbuf.copy_(o, non_blocking=True)
+                            d2h += o.numel() * o.element_size()
+        for st in streams:
+            st.synchronize()
         return d2h
 
     d2h = e2e_step()
@@ -221,10 +236,8 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(dt_e2e, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = world * (fwd_b + bwd_b) * e2e_steps / float(dt_e2e.item()) / 1e9
+    dt_e2e = D.max_over_ranks(time.perf_counter() - t0, device)
+    e2e_val = world * (fwd_b + bwd_b) * e2e_steps / dt_e2e / 1e9
 
     line = {
         "metric": "selective-scan fwd+bwd algorithmic HBM GB/s", "value": round(value, 1), "unit": "GB/s",
@@ -237,10 +250,15 @@ def run_ours(args, rank, world, local_rank):
                    "alg_bytes_fwd": fwd_b, "alg_bytes_bwd": bwd_b, "per_gpu_batch": calls[0][1]},
         "frac_of_hbm_peak": round(value / world / peak, 4),
         "e2e": {"value": round(e2e_val, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "note": "pinned host buffers; every input copied in and every result copied out per step"},
+                "steps": e2e_steps, "note": "pinned host buffers; every input copied in and every result copied out per step; batch chunks pipelined over 2 streams"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
     line.update(extra)
+    # secondary ceilings for d_state > 1: one MUFU.EX2 per (row, position, state) forward, two backward,
+    # plus softplus; measured MUFU rate 16 lanes/clk/SM (tools/ubench/pipes.cu: 4.6e12 ex2/s at 1.965 GHz)
+    ex2 = sum(c * b * dt * L * (3 * n + 6) for c, b, dt, L, n, g in calls)
+    line["mufu_roofline"] = {"ex2_per_step": ex2, "peak_ex2_per_s": 4.6e12, "floor_ms": round(ex2 / 4.6e12 * 1e3, 4),
+                             "frac": round(ex2 / 4.6e12 * 1e3 / ms_per_step, 4)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port(args.workload)
     return line
@@ -330,7 +348,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -346,9 +364,8 @@ def main():
         return 0
 
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from ceigm_unet_b200 import dist as D
+        D.init_from_env("nccl")
     try:
         line = run_ours(args, rank, world, local_rank)
         if rank == 0:
