@@ -48,6 +48,11 @@ WORKLOADS = {
     # live GM-UNet census: per forward 20/24/48/12 calls on the four stages
     "gm_live": [(20, 24, 16, 3136, 1, 1), (24, 24, 32, 784, 1, 1), (48, 24, 87, 196, 1, 1), (12, 24, 112, 49, 1, 1)],
 }
+# single calls of the live regime, alone and with the 4 SS2Ds of a GroupMambaLayer grouped into one launch (G=4)
+for _i, (_c, _b, _d, _l, _n, _g) in enumerate(WORKLOADS["gm_live"], 1):
+    WORKLOADS[f"gm_s{_i}"] = [(1, _b, _d, _l, _n, _g)]
+    WORKLOADS[f"gm_s{_i}_g4"] = [(1, _b, 4 * _d, _l, _n, 4)]
+WORKLOADS["gm_s1_b64_512"] = [(1, 64, 64, 16384, 1, 4)]
 DEFAULT_WORKLOAD = "vm_d192"
 
 

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "scan_params.h"
@@ -11,6 +12,15 @@ namespace ss2d {
 cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_bwd_finalize(const ScanParams& p, float* dA, float* dD, float* dbias, cudaStream_t stream);
+cudaError_t scan_par_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
+cudaError_t scan_par_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
+
+// d_state == 1 (the live GM-UNet regime) runs the parallel-along-L kernels (scan_par.cu); SS2D_FORCE_SEQ=1 keeps the
+// row-sequential kernels for comparison.
+static bool use_par(const ScanParams& p) {
+  static const bool force_seq = getenv("SS2D_FORCE_SEQ") != nullptr;
+  return p.N == 1 && p.A_ld == 1 && !force_seq;
+}
 cudaError_t cross_scan_launch(const void* x, void* xs, int batch, int channels, int H, int W, int K, const int* dirs,
                               int dtype, cudaStream_t stream);
 cudaError_t cross_merge_launch(const void* ys, void* y, int batch, int channels, int H, int W, int K, const int* dirs,
@@ -146,7 +156,8 @@ int ss2d_scan_fwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
     p.ckpt = ckpt ? ckpt + ck_off : nullptr;
     p.last_state = last_state ? last_state + (d->last_state_interleaved ? 2 : 1) * n0 : nullptr;
     ck_off += round4(ckpt_floats_pass(d, n));
-    cudaError_t e = scan_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
+    cudaError_t e = use_par(p) ? scan_par_fwd_dispatch(p, static_cast<cudaStream_t>(stream))
+                               : scan_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e);
     ++g_launches;
   }
@@ -193,7 +204,7 @@ int ss2d_scan_bwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
     p.dB = dB + (size_t)n0 * d->seqlen;
     p.dC = dC + (size_t)n0 * d->seqlen;
     ck_off += round4(ckpt_floats_pass(d, n));
-    cudaError_t e = scan_bwd_dispatch(p, st);
+    cudaError_t e = use_par(p) ? scan_par_bwd_dispatch(p, st) : scan_bwd_dispatch(p, st);
     if (e != cudaSuccess) return cuda_fail(e);
     e = scan_bwd_finalize(p, dA + n0, dD, ddelta_bias, st);
     if (e != cudaSuccess) return cuda_fail(e);
