@@ -41,6 +41,40 @@ __device__ __forceinline__ void load_seg(const void* __restrict__ src, int dt, i
   }
 }
 
+// Fast path: fp32, contiguous traversal (forward or reversed), 16-byte aligned row, segment fully inside the row.
+// `base` points at the row's first element in memory; rev = traversal runs against memory order.
+template <int P>
+__device__ __forceinline__ void load_seg_fast(const float* __restrict__ base, int l, int L, bool rev, float* out) {
+  if (!rev) {
+#pragma unroll
+    for (int c = 0; c < P; c += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + l + c));
+      out[c] = v.x; out[c + 1] = v.y; out[c + 2] = v.z; out[c + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < P; c += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (L - 4 - (l + c))));
+      out[c] = v.w; out[c + 1] = v.z; out[c + 2] = v.y; out[c + 3] = v.x;
+    }
+  }
+}
+template <int P>
+__device__ __forceinline__ void store_seg_fast(float* __restrict__ base, int l, int L, bool rev, const float* v) {
+  if (!rev) {
+#pragma unroll
+    for (int c = 0; c < P; c += 4) *reinterpret_cast<float4*>(base + l + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < P; c += 4)
+      *reinterpret_cast<float4*>(base + (L - 4 - (l + c))) = make_float4(v[c + 3], v[c + 2], v[c + 1], v[c]);
+  }
+}
+// true when a row starting at element offset `ro` of an fp32 tensor can use the fast path
+__device__ __forceinline__ bool row_fast(const void* p, int64_t ro) {
+  return ((reinterpret_cast<uintptr_t>(p) + static_cast<uintptr_t>(ro) * 4) & 15) == 0;
+}
+
 template <int P>
 __device__ __forceinline__ void store_seg(void* __restrict__ dst, int dt, int64_t ro, int l, int l_end, const ScanOrder so,
                                           const float* v, bool accum) {
@@ -127,14 +161,32 @@ __global__ void __launch_bounds__(kParThreads) scan_par_fwd_kernel(const ScanPar
   const int64_t B_ro = (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
   const int64_t C_ro = (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
 
+  // one decision per thread: 128-bit unchecked accesses are possible for its rows (fp32, contiguous traversal, aligned)
+  const bool rev = so.reversed();
+  const bool fast_in = valid && p.io_dtype == SS2D_F32 && so.contiguous() && (L & 3) == 0 && row_fast(p.u, u_ro) &&
+                       row_fast(p.delta, dl_ro) && row_fast(p.Bm, B_ro) && row_fast(p.Cm, C_ro);
+  const bool fast_out = valid && p.out_dtype == SS2D_F32 && so.contiguous() && (L & 3) == 0 && !p.accum && p.out != nullptr &&
+                        row_fast(p.out, out_ro);
+  const float* fu = reinterpret_cast<const float*>(p.u) + u_ro;
+  const float* fd = reinterpret_cast<const float*>(p.delta) + dl_ro;
+  const float* fB = reinterpret_cast<const float*>(p.Bm) + B_ro;
+  const float* fC = reinterpret_cast<const float*>(p.Cm) + C_ro;
+
   float h_carry = 0.f;
   const int nchunks = (L + LC - 1) / LC;
   for (int c = 0; c < nchunks; ++c) {
     const int l0 = c * LC + t * P;
+    const bool full = l0 + P <= l_end;
     float dl[P], uu[P], bb[P];
-    load_seg<P>(p.delta, p.io_dtype, dl_ro, l0, l_end, so, dl);
-    load_seg<P>(p.u, p.io_dtype, u_ro, l0, l_end, so, uu);
-    load_seg<P>(p.Bm, p.io_dtype, B_ro, l0, l_end, so, bb);
+    if (fast_in && full) {
+      load_seg_fast<P>(fd, l0, L, rev, dl);
+      load_seg_fast<P>(fu, l0, L, rev, uu);
+      load_seg_fast<P>(fB, l0, L, rev, bb);
+    } else {
+      load_seg<P>(p.delta, p.io_dtype, dl_ro, l0, l_end, so, dl);
+      load_seg<P>(p.u, p.io_dtype, u_ro, l0, l_end, so, uu);
+      load_seg<P>(p.Bm, p.io_dtype, B_ro, l0, l_end, so, bb);
+    }
     // local scan from h = 0: hl = local state, pc = cumulative decay; beyond the end of the row the state is frozen
     float hl[P], pc[P];
     float h = 0.f, pm = 1.f;
@@ -152,10 +204,12 @@ __global__ void __launch_bounds__(kParThreads) scan_par_fwd_kernel(const ScanPar
     row_exclusive<T, true>(pm, h, t, r, s_agg[c & 1], Pex, Hex, Ptot, Htot);
     const float h_in = fmaf(Pex, h_carry, Hex);             // state entering this thread's first position
     float cc[P], y[P];
-    load_seg<P>(p.Cm, p.io_dtype, C_ro, l0, l_end, so, cc);
+    if (fast_in && full) load_seg_fast<P>(fC, l0, L, rev, cc);
+    else load_seg<P>(p.Cm, p.io_dtype, C_ro, l0, l_end, so, cc);
 #pragma unroll
     for (int i = 0; i < P; ++i) y[i] = fmaf(cc[i], fmaf(pc[i], h_in, hl[i]), Dd * uu[i]);
-    if (p.out != nullptr) store_seg<P>(p.out, p.out_dtype, out_ro, l0, l_end, so, y, p.accum != 0);
+    if (fast_out && full) store_seg_fast<P>(reinterpret_cast<float*>(p.out) + out_ro, l0, L, rev, y);
+    else if (p.out != nullptr) store_seg<P>(p.out, p.out_dtype, out_ro, l0, l_end, so, y, p.accum != 0);
     // chunk checkpoint every SS2D_CHUNK positions: the thread whose last position closes a chunk owns it
     if (p.ckpt != nullptr && valid && ((l0 + P) % SS2D_CHUNK) == 0) {
       const int idx = (l0 + P) / SS2D_CHUNK - 1;
@@ -172,7 +226,7 @@ __global__ void __launch_bounds__(kParThreads) scan_par_fwd_kernel(const ScanPar
 
 // ------------------------------------------------------------------------------------------------- backward
 template <int T>
-__global__ void __launch_bounds__(kParThreads) scan_par_bwd_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kParThreads, 2) scan_par_bwd_kernel(const ScanParams p) {
   using S = ParShape<T>;
   constexpr int P = 8, LC = T * P;
   __shared__ float s_agg[2][S::RT * S::WPR][2];
@@ -204,17 +258,36 @@ __global__ void __launch_bounds__(kParThreads) scan_par_bwd_kernel(const ScanPar
   float* dBrow = p.dB + (int64_t)(b * p.G + g) * p.A_ld * L;
   float* dCrow = p.dC + (int64_t)(b * p.G + g) * p.A_ld * L;
 
+  const bool rev = so.reversed();
+  const bool fast_io = valid && p.io_dtype == SS2D_F32 && p.out_dtype == SS2D_F32 && so.contiguous() && (L & 3) == 0 &&
+                       !p.accum && row_fast(p.u, u_ro) && row_fast(p.delta, dl_ro) && row_fast(p.dout, dy_ro) &&
+                       row_fast(p.Bm, B_ro) && row_fast(p.Cm, C_ro) && row_fast(p.du, du_ro) && row_fast(p.ddelta, dl_ro);
+  const float* fu = reinterpret_cast<const float*>(p.u) + u_ro;
+  const float* fd = reinterpret_cast<const float*>(p.delta) + dl_ro;
+  const float* fy = reinterpret_cast<const float*>(p.dout) + dy_ro;
+  const float* fB = reinterpret_cast<const float*>(p.Bm) + B_ro;
+  const float* fC = reinterpret_cast<const float*>(p.Cm) + C_ro;
+
   float t_carry = 0.f;          // a_l g_l of the first position of the chunk after this one
   float accA = 0.f, accD = 0.f, accb = 0.f;
   const int nchunks = (L + LC - 1) / LC;
   for (int c = nchunks - 1; c >= 0; --c) {
     const int l0 = c * LC + t * P;
+    const bool full = l0 + P <= l_end;
     float dl[P], uu[P], bb[P], cc[P], dy[P];
-    load_seg<P>(p.delta, p.io_dtype, dl_ro, l0, l_end, so, dl);
-    load_seg<P>(p.u, p.io_dtype, u_ro, l0, l_end, so, uu);
-    load_seg<P>(p.dout, p.out_dtype, dy_ro, l0, l_end, so, dy);
-    load_seg<P>(p.Bm, p.io_dtype, B_ro, l0, l_end, so, bb);
-    load_seg<P>(p.Cm, p.io_dtype, C_ro, l0, l_end, so, cc);
+    if (fast_io && full) {
+      load_seg_fast<P>(fd, l0, L, rev, dl);
+      load_seg_fast<P>(fu, l0, L, rev, uu);
+      load_seg_fast<P>(fy, l0, L, rev, dy);
+      load_seg_fast<P>(fB, l0, L, rev, bb);
+      load_seg_fast<P>(fC, l0, L, rev, cc);
+    } else {
+      load_seg<P>(p.delta, p.io_dtype, dl_ro, l0, l_end, so, dl);
+      load_seg<P>(p.u, p.io_dtype, u_ro, l0, l_end, so, uu);
+      load_seg<P>(p.dout, p.out_dtype, dy_ro, l0, l_end, so, dy);
+      load_seg<P>(p.Bm, p.io_dtype, B_ro, l0, l_end, so, bb);
+      load_seg<P>(p.Cm, p.io_dtype, C_ro, l0, l_end, so, cc);
+    }
     // state entering the chunk: checkpoint written by the forward at the end of the previous SS2D_CHUNK block
     const float h_chunk = (c > 0 && valid)
                               ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d) * p.nck + (c * LC) / SS2D_CHUNK - 1) * p.N) : 0.f;
@@ -276,8 +349,13 @@ __global__ void __launch_bounds__(kParThreads) scan_par_bwd_kernel(const ScanPar
         accb += dd;
       }
     }
-    store_seg<P>(p.du, p.io_dtype, du_ro, l0, l_end, so, dub, p.accum != 0);
-    store_seg<P>(p.ddelta, p.io_dtype, dl_ro, l0, l_end, so, ddl, p.accum != 0);
+    if (fast_io && full) {
+      store_seg_fast<P>(reinterpret_cast<float*>(p.du) + du_ro, l0, L, rev, dub);
+      store_seg_fast<P>(reinterpret_cast<float*>(p.ddelta) + dl_ro, l0, L, rev, ddl);
+    } else {
+      store_seg<P>(p.du, p.io_dtype, du_ro, l0, l_end, so, dub, p.accum != 0);
+      store_seg<P>(p.ddelta, p.io_dtype, dl_ro, l0, l_end, so, ddl, p.accum != 0);
+    }
     t_carry = fmaf(Qtot, t_carry, Ttot);
     // ---- dB / dC: sum over the rows of this CTA, then one (vector) reduction per 4 positions to global memory ----
 #pragma unroll
@@ -345,6 +423,11 @@ static cudaError_t launch_par_fwd(const ScanParams& p, cudaStream_t stream) {
 template <int T>
 static cudaError_t launch_par_bwd(const ScanParams& p, cudaStream_t stream) {
   dim3 grid((p.dpg + ParShape<T>::RT - 1) / ParShape<T>::RT, p.G, p.batch);
+  static bool configured = false;
+  if (!configured) {   // 16.6 KB of static shared memory per CTA: ask for a carve-out that fits several CTAs per SM
+    cudaFuncSetAttribute(scan_par_bwd_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    configured = true;
+  }
   scan_par_bwd_kernel<T><<<grid, kParThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
