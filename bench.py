@@ -264,13 +264,65 @@ def run_ours(args, rank, world, local_rank):
     ex2 = sum(c * b * dt * L * (3 * n + 6) for c, b, dt, L, n, g in calls)
     line["mufu_roofline"] = {"ex2_per_step": ex2, "peak_ex2_per_s": 4.6e12, "floor_ms": round(ex2 / 4.6e12 * 1e3, 4),
                              "frac": round(ex2 / 4.6e12 * 1e3 / ms_per_step, 4)}
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["other_workloads"] = other_workloads(core, device, peak, exclude=args.workload)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port(args.workload)
     return line
 
 
-def cpu_baseline_port(workload, sample_batch=4):
-    """The C oracle (oracle/scan_oracle.c, OpenMP, f64 accumulate) on a bounded sample of the same workload."""
+def graph_time_ms(core, sets, iters=10, with_bwd=True):
+    """GPU time of one step (all calls) replayed from a CUDA graph: no host launch overhead between kernels."""
+    def run():
+        for count, t in sets:
+            for _ in range(count):
+                out, x = core.fwd(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], t["delta_bias"], True, 1)
+                if with_bwd:
+                    core.bwd(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], t["delta_bias"], t["dout"], x, True, 1)
+    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        run()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            run()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        g.replay()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def other_workloads(core, device, peak, exclude):
+    """Context numbers in the same run (not the headline): the live GM-UNet regime (d_state = 1; the scan calls of one
+    224^2 batch-24 training step, and the 512^2 batch-64 stage-1 shape of config 5) and two more config-4 points.
+    Each is one CUDA-graph replay of fwd+bwd, median of 10."""
+    out = []
+    for name in ("gm_live", "gm_s1_g4", "gm_s1_b64_512", "vm_d96", "vm_d384"):
+        if name == exclude:
+            continue
+        calls = WORKLOADS[name]
+        sets = [(c, {k: v.to(device) for k, v in inp.items()}) for c, inp in build_inputs(calls, device)]
+        fb, bb = alg_bytes(calls)
+        ms_f = graph_time_ms(core, sets, with_bwd=False)
+        ms = graph_time_ms(core, sets, with_bwd=True)
+        rec = {"workload": name, "calls_per_step": [list(c) for c in calls], "fwd_ms": round(ms_f, 4),
+               "fwd_bwd_ms": round(ms, 4), "fwd_GBps": round(fb / ms_f / 1e6, 1), "fwd_bwd_GBps": round((fb + bb) / ms / 1e6, 1),
+               "frac_of_hbm_peak": round((fb + bb) / ms / 1e6 / peak, 4), "timing": "CUDA graph replay"}
+        if name == "gm_live":
+            rec["scan_only_slices_per_s"] = round(calls[0][1] / (ms * 1e-3), 1)
+        out.append(rec)
+        del sets
+        torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline_port(workload, sample_batch=8, min_seconds=10.0):
+    """The C oracle (oracle/scan_oracle.c, OpenMP over rows, f64 accumulate) on a bounded sample of the same workload:
+    fwd+bwd on `sample_batch` samples of the largest call, repeated until at least `min_seconds` of CPU work."""
     from oracle import c_oracle
     calls = WORKLOADS[workload]
     count, b, dt, L, n, g = max(calls, key=lambda c: c[0] * c[1] * c[2] * c[3] * c[4])
@@ -282,15 +334,19 @@ def cpu_baseline_port(workload, sample_batch=4):
     u, dl = torch.randn(sb, dt, L, generator=gen).numpy(), (0.5 * torch.rand(sb, dt, L, generator=gen)).numpy()
     dy = torch.randn(sb, dt, L, generator=gen).numpy()
     c_oracle.scan_fwd(u[:1], dl[:1], A, Bm[:1], Cm[:1], Dv, bias, True)          # warm-up (page-in, thread pool)
-    t0 = time.perf_counter()
-    c_oracle.scan_fwd(u, dl, A, Bm, Cm, Dv, bias, True, acc="f64")
-    c_oracle.scan_bwd(u, dl, A, Bm, Cm, Dv, bias, dy, True, acc="f64")
-    dt_s = time.perf_counter() - t0
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        c_oracle.scan_fwd(u, dl, A, Bm, Cm, Dv, bias, True, acc="f64")
+        c_oracle.scan_bwd(u, dl, A, Bm, Cm, Dv, bias, dy, True, acc="f64")
+        reps += 1
+        dt_s = time.perf_counter() - t0
+        if dt_s >= min_seconds or reps >= 200:
+            break
     fwd_b, bwd_b = alg_bytes([(1, sb, dt, L, n, g)])
-    return {"value": round((fwd_b + bwd_b) / dt_s / 1e9, 4), "unit": "GB/s", "cores": c_oracle.num_threads(),
+    return {"value": round(reps * (fwd_b + bwd_b) / dt_s / 1e9, 4), "unit": "GB/s", "cores": c_oracle.num_threads(),
             "kind": "port", "seconds": round(dt_s, 2),
             "sample": f"C oracle (OpenMP) fwd+bwd on batch {sb} of {b} of the largest call of '{workload}' "
-                      f"(Dt={dt}, L={L}, N={n}, G={g})"}
+                      f"(Dt={dt}, L={L}, N={n}, G={g}), {reps} repetitions"}
 
 
 def run_reference(args):
@@ -358,6 +414,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_workloads context block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
