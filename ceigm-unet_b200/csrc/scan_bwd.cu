@@ -97,7 +97,7 @@ __device__ __forceinline__ void store_states(float* __restrict__ dst, const floa
 }
 
 template <int NS, int R, int RPT>
-__global__ void __launch_bounds__(kBwdThreads, 3) scan_bwd_kernel(const ScanParams p, const __grid_constant__ TmaMaps maps) {
+__global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel(const ScanParams p, const __grid_constant__ TmaMaps maps) {
   using S = BwdShape<NS, R, RPT>;
   constexpr int CH = S::CH, NP = S::NP, NPB = S::NPB, RL = S::RL, RPW = S::RPW, CNT = S::CNT, NW = kBwdConsumerWarps;
   extern __shared__ __align__(16) float smem_raw[];
@@ -551,7 +551,16 @@ cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream) {
   if (N <= 2) return launch_bwd<2, 1, 1>(p, stream);
   if (N <= 4) return launch_bwd<2, 2, 1>(p, stream);
   if (N <= 8) return launch_bwd<2, 4, 2>(p, stream);
-  if (N <= 16) return launch_bwd<2, 8, 2>(p, stream);
+  if (N <= 16) {
+    // Two rows per thread amortise the B/C loads and the dB/dC row reduction (best on big grids); one row per thread
+    // needs fewer registers / shared memory (4 CTAs per SM instead of 3) and halves the CTA size, which wins when the
+    // two-row grid would not fill ~2.5 waves (measured on vm_d96 / vm_d192 / vm_d384, B200).
+    static const int forced = getenv("SS2D_BWD_RPT") ? atoi(getenv("SS2D_BWD_RPT")) : 0;     // tuning knob
+    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    const long ctas2 = (long)((p.dpg + 31) / 32) * p.G * p.batch;
+    const int rpt = forced ? forced : (ctas2 * 2 < 5L * 3 * sms ? 1 : 2);
+    return rpt == 1 ? launch_bwd<2, 8, 1>(p, stream) : launch_bwd<2, 8, 2>(p, stream);
+  }
   return launch_bwd<4, 8, 1>(p, stream);
 }
 
