@@ -176,6 +176,17 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
 constexpr int kTileL = 32;
 __device__ __forceinline__ int swz(int r, int c) { return r * kTileL + ((((c >> 2) ^ r) & 7) << 2) + (c & 3); }
 
+// Tile accessors in SCAN coordinates. When a reversed traversal (direction 3) is staged by TMA the tile holds the 32
+// positions in MEMORY order, i.e. mirrored: scan column c lives at tile column 31 - c. rev selects that mirror.
+__device__ __forceinline__ int swz1(int r, int c, bool rev) { return swz(r, rev ? kTileL - 1 - c : c); }
+__device__ __forceinline__ float4 tile_ld4(const float* tile, int r, int c, bool rev) {   // scan columns c..c+3, c % 4 == 0
+  const float4 v = *reinterpret_cast<const float4*>(tile + swz(r, rev ? kTileL - 4 - c : c));
+  return rev ? make_float4(v.w, v.z, v.y, v.x) : v;
+}
+__device__ __forceinline__ void tile_st4(float* tile, int r, int c, bool rev, float4 v) {
+  *reinterpret_cast<float4*>(tile + swz(r, rev ? kTileL - 4 - c : c)) = rev ? make_float4(v.w, v.z, v.y, v.x) : v;
+}
+
 __device__ __forceinline__ float& f4_at(float4& v, int e) { return reinterpret_cast<float*>(&v)[e]; }
 
 }  // namespace ss2d

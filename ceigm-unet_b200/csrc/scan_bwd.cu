@@ -19,6 +19,7 @@
 //   * dA, dD, d(delta_bias) leave through a per-batch partial buffer and a deterministic second pass.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "scan_params.h"
 #include "scan_tile.cuh"
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
   ScanOrder so;
   so.dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
   so.H = p.H; so.W = p.W; so.L = L;
-  const bool tma = p.tma_ok && (so.dir == 0 || so.dir == 1);
+  const bool tma = p.tma_ok && so.contiguous();          // SCAN layout, directions 1 and 3
+  const bool rev = tma && so.reversed();                 // TMA-staged tiles of a reversed traversal are mirrored
   const int ntiles = (L + BLT - 1) / BLT;
 
   for (int r = tid; r < CH; r += kBwdThreads) {
@@ -207,12 +209,13 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
       mbar_wait_relaxed(&empty[s], (use & 1) ^ 1);
       if (tma) {
         if (lane == 0) {
+          const int m0 = rev ? L - l0 - BLT : l0;      // memory offset of the tile (may be < 0: zero-filled by TMA)
           mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_floats * 4);
-          tma_load_3d(st_u(s), &maps.u, l0, urow0, b, &full[s]);
-          tma_load_3d(st_dl(s), &maps.dl, l0, d0, b, &full[s]);
-          tma_load_3d(st_dy(s), &maps.dy, l0, urow0, b, &full[s]);
-          tma_load_4d(st_B(s), &maps.B, l0, 0, g, b, &full[s]);
-          tma_load_4d(st_C(s), &maps.C, l0, 0, g, b, &full[s]);
+          tma_load_3d(st_u(s), &maps.u, m0, urow0, b, &full[s]);
+          tma_load_3d(st_dl(s), &maps.dl, m0, d0, b, &full[s]);
+          tma_load_3d(st_dy(s), &maps.dy, m0, urow0, b, &full[s]);
+          tma_load_4d(st_B(s), &maps.B, m0, 0, g, b, &full[s]);
+          tma_load_4d(st_C(s), &maps.C, m0, 0, g, b, &full[s]);
         }
       } else {
         stage_rows<BLT, BLT>(st_u(s), p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so, lane, 32);
@@ -260,6 +263,9 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
                           ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + rk[k]) * p.nck + (ntiles - 2)) * p.N + n) : 0.f;
     }
 
+  // the tile loop is instantiated twice so that the mirror of reversed traversals costs nothing at run time
+  auto consume = [&](auto REV) {
+    constexpr bool REVV = decltype(REV)::value;
   for (int it = 0; it < ntiles; ++it) {
     const int t = ntiles - 1 - it;
     const int s = it % kBwdStages, use = it / kBwdStages;
@@ -272,9 +278,8 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
     mbar_wait(&full[s], use & 1);
     // activate delta for this warp's own rows, in place
     for (int i = lane; i < RPW * (BLT / 4); i += 32) {
-      const int r = warp * RPW + i / (BLT / 4), c = (i % (BLT / 4)) * 4;
-      const int o = swz(r, c);
-      float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
+      const int r = warp * RPW + i / (BLT / 4), c = (i % (BLT / 4)) * 4;    // c: scan column of the 4-group
+      float4 dv = tile_ld4(s_dl, r, c, REVV);
       const float bias = s_bias[r];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
         if (p.softplus) x = softplus20(x);
         f4_at(dv, e) = (c + e < len && r < rows_valid) ? x : 0.f;   // idle rows may hold a neighbour group's data (TMA)
       }
-      *reinterpret_cast<float4*>(s_dl + o) = dv;
+      tile_st4(s_dl, r, c, REVV, dv);
     }
     __syncwarp();
 
@@ -310,11 +315,11 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
         const int c = gi * 4;
         float4 Bv[NS];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
+        for (int j = 0; j < NS; ++j) Bv[j] = tile_ld4(s_B, j * R + q, c, REVV);
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const float4 dv = *reinterpret_cast<const float4*>(s_dl + swz(rk[k], c));
-          const float4 uv = *reinterpret_cast<const float4*>(s_u + swz(rk[k], c));
+          const float4 dv = tile_ld4(s_dl, rk[k], c, REVV);
+          const float4 uv = tile_ld4(s_u, rk[k], c, REVV);
 #pragma unroll
           for (int ep = 0; ep < 2; ++ep) {
             const float2 d2 = ep == 0 ? make_float2(dv.x, dv.y) : make_float2(dv.z, dv.w);
@@ -339,8 +344,8 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
       float4 Bv[NS], Cv[NS];
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
-        Cv[j] = *reinterpret_cast<const float4*>(s_C + swz(j * R + q, c));
+        Bv[j] = tile_ld4(s_B, j * R + q, c, REVV);
+        Cv[j] = tile_ld4(s_C, j * R + q, c, REVV);
       }
       // dB / dC partials [NS][2 position pairs], summed over this thread's RPT rows; packed f32x2 arithmetic throughout:
       // only the two recurrences (h forward, g backward) are inherently scalar chains
@@ -349,10 +354,9 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
       for (int j = 0; j < NS; ++j) { pB[j][0] = pB[j][1] = pC[j][0] = pC[j][1] = make_float2(0.f, 0.f); }
 #pragma unroll
       for (int k = 0; k < RPT; ++k) {
-        const int o = swz(rk[k], c);
-        const float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
-        const float4 uv = *reinterpret_cast<const float4*>(s_u + o);
-        const float4 dy = *reinterpret_cast<const float4*>(s_dy + o);
+        const float4 dv = tile_ld4(s_dl, rk[k], c, REVV);
+        const float4 uv = tile_ld4(s_u, rk[k], c, REVV);
+        const float4 dy = tile_ld4(s_dy, rk[k], c, REVV);
         const float2 dl01 = make_float2(dv.x, dv.y), dl23 = make_float2(dv.z, dv.w);
         const float2 dy01 = make_float2(dy.x, dy.y), dy23 = make_float2(dy.z, dy.w);
         const float2 dU01 = __fmul2_rn(dl01, make_float2(uv.x, uv.y)), dU23 = __fmul2_rn(dl23, make_float2(uv.z, uv.w));
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
             const int e = e0 + ee;
             const float sBe = sums[ee * 2 + 0];
             const float sAe = R == 8 ? other : sums[ee * 2 + 1];
-            const int idx = swz(rk[k], c + e);
+            const int idx = swz1(rk[k], c + e, REVV);
             const float de = s_dl[idx], uu = s_u[idx], dyv = s_dy[idx];
             const float du_out = fmaf(s_D[rk[k]], dyv, de * sBe);
             float ddl = fmaf(uu, sBe, sAe);
@@ -481,8 +485,8 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
     for (int i = lane; i < RPW * (BLT / 4); i += 32) {
       const int r = warp * RPW + i / (BLT / 4), c = (i % (BLT / 4)) * 4;
       if (r < rows_valid && c < len) {
-        const float4 a = *reinterpret_cast<const float4*>(s_dy + swz(r, c));
-        const float4 d = *reinterpret_cast<const float4*>(s_dl + swz(r, c));
+        const float4 a = tile_ld4(s_dy, r, c, REVV);
+        const float4 d = tile_ld4(s_dl, r, c, REVV);
         store_scan4(p.du, p.io_dtype, du_off(r), l0 + c, l0 + len, a, so, p.accum != 0);
         store_scan4(p.ddelta, p.io_dtype, dl_off(r), l0 + c, l0 + len, d, so, p.accum != 0);
       }
@@ -491,6 +495,9 @@ __global__ void __launch_bounds__(kBwdThreads, RPT == 1 ? 4 : 3) scan_bwd_kernel
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
+
+  };
+  if (rev) consume(std::true_type{}); else consume(std::false_type{});
 
   // ---- per-(batch, channel) partials of dA, dD, d(delta_bias) ----
 #pragma unroll
@@ -537,7 +544,7 @@ static cudaError_t launch_bwd(ScanParams p, cudaStream_t stream) {
     configured = true;
   }
   TmaMaps maps;
-  if (p.tma_ok && !(p.u_mod == 0 || p.u_mod == p.dpg)) p.tma_ok = 0;
+  if (p.tma_ok && !(p.u_mod == 0 || p.u_mod % p.dpg == 0)) p.tma_ok = 0;
   if (p.tma_ok && !make_scan_maps(p, S::CH, S::NPB, true, &maps)) p.tma_ok = 0;
   if (!p.tma_ok) memset(&maps, 0, sizeof(maps));
   dim3 grid((p.dpg + S::CH - 1) / S::CH, p.G, p.batch);

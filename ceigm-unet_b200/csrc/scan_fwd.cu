@@ -10,6 +10,7 @@
 // see DESIGN.md.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "scan_params.h"
 #include "scan_tile.cuh"
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
   ScanOrder so;
   so.dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
   so.H = p.H; so.W = p.W; so.L = L;
-  const bool tma = p.tma_ok && (so.dir == 0 || so.dir == 1);
+  const bool tma = p.tma_ok && so.contiguous();          // SCAN layout, directions 1 and 3
+  const bool rev = tma && so.reversed();                 // TMA-staged tiles of a reversed traversal are mirrored
   const int ntiles = (L + LT - 1) / LT;
 
   for (int r = tid; r < CH; r += kFwdThreads) {
@@ -102,11 +104,12 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
       mbar_wait_relaxed(&empty[s], (use & 1) ^ 1);    // passes immediately the first time a stage is used
       if (tma) {
         if (lane == 0) {
+          const int m0 = rev ? L - l0 - LT : l0;       // memory offset of the tile (may be < 0: zero-filled by TMA)
           mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_floats * 4);
-          tma_load_3d(st_u(s), &maps.u, l0, urow0, b, &full[s]);
-          tma_load_3d(st_dl(s), &maps.dl, l0, d0, b, &full[s]);
-          tma_load_4d(st_B(s), &maps.B, l0, 0, g, b, &full[s]);
-          tma_load_4d(st_C(s), &maps.C, l0, 0, g, b, &full[s]);
+          tma_load_3d(st_u(s), &maps.u, m0, urow0, b, &full[s]);
+          tma_load_3d(st_dl(s), &maps.dl, m0, d0, b, &full[s]);
+          tma_load_4d(st_B(s), &maps.B, m0, 0, g, b, &full[s]);
+          tma_load_4d(st_C(s), &maps.C, m0, 0, g, b, &full[s]);
         }
       } else {
         stage_rows<LT, LT>(st_u(s), p.u, p.io_dtype, u_off, CH, rows_valid, l0, len, so, lane, 32);
@@ -135,6 +138,9 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
     }
   }
 
+  // the tile loop is instantiated twice so that the mirror of reversed traversals costs nothing at run time
+  auto consume = [&](auto REV) {
+    constexpr bool REVV = decltype(REV)::value;
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % STAGES, use = t / STAGES;
     const int l0 = t * LT, len = min(LT, L - l0);
@@ -145,10 +151,9 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
     mbar_wait(&full[s], use & 1);
     // activate delta once per element, for this warp's own rows: delta = softplus(raw + bias); du = delta * u
     for (int i = lane; i < RPW * (LT / 4); i += 32) {
-      const int r = warp * RPW + i / (LT / 4), c = (i % (LT / 4)) * 4;
-      const int o = swz(r, c);
-      float4 dv = *reinterpret_cast<const float4*>(s_dl + o);
-      float4 uv = *reinterpret_cast<const float4*>(s_u + o);
+      const int r = warp * RPW + i / (LT / 4), c = (i % (LT / 4)) * 4;      // c: scan column of the 4-group
+      float4 dv = tile_ld4(s_dl, r, c, REVV);
+      float4 uv = tile_ld4(s_u, r, c, REVV);
       const float bias = s_bias[r];
       float4 du;
 #pragma unroll
@@ -159,8 +164,8 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         f4_at(dv, e) = live ? x : 0.f;
         f4_at(du, e) = live ? x * f4_at(uv, e) : 0.f;
       }
-      *reinterpret_cast<float4*>(s_dl + o) = dv;
-      *reinterpret_cast<float4*>(s_du + o) = du;
+      tile_st4(s_dl, r, c, REVV, dv);
+      tile_st4(s_du, r, c, REVV, du);
     }
     __syncwarp();
 
@@ -172,13 +177,13 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         float4 Bv[NS], Cv[NS];
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-          Bv[j] = *reinterpret_cast<const float4*>(s_B + swz(j * R + q, c));
-          Cv[j] = *reinterpret_cast<const float4*>(s_C + swz(j * R + q, c));
+          Bv[j] = tile_ld4(s_B, j * R + q, c, REVV);
+          Cv[j] = tile_ld4(s_C, j * R + q, c, REVV);
         }
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
-          const float4 dv = *reinterpret_cast<const float4*>(s_dl + swz(rk[k], c));
-          const float4 du = *reinterpret_cast<const float4*>(s_du + swz(rk[k], c));
+          const float4 dv = tile_ld4(s_dl, rk[k], c, REVV);
+          const float4 du = tile_ld4(s_du, rk[k], c, REVV);
           // two scan positions per packed instruction (FMUL2 / FFMA2 halve the issue slots of the products and of
           // the C.h accumulation); only the recurrence itself is inherently sequential and stays scalar
 #pragma unroll
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
         reduce_scatter_groups<R>(yacc[k], q);
         const int c = (i4 + q) * 4;                 // this lane owns group q of the R groups just finished
         if (p.out != nullptr && rk[k] < rows_valid && c < len) {
-          const float4 uv = *reinterpret_cast<const float4*>(s_u + swz(rk[k], c));
+          const float4 uv = tile_ld4(s_u, rk[k], c, REVV);
           const float Dd = s_D[rk[k]];
           const float4 y4 = make_float4(fmaf(Dd, uv.x, yacc[k][0]), fmaf(Dd, uv.y, yacc[k][1]),
                                         fmaf(Dd, uv.z, yacc[k][2]), fmaf(Dd, uv.w, yacc[k][3]));
@@ -235,6 +240,8 @@ __global__ void __launch_bounds__(kFwdThreads) scan_fwd_kernel(const ScanParams 
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
+  };
+  if (rev) consume(std::true_type{}); else consume(std::false_type{});
   if (p.last_state != nullptr) {
 #pragma unroll
     for (int k = 0; k < RPT; ++k)
@@ -261,7 +268,7 @@ static cudaError_t launch_fwd(ScanParams p, cudaStream_t stream) {
     configured = true;
   }
   TmaMaps maps;
-  if (p.tma_ok && !(p.u_mod == 0 || p.u_mod == p.dpg)) p.tma_ok = 0;
+  if (p.tma_ok && !(p.u_mod == 0 || p.u_mod % p.dpg == 0)) p.tma_ok = 0;
   if (p.tma_ok && !make_scan_maps(p, S::CH, S::NPB, false, &maps)) p.tma_ok = 0;
   if (!p.tma_ok) memset(&maps, 0, sizeof(maps));
   dim3 grid((p.dpg + S::CH - 1) / S::CH, p.G, p.batch);
