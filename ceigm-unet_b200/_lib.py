@@ -82,10 +82,11 @@ def lib() -> ctypes.CDLL:
     L.ss2d_cross_scan.restype = ctypes.c_int
     L.ss2d_cross_merge.argtypes = [vp, vp, i32, i32, i32, i32, i32, ip, i32, vp]
     L.ss2d_cross_merge.restype = ctypes.c_int
-    L.ss2d_out_gate_fwd.argtypes = [fp, i32, fp, fp, vp, i64, i32, vp, fp, i32, i32, i32, ctypes.c_float, i32, i32, vp]
+    L.ss2d_out_gate_fwd.argtypes = [fp, i32, fp, fp, vp, i64, i32, vp, fp, i32, i32, i32, ctypes.c_float, i32, i32, i32, i32,
+                                    ctypes.c_uint32, vp]
     L.ss2d_out_gate_fwd.restype = ctypes.c_int
     L.ss2d_out_gate_bwd.argtypes = [fp, i32, fp, fp, vp, i64, i32, vp, fp, fp, vp, i64, fp, fp, i32, i32, i32, i32,
-                                    i32, i32, vp]
+                                    i32, i32, i32, i32, ctypes.c_uint32, vp]
     L.ss2d_out_gate_bwd.restype = ctypes.c_int
     L.ss2d_out_gate_bwd_partials.argtypes = [i32, i32]
     L.ss2d_out_gate_bwd_partials.restype = i32

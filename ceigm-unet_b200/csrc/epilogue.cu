@@ -11,14 +11,22 @@ constexpr int kEpiTL = 32;         // pixels per tile
 constexpr int kEpiThreads = 256;
 constexpr int kEpiMaxDPT = 4;     // channels per thread in the backward: D <= 1024 (shared memory caps D near 860)
 
-__device__ __forceinline__ float merge_k(const float* __restrict__ ys, int K, int64_t plane_stride, int64_t off) {
+// Plane k of `ys` is stored either in natural pixel order (offset l = h W + w) or, when bit k of tmask is set, in
+// the pixel order of the TRANSPOSED image (offset w H + h): the column-major directions are scanned as row-major
+// traversals of a transposed input, and the transposition back happens here, inside the merge.
+struct PlaneIdx { int L, H, W; unsigned tmask; };
+__device__ __forceinline__ float merge_k(const float* __restrict__ ys, int K, int64_t plane_stride, int64_t row_off, int l,
+                                         const PlaneIdx pi) {
+  int lt = l;
+  if (pi.tmask) { const int h = l / pi.W, w = l - h * pi.W; lt = w * pi.H + h; }
+  auto at = [&](int k) { return __ldg(ys + k * plane_stride + row_off + (((pi.tmask >> k) & 1u) ? lt : l)); };
   if (K == 4) {   // association of CrossMerge.forward, csms6s.py:38-39
-    const float a = __ldg(ys + off) + __ldg(ys + 2 * plane_stride + off);
-    const float b = __ldg(ys + plane_stride + off) + __ldg(ys + 3 * plane_stride + off);
+    const float a = at(0) + at(2);
+    const float b = at(1) + at(3);
     return a + b;
   }
-  float acc = __ldg(ys + off);
-  for (int k = 1; k < K; ++k) acc += __ldg(ys + k * plane_stride + off);
+  float acc = at(0);
+  for (int k = 1; k < K; ++k) acc += at(k);
   return acc;
 }
 
@@ -30,13 +38,13 @@ __device__ __forceinline__ float silu_grad_f(float x) {
 
 // loads the merged tile y[d][pix] for pixels [l0, l0+32) of batch b into s_y[d * 33 + pix]
 __device__ __forceinline__ void load_merged_tile(float* s_y, const float* __restrict__ ys, int K, int b, int D, int L,
-                                                 int l0) {
+                                                 int l0, const PlaneIdx pi) {
   const int64_t plane = (int64_t)D * L;
   const float* base = ys + (int64_t)b * K * plane;
   for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
     const int d = i / kEpiTL, px = i - d * kEpiTL;
     const int l = l0 + px;
-    s_y[d * (kEpiTL + 1) + px] = l < L ? merge_k(base, K, plane, (int64_t)d * L + l) : 0.f;
+    s_y[d * (kEpiTL + 1) + px] = l < L ? merge_k(base, K, plane, (int64_t)d * L, l, pi) : 0.f;
   }
 }
 
@@ -44,14 +52,14 @@ __global__ void __launch_bounds__(kEpiThreads)
 out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict__ lnw, const float* __restrict__ lnb,
                     const void* __restrict__ z, int64_t z_rs, int z_act, void* __restrict__ out,
                     float* __restrict__ mean_rstd, int batch, int D, int L, float eps, int z_dtype, int out_dtype,
-                    int tiles_per_batch) {
+                    int tiles_per_batch, PlaneIdx pi) {
   extern __shared__ float s_y[];                 // [D][33]
   __shared__ float s_stat[kEpiTL][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
     const int b = tile / tiles_per_batch, l0 = (tile - b * tiles_per_batch) * kEpiTL;
     __syncthreads();
-    load_merged_tile(s_y, ys, K, b, D, L, l0);
+    load_merged_tile(s_y, ys, K, b, D, L, l0, pi);
     __syncthreads();
     // LayerNorm statistics per pixel (two-pass, fp32): warp w handles pixels w, w+8, ...
     for (int px = warp; px < kEpiTL; px += kEpiThreads / 32) {
@@ -96,7 +104,7 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
                     const void* __restrict__ z, int64_t z_rs, int z_act, const void* __restrict__ dout,
                     const float* __restrict__ mean_rstd, float* __restrict__ dy, void* __restrict__ dz, int64_t dz_rs,
                     float* __restrict__ dw_part, float* __restrict__ db_part, int batch, int D, int L, int z_dtype,
-                    int out_dtype, int tiles_per_batch) {
+                    int out_dtype, int tiles_per_batch, PlaneIdx pi) {
   extern __shared__ float smem[];
   float* s_y = smem;                               // [D][33] merged y, then dy
   float* s_g = s_y + (size_t)D * (kEpiTL + 1);     // [D][33] d(yn) = dout * gate * w
@@ -108,7 +116,7 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
     const int b = tile / tiles_per_batch, l0 = (tile - b * tiles_per_batch) * kEpiTL;
     __syncthreads();
-    load_merged_tile(s_y, ys, K, b, D, L, l0);
+    load_merged_tile(s_y, ys, K, b, D, L, l0, pi);
     for (int px = threadIdx.x; px < kEpiTL; px += kEpiThreads) {
       const int l = l0 + px;
       s_stat[px][0] = l < L ? mean_rstd[((int64_t)b * L + l) * 2 + 0] : 0.f;
@@ -184,29 +192,31 @@ int epi_max_D(bool backward) { return backward ? 832 : 1664; }   // keeps the ti
 
 cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
                                 int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
-                                int out_dtype, cudaStream_t stream) {
+                                int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
   const size_t smem = (size_t)D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int tpb = (L + kEpiTL - 1) / kEpiTL;
   const int tiles = batch * tpb;
   const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
+  const PlaneIdx pi{L, H, W, tmask};
   out_gate_fwd_kernel<<<grid, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
-                                                          eps, z_dtype, out_dtype, tpb);
+                                                          eps, z_dtype, out_dtype, tpb, pi);
   return cudaGetLastError();
 }
 
 cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
                                 int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
-                                int out_dtype, cudaStream_t stream) {
+                                int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
   const size_t smem = (size_t)2 * D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int tpb = (L + kEpiTL - 1) / kEpiTL;
+  const PlaneIdx pi{L, H, W, tmask};
   out_gate_bwd_kernel<<<n_partials, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
                                                                 dz_rs, dw_part, db_part, batch, D, L, z_dtype, out_dtype,
-                                                                tpb);
+                                                                tpb, pi);
   return cudaGetLastError();
 }
 

@@ -123,49 +123,59 @@ def directions_of(cross_scan_cls, cross_merge_cls):
 
 # ---- fused SS2D core ------------------------------------------------------------------------------
 class _SS2DScanNatural(torch.autograd.Function):
-    """Selective scan over K directions in NATURAL layout: x (B, D, L) shared by all directions, delta
-    (B, K*D, L), Bs/Cs (B, K, N, L) all in natural pixel order -> ys (B, K, D, L) natural order, fp32."""
+    """Selective scan over K groups in NATURAL layout, each group traversed in its direction.
+
+    u: (B, P*D, L) — P input planes shared cyclically by the groups (group g reads plane g % P): P = 1 when every
+    direction scans the same image, P = 2 for (natural, transposed) pairs. delta (B, K*D, L), Bs/Cs (B, K, N, L), all
+    in the pixel order of the plane their group reads. Returns ys (B, K/P, P, D, L) fp32 in that same pixel order."""
 
     @staticmethod
     @_custom_fwd
-    def forward(ctx, x, dts, A, Bs, Cs, Ds, delta_bias, H, W, dirs):
-        D = x.shape[1]
-        prob = ops.ScanProblem(x, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=D)
+    def forward(ctx, u, dts, A, Bs, Cs, Ds, delta_bias, H, W, dirs, P):
+        Bn, PD, L = u.shape
+        D, K = PD // P, len(dirs)
+        prob = ops.ScanProblem(u, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=PD)
         out, st = prob.forward(want_state=True)
-        ctx.meta = (H, W, tuple(dirs), D)
-        ctx.save_for_backward(x, dts, A, Bs, Cs, Ds, delta_bias, st)
-        return out.view(x.shape[0], len(dirs), D, H * W)
+        ctx.meta = (H, W, tuple(dirs), D, P)
+        ctx.save_for_backward(u, dts, A, Bs, Cs, Ds, delta_bias, st)
+        return out.view(Bn, K // P, P, D, L)
 
     @staticmethod
     @_custom_bwd
     def backward(ctx, dys):
-        """dys arrives as (B, K, D, L). When it is a stride-0 expansion over K (what `_OutGate.backward` returns:
-        CrossMerge's adjoint hands every direction the same gradient, csms6s.py:42-53) the kernel reads the single
-        (B, D, L) plane for all directions; otherwise the per-direction planes are used as they are."""
-        x, dts, A, Bs, Cs, Ds, delta_bias, st = ctx.saved_tensors
-        H, W, dirs, D = ctx.meta
+        """dys: (B, K/P, P, D, L). When it is a stride-0 expansion over dim 1 (what `_OutGate.backward` returns:
+        CrossMerge's adjoint hands every direction the same gradient, csms6s.py:42-53) the kernel reads the P shared
+        (B, D, L) planes for all groups; otherwise the per-direction planes are used as they are."""
+        u, dts, A, Bs, Cs, Ds, delta_bias, st = ctx.saved_tensors
+        H, W, dirs, D, P = ctx.meta
         K = len(dirs)
-        Bn, L = x.shape[0], H * W
-        if K == 1 or dys.stride(1) == 0:
-            prob = ops.ScanProblem(x, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=D)
-            du, ddelta, dA, dB, dC, dD, dbias = prob.backward(dys[:, 0].float(), st)
+        Bn, L = u.shape[0], H * W
+        if K == P or dys.stride(1) == 0:
+            prob = ops.ScanProblem(u, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=P * D)
+            du, ddelta, dA, dB, dC, dD, dbias = prob.backward(dys[:, 0].reshape(Bn, P * D, L).float(), st)
         else:
-            prob = ops.ScanProblem(x.repeat(1, K, 1), dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True,
-                                   hw=(H, W), dirs=dirs, u_mod=0)
+            u_full = u.view(Bn, 1, P * D, L).expand(Bn, K // P, P * D, L).reshape(Bn, K * D, L)
+            prob = ops.ScanProblem(u_full, dts, A, Bs, Cs, Ds, delta_bias, True, out_float=True, hw=(H, W), dirs=dirs, u_mod=0)
             du, ddelta, dA, dB, dC, dD, dbias = prob.backward(dys.reshape(Bn, K * D, L).float().contiguous(), st)
-        dx = du.view(Bn, K, D, L).sum(dim=1) if K > 1 else du.view_as(x)
-        return dx, ddelta, dA, dB, dC, dD, dbias, None, None, None
+        du = du.view(Bn, K // P, P * D, L).sum(dim=1) if K > P else du.view_as(u)
+        return du, ddelta, dA, dB, dC, dD, dbias, None, None, None, None
 
 
 class _OutGate(torch.autograd.Function):
-    """merge over K + transpose + LayerNorm(D) + SiLU(z) gate (ops.out_gate_fwd/bwd)."""
+    """merge over K + un-transpose + (B,D,L)->(B,L,D) + LayerNorm(D) + SiLU(z) gate (ops.out_gate_fwd/bwd).
+    ys: (B, K/P, P, D, L); plane (i, j) is in transposed pixel order when bit j of `tplanes` is set."""
 
     @staticmethod
     @_custom_fwd
-    def forward(ctx, ys, ln_w, ln_b, z, z_act, eps, out_dtype):
-        out, stats = ops.out_gate_fwd(ys, ln_w, ln_b, z, z_act, eps, out_dtype)
-        ctx.z_act = z_act
-        ctx.has_z = z is not None
+    def forward(ctx, ys, ln_w, ln_b, z, z_act, eps, out_dtype, H, W, tplanes):
+        Bn, G, P, D, L = ys.shape
+        K = G * P
+        tmask = 0
+        for k in range(K):
+            if (tplanes >> (k % P)) & 1:
+                tmask |= 1 << k
+        out, stats = ops.out_gate_fwd(ys.view(Bn, K, D, L), ln_w, ln_b, z, z_act, eps, out_dtype, (H, W), tmask)
+        ctx.meta = (z_act, z is not None, H, W, tmask, tplanes)
         ctx.save_for_backward(ys, ln_w, ln_b, z, stats)
         return out
 
@@ -173,9 +183,14 @@ class _OutGate(torch.autograd.Function):
     @_custom_bwd
     def backward(ctx, dout):
         ys, ln_w, ln_b, z, stats = ctx.saved_tensors
-        dz = torch.empty(z.shape, dtype=z.dtype, device=z.device) if ctx.has_z else None
-        dy, dw, db = ops.out_gate_bwd(ys, ln_w, ln_b, z, ctx.z_act, dout, stats, dz)
-        # dy is the gradient of the merged y: hand it to the scan's backward as a shared (B, D, L) dout
-        K = ys.shape[1]
-        return (dy.unsqueeze(1).expand(-1, K, -1, -1), (dw if ln_w is not None else None),
-                (db if ln_b is not None else None), dz, None, None, None)
+        z_act, has_z, H, W, tmask, tplanes = ctx.meta
+        Bn, G, P, D, L = ys.shape
+        dz = torch.empty(z.shape, dtype=z.dtype, device=z.device) if has_z else None
+        dy, dw, db = ops.out_gate_bwd(ys.view(Bn, G * P, D, L), ln_w, ln_b, z, z_act, dout, stats, dz, (H, W), tmask)
+        # dy is the gradient of the merged y in natural pixel order; every group receives it (transposed for the groups
+        # that ran on the transposed image). Returned as a stride-0 expansion over the K/P repeats: no K-fold copy.
+        planes = [dy.view(Bn, D, H, W).transpose(2, 3).reshape(Bn, D, L) if (tplanes >> j) & 1 else dy for j in range(P)]
+        base = planes[0].unsqueeze(1) if P == 1 else torch.stack(planes, dim=1)          # (B, P, D, L)
+        dys = base.unsqueeze(1).expand(Bn, G, P, D, L)
+        return (dys, (dw if ln_w is not None else None), (db if ln_b is not None else None), dz,
+                None, None, None, None, None, None)

@@ -107,29 +107,57 @@ class SS2D(nn.Module, mamba_init):
         self.Ds = self.D_init(d_inner, copies=k_group, merge=True)                                 # (K*D)
 
     # -- forward_corev2 (ss2d.py:349-500) as ONE fused pipeline ------------------------------------
+    @staticmethod
+    def _plan(dirs):
+        """How the K directions map onto contiguous traversals. Column-major directions (2, 4) are row-major traversals
+        (1, 3) of the TRANSPOSED image, so the scan kernels only ever see TMA-friendly contiguous rows; the transposition
+        is paid once on x (and once on dy in the backward) and undone inside the epilogue's merge.
+        -> (P input planes, per-plane transposed flags, kernel directions) or None if the pattern is not periodic."""
+        tflag = [k in (2, 4) for k in dirs]
+        kdirs = tuple({1: 1, 2: 1, 3: 3, 4: 3}[k] for k in dirs)
+        if all(t == tflag[0] for t in tflag):
+            return 1, (tflag[0],), kdirs
+        if len(dirs) % 2 == 0 and all(tflag[i] == tflag[i % 2] for i in range(len(dirs))) and tflag[0] != tflag[1]:
+            return 2, (tflag[0], tflag[1]), kdirs
+        return None
+
     def forward_core(self, x: torch.Tensor, z, dirs):
         """x: (B, D, H, W) activated conv output; z: (B, H, W, D) raw gate view or None -> (B, H, W, D)."""
         Bn, D, H, W = x.shape
         K, _, R = self.dt_projs_weight.shape
         N = self.A_logs.shape[1]
         L = H * W
+        C = R + 2 * N
         assert K == len(dirs), "one direction per k_group"
-        xf = x.reshape(Bn, D, L)
-        # pointwise projections evaluated in natural pixel order (identical values to projecting the permuted xs)
-        x_dbl = torch.matmul(self.x_proj_weight.reshape(K * (R + 2 * N), D).to(xf.dtype), xf).view(Bn, K, R + 2 * N, L)
+        plan = self._plan(dirs)
+        if plan is None:      # irregular direction sets: index-mapped traversal inside the kernels (slower, no TMA)
+            P, tflags, kdirs = 1, (False,), tuple(dirs)
+        else:
+            P, tflags, kdirs = plan
+        planes = [x.transpose(2, 3).reshape(Bn, D, L) if t else x.reshape(Bn, D, L) for t in tflags]
+        # pointwise projections evaluated in each plane's own pixel order (identical values to projecting the permuted xs)
+        Wx = self.x_proj_weight.to(x.dtype)
+        if P == 1:
+            u = planes[0]
+            x_dbl = torch.matmul(Wx.reshape(K * C, D), u).view(Bn, K, C, L)
+        else:
+            u = torch.cat(planes, dim=1)                                                     # (B, 2D, L)
+            per_plane = [torch.matmul(Wx[j::2].reshape((K // 2) * C, D), planes[j]).view(Bn, K // 2, C, L) for j in range(2)]
+            x_dbl = torch.stack(per_plane, dim=2).view(Bn, K, C, L)                          # group order restored
         dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         dts = torch.matmul(self.dt_projs_weight.to(dts_r.dtype).unsqueeze(0), dts_r).reshape(Bn, K * D, L)
         As = -torch.exp(self.A_logs.float())
         Ds = self.Ds.float()
         bias = self.dt_projs_bias.reshape(-1).float()
         if not self.disable_force32:
-            xf, dts, Bs, Cs = xf.float(), dts.float(), Bs.float(), Cs.float()
+            u, dts, Bs, Cs = u.float(), dts.float(), Bs.float(), Cs.float()
         else:
-            dts, Bs, Cs = dts.to(xf.dtype), Bs.to(xf.dtype), Cs.to(xf.dtype)
-        ys = Fn._SS2DScanNatural.apply(xf, dts, As, Bs, Cs, Ds, bias, H, W, tuple(dirs))       # (B, K, D, L) fp32
+            dts, Bs, Cs = dts.to(u.dtype), Bs.to(u.dtype), Cs.to(u.dtype)
+        ys = Fn._SS2DScanNatural.apply(u.contiguous(), dts, As, Bs, Cs, Ds, bias, H, W, kdirs, P)   # (B, K/P, P, D, L)
         zz = z.reshape(Bn, L, D) if z is not None else None
+        tplanes = sum(1 << j for j, t in enumerate(tflags) if t)
         y = Fn._OutGate.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, True,
-                              self.out_norm.eps, x.dtype)
+                              self.out_norm.eps, x.dtype, H, W, tplanes)
         return y.view(Bn, H, W, D)
 
     def forward(self, x: torch.Tensor, CrossScan=None, CrossMerge=None, **kwargs):

@@ -204,7 +204,7 @@ def cross_merge(ys: torch.Tensor, hw: Tuple[int, int], dirs: Sequence[int]) -> t
 
 
 # ---- fused epilogue ----------------------------------------------------------------------------
-def out_gate_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, out_dtype):
+def out_gate_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, out_dtype, hw=(0, 0), tmask: int = 0):
     """ys (B, K, D, L) fp32 natural order; z (B, L, D) view with stride(-1)==1 or None -> out (B, L, D), mean_rstd."""
     _require(ys.is_cuda and ys.dtype == torch.float32 and ys.is_contiguous(), "ys must be contiguous CUDA fp32")
     Bn, K, D, L = ys.shape
@@ -217,7 +217,7 @@ def out_gate_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, out_dtype):
     with torch.cuda.device(ys.device):
         rc = _lib.lib().ss2d_out_gate_fwd(_ptr(ys), K, _ptr(ln_w), _ptr(ln_b), _ptr(z), zrs, int(z_act), _ptr(out),
                                           _ptr(stats), Bn, D, L, ctypes.c_float(eps), zdt, _DT[out_dtype],
-                                          _stream(ys.device))
+                                          int(hw[0]), int(hw[1]), ctypes.c_uint32(tmask), _stream(ys.device))
     _lib.check(rc, "ss2d_out_gate_fwd")
     return out, stats
 
@@ -236,7 +236,7 @@ def _row_stride(z, Bn, L) -> int:
     return rs
 
 
-def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[torch.Tensor]):
+def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[torch.Tensor], hw=(0, 0), tmask: int = 0):
     """-> dy (B, D, L) fp32, dln_w, dln_b. dz is written into `dz_out` (a (B, L, D) uniformly strided view)."""
     Bn, K, D, L = ys.shape
     dout = dout.contiguous()
@@ -251,7 +251,7 @@ def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[t
         rc = _lib.lib().ss2d_out_gate_bwd(_ptr(ys), K, _ptr(ln_w), _ptr(ln_b), _ptr(z), zrs, int(z_act), _ptr(dout),
                                           _ptr(stats), _ptr(dy), _ptr(dz_out) if z is not None else None, dzrs,
                                           _ptr(part[0]), _ptr(part[1]), npart, Bn, D, L, zdt, _DT[dout.dtype],
-                                          _stream(ys.device))
+                                          int(hw[0]), int(hw[1]), ctypes.c_uint32(tmask), _stream(ys.device))
     _lib.check(rc, "ss2d_out_gate_bwd")
     sums = part.sum(dim=1)
     return dy, sums[0], sums[1]

@@ -136,11 +136,14 @@ int ss2d_cross_merge(const void* ys, void* y, int32_t batch, int32_t channels, i
  * z:  gate rows, element (b, l, d) at z[(b*L + l) * z_row_stride + d] (a strided view of in_proj's output),
  *     or NULL for no gate; z_act != 0 applies SiLU to z inside the kernel.
  * out: (batch, L, D) channels-last. mean_rstd: (batch, L, 2) fp32 saved for the backward (may be NULL).
- * ln_weight / ln_bias: (D) fp32 or NULL (no affine). D <= 1664 forward, <= 832 backward. */
+ * ln_weight / ln_bias: (D) fp32 or NULL (no affine). D <= 1664 forward, <= 832 backward.
+ * transposed_mask: bit k set = plane k of ys is in the pixel order of the TRANSPOSED (W, H) image — how the
+ *     column-major directions 2 and 4 are run (as directions 1 and 3 of a transposed input); the kernel undoes
+ *     the transposition while merging. H, W are the natural image sizes (only read when the mask is non-zero). */
 int ss2d_out_gate_fwd(const float* ys, int32_t K, const float* ln_weight, const float* ln_bias,
                       const void* z, int64_t z_row_stride, int32_t z_act, void* out, float* mean_rstd,
                       int32_t batch, int32_t D, int32_t L, float eps, int32_t z_dtype, int32_t out_dtype,
-                      ss2d_stream_t stream);
+                      int32_t H, int32_t W, uint32_t transposed_mask, ss2d_stream_t stream);
 /* dy: (batch, D, L) fp32 gradient of the MERGED y (every direction receives the same gradient: pass it to
  *     ss2d_scan_bwd as a shared dout through u_dim_modulo). dz: gradient of the RAW z when z_act != 0, rows
  *     strided by dz_row_stride, or NULL. dln_*_partial: (n_partials, D) fp32, n_partials =
@@ -149,7 +152,8 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                       const void* z, int64_t z_row_stride, int32_t z_act, const void* dout,
                       const float* mean_rstd, float* dy, void* dz, int64_t dz_row_stride,
                       float* dln_weight_partial, float* dln_bias_partial, int32_t n_partials, int32_t batch,
-                      int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, ss2d_stream_t stream);
+                      int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, int32_t H, int32_t W,
+                      uint32_t transposed_mask, ss2d_stream_t stream);
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
