@@ -14,7 +14,17 @@ constexpr int kEpiMaxDPT = 4;     // channels per thread in the backward: D <= 1
 // Plane k of `ys` is stored either in natural pixel order (offset l = h W + w) or, when bit k of tmask is set, in
 // the pixel order of the TRANSPOSED image (offset w H + h): the column-major directions are scanned as row-major
 // traversals of a transposed input, and the transposition back happens here, inside the merge.
-struct PlaneIdx { int L, H, W; unsigned tmask; };
+// A tile is 32 pixels: a 1 x 32 run of the flattened image when every plane is in natural order, a 4 x 8 (h x w) patch
+// when some planes are transposed, so that both orders are read in contiguous pieces (32 B and 16 B).
+struct PlaneIdx {
+  int L, H, W; unsigned tmask; int tiles_w;     // tiles_w: patches per image row (patch mode only)
+  __device__ __forceinline__ int pixel(int tile_in_batch, int px) const {   // -> flattened natural index or -1
+    if (!tmask) { const int l = tile_in_batch * kEpiTL + px; return l < L ? l : -1; }
+    const int th = tile_in_batch / tiles_w, tw = tile_in_batch - th * tiles_w;
+    const int h = th * 4 + (px >> 3), w = tw * 8 + (px & 7);
+    return (h < H && w < W) ? h * W + w : -1;
+  }
+};
 __device__ __forceinline__ float merge_k(const float* __restrict__ ys, int K, int64_t plane_stride, int64_t row_off, int l,
                                          const PlaneIdx pi) {
   int lt = l;
@@ -38,13 +48,13 @@ __device__ __forceinline__ float silu_grad_f(float x) {
 
 // loads the merged tile y[d][pix] for pixels [l0, l0+32) of batch b into s_y[d * 33 + pix]
 __device__ __forceinline__ void load_merged_tile(float* s_y, const float* __restrict__ ys, int K, int b, int D, int L,
-                                                 int l0, const PlaneIdx pi) {
+                                                 int tib, const PlaneIdx pi) {
   const int64_t plane = (int64_t)D * L;
   const float* base = ys + (int64_t)b * K * plane;
   for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
     const int d = i / kEpiTL, px = i - d * kEpiTL;
-    const int l = l0 + px;
-    s_y[d * (kEpiTL + 1) + px] = l < L ? merge_k(base, K, plane, (int64_t)d * L, l, pi) : 0.f;
+    const int l = pi.pixel(tib, px);
+    s_y[d * (kEpiTL + 1) + px] = l >= 0 ? merge_k(base, K, plane, (int64_t)d * L, l, pi) : 0.f;
   }
 }
 
@@ -57,9 +67,9 @@ out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
   __shared__ float s_stat[kEpiTL][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
-    const int b = tile / tiles_per_batch, l0 = (tile - b * tiles_per_batch) * kEpiTL;
+    const int b = tile / tiles_per_batch, tib = tile - b * tiles_per_batch;
     __syncthreads();
-    load_merged_tile(s_y, ys, K, b, D, L, l0, pi);
+    load_merged_tile(s_y, ys, K, b, D, L, tib, pi);
     __syncthreads();
     // LayerNorm statistics per pixel (two-pass, fp32): warp w handles pixels w, w+8, ...
     for (int px = warp; px < kEpiTL; px += kEpiThreads / 32) {
@@ -75,9 +85,10 @@ out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       const float rstd = rsqrtf(v / D + eps);
       if (lane == 0) {
         s_stat[px][0] = mean; s_stat[px][1] = rstd;
-        if (l0 + px < L && mean_rstd) {
-          mean_rstd[((int64_t)b * L + l0 + px) * 2 + 0] = mean;
-          mean_rstd[((int64_t)b * L + l0 + px) * 2 + 1] = rstd;
+        const int l = pi.pixel(tib, px);
+        if (l >= 0 && mean_rstd) {
+          mean_rstd[((int64_t)b * L + l) * 2 + 0] = mean;
+          mean_rstd[((int64_t)b * L + l) * 2 + 1] = rstd;
         }
       }
     }
@@ -85,8 +96,8 @@ out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
     // normalise, gate, write channels-last (threads run along D: coalesced)
     for (int i = threadIdx.x; i < kEpiTL * D; i += kEpiThreads) {
       const int px = i / D, d = i - px * D;
-      const int l = l0 + px;
-      if (l >= L) continue;
+      const int l = pi.pixel(tib, px);
+      if (l < 0) continue;
       float o = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
       o = lnw ? fmaf(o, __ldg(lnw + d), lnb ? __ldg(lnb + d) : 0.f) : o;
       if (z) {
@@ -114,25 +125,26 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
 #pragma unroll
   for (int m = 0; m < kEpiMaxDPT; ++m) { acc_dw[m] = 0.f; acc_db[m] = 0.f; }
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
-    const int b = tile / tiles_per_batch, l0 = (tile - b * tiles_per_batch) * kEpiTL;
+    const int b = tile / tiles_per_batch, tib = tile - b * tiles_per_batch;
     __syncthreads();
-    load_merged_tile(s_y, ys, K, b, D, L, l0, pi);
+    load_merged_tile(s_y, ys, K, b, D, L, tib, pi);
     for (int px = threadIdx.x; px < kEpiTL; px += kEpiThreads) {
-      const int l = l0 + px;
-      s_stat[px][0] = l < L ? mean_rstd[((int64_t)b * L + l) * 2 + 0] : 0.f;
-      s_stat[px][1] = l < L ? mean_rstd[((int64_t)b * L + l) * 2 + 1] : 0.f;
+      const int l = pi.pixel(tib, px);
+      s_stat[px][0] = l >= 0 ? mean_rstd[((int64_t)b * L + l) * 2 + 0] : 0.f;
+      s_stat[px][1] = l >= 0 ? mean_rstd[((int64_t)b * L + l) * 2 + 1] : 0.f;
     }
     __syncthreads();
     // pass 1 (threads along D, coalesced): gate grads and d(yn). Thread t always meets channels t, t+256, ... so
     // the LayerNorm weight/bias gradients accumulate in registers, without atomics.
+#pragma unroll 4
     for (int px = 0; px < kEpiTL; ++px) {
-      const int l = l0 + px;
+      const int l = pi.pixel(tib, px);
 #pragma unroll
       for (int m = 0; m < kEpiMaxDPT; ++m) {
         const int d = threadIdx.x + m * kEpiThreads;
         if (d >= D) break;
         float g = 0.f;
-        if (l < L) {
+        if (l >= 0) {
           const float yn = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
           const float w = lnw ? __ldg(lnw + d) : 1.f;
           const float lin = lnw ? fmaf(yn, w, lnb ? __ldg(lnb + d) : 0.f) : yn;
@@ -167,8 +179,8 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
     // dy[b][d][l] = rstd * (g - mean(g) - yn * mean(g yn)); threads along pixels: coalesced along L
     for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
       const int d = i / kEpiTL, px = i - d * kEpiTL;
-      const int l = l0 + px;
-      if (l >= L) continue;
+      const int l = pi.pixel(tib, px);
+      if (l < 0) continue;
       const float mean = s_stat[px][0], rstd = s_stat[px][1];
       const float yn = (s_y[d * (kEpiTL + 1) + px] - mean) * rstd;
       dy[((int64_t)b * D + d) * L + l] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
@@ -184,7 +196,10 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
   }
 }
 
-int epi_bwd_partials(int batch, int L) {
+static int epi_tiles_per_batch(int L, int H, int W, unsigned tmask) {
+  return tmask ? ((H + 3) / 4) * ((W + 7) / 8) : (L + kEpiTL - 1) / kEpiTL;
+}
+int epi_bwd_partials(int batch, int L) {     // an upper bound that does not depend on the tiling mode
   const int tiles = batch * ((L + kEpiTL - 1) / kEpiTL);
   return tiles < 148 * 2 ? tiles : 148 * 2;
 }
@@ -196,10 +211,10 @@ cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const 
   const size_t smem = (size_t)D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int tpb = (L + kEpiTL - 1) / kEpiTL;
+  const int tpb = epi_tiles_per_batch(L, H, W, tmask);
   const int tiles = batch * tpb;
   const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
-  const PlaneIdx pi{L, H, W, tmask};
+  const PlaneIdx pi{L, H, W, tmask, tmask ? (W + 7) / 8 : 0};
   out_gate_fwd_kernel<<<grid, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
                                                           eps, z_dtype, out_dtype, tpb, pi);
   return cudaGetLastError();
@@ -212,8 +227,8 @@ cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const 
   const size_t smem = (size_t)2 * D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int tpb = (L + kEpiTL - 1) / kEpiTL;
-  const PlaneIdx pi{L, H, W, tmask};
+  const int tpb = epi_tiles_per_batch(L, H, W, tmask);
+  const PlaneIdx pi{L, H, W, tmask, tmask ? (W + 7) / 8 : 0};
   out_gate_bwd_kernel<<<n_partials, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
                                                                 dz_rs, dw_part, db_part, batch, D, L, z_dtype, out_dtype,
                                                                 tpb, pi);
