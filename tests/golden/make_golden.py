@@ -160,6 +160,23 @@ def gen_group_layer(gm):
     print("group_mamba_layer", rec["y"].shape)
 
 
+def gen_init(gm, vm):
+    """Parameters right after construction under a fixed seed: pins the RNG consumption order of the constructors
+    (mamba_init, ss2d.py:154-209; __initv2__, ss2d.py:294-335)."""
+    rec = {}
+    torch.manual_seed(1234)
+    m = gm["ss2d"].SS2D(d_model=32, d_state=1, ssm_ratio=1, d_conv=3)
+    rec.update({"gm." + k: _np(v) for k, v in m.state_dict().items()})
+    torch.manual_seed(1234)
+    m = vm["vmamba"].SS2D(d_model=16, d_state=16, ssm_ratio=2.0, forward_type="v2")
+    rec.update({"vm." + k: _np(v) for k, v in m.state_dict().items()})
+    torch.manual_seed(1234)
+    m = gm["groupmamba"].GroupMambaLayer(64, 64)
+    rec.update({"layer." + k: _np(v) for k, v in m.state_dict().items()})
+    np.savez_compressed(os.path.join(HERE, "init_seed1234.npz"), **rec)
+    print("init_seed1234", len(rec), "arrays")
+
+
 if __name__ == "__main__":
     if not RL.available():
         raise SystemExit("reference tree not present: golden vectors can only be regenerated in the build container")
@@ -167,5 +184,7 @@ if __name__ == "__main__":
     gm = RL.load_gm()
     gen_cross(gm["csms6s"])
     gen_ss2d_gm(gm)
-    gen_ss2d_vm(RL.load_vmamba())
+    vm = RL.load_vmamba()
+    gen_ss2d_vm(vm)
     gen_group_layer(gm)
+    gen_init(gm, vm)
