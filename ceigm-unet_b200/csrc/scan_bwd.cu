@@ -552,7 +552,11 @@ static cudaError_t launch_bwd(ScanParams p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+bool scan_bwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err);   // scan_bwd2.cu
+
 cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream) {
+  cudaError_t e2;
+  if (scan_bwd2_try(p, stream, &e2)) return e2;     // fast path: fp32 + TMA, 8 < N <= 16, contiguous traversal
   const int N = p.N;
   if (N <= 1) return launch_bwd<1, 1, 1>(p, stream);
   if (N <= 2) return launch_bwd<2, 1, 1>(p, stream);

@@ -1,0 +1,480 @@
+// Selective-scan backward, fast path for the north-star regime (8 < d_state <= 16, fp32, TMA-stageable operands,
+// contiguous traversal: SCAN layout or directions 1 / 3). Everything else runs scan_bwd.cu.
+//
+// Replaces selective_scan_bwd_kernel (/root/reference/gm-unet/kernels/selective_scan/csrc/selective_scan/cus/
+// selective_scan_bwd_kernel.cuh:66-273). Same mathematics as scan_bwd.cu (two-level state recompute from the
+// forward's chunk checkpoints, adjoint recurrence g_l = C_l dy_l + a_(l+1) g_(l+1)); different machine mapping:
+//   * a warp owns 8 channel rows = 4 ROW PAIRS; lane = (row pair, state lane q): states q and q + 8 of two rows.
+//     Everything a lane computes is packed f32x2 with one row per half — both recurrences included; B and C enter
+//     as broadcast scalar operands, delta / delta*u / dout as ready-made register pairs.
+//   * no producer warp, no polling: each warp streams its own delta / u / dout rows through a private 2-stage TMA
+//     ring; the B/C tiles are shared by the CTA and refilled by the last warp that releases them.
+//   * per tile the warp rewrites its tiles in place as activated, row-pair-interleaved arrays (scan order, so that
+//     reversed traversals cost nothing afterwards); du / d(delta) are written over dout' / delta' and leave as
+//     128-bit row-contiguous stores at the end of the tile.
+//   * sum over states (du, d delta): shuffle reduce-scatter over the 8 state lanes; sum over rows (dB, dC): x+y of
+//     the packed halves, reduce-scatter over the 4 row-pair lanes, then a 512-byte slab per warp and group that the
+//     four warps fold together one group later (mbarrier hand-off, no CTA barrier) into one red.global.add.v4.f32
+//     per (state, 4 positions) and CTA.
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+#include "scan_params.h"
+#include "common.cuh"
+#include "tma_host.h"
+
+namespace ss2d {
+
+constexpr int B2_NW = 4;                    // warps per CTA
+constexpr int B2_RPW = 8;                   // rows per warp
+constexpr int B2_CH = B2_NW * B2_RPW;       // rows per CTA
+constexpr int B2_STAGES = 2;
+constexpr int B2_WSTAGE = 3 * 1024;         // delta | u | dout tiles of one warp (8 rows x 128 bytes each)
+constexpr int B2_BC_STAGE = 4096;           // B | C tiles, 16 state rows each
+constexpr int B2_HS_BYTES = 7 * 512;        // per warp: states at the 7 inner group boundaries of a tile
+constexpr int B2_OFF_ROWS = B2_STAGES * B2_BC_STAGE;
+constexpr int B2_OFF_UP = B2_OFF_ROWS + B2_NW * B2_STAGES * B2_WSTAGE;
+constexpr int B2_OFF_HS = B2_OFF_UP + B2_NW * 1024;
+constexpr int B2_OFF_SLAB = B2_OFF_HS + B2_NW * B2_HS_BYTES;
+constexpr int B2_OFF_BARS = B2_OFF_SLAB + 2 * B2_NW * 512;
+constexpr size_t B2_SMEM = B2_OFF_BARS + 256 + 1024;
+
+struct Bwd2Maps { TMap u, dl, dy, B, C; };
+
+__device__ __forceinline__ int b2_atom_add_acqrel_shared(int* addr, int v) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  return old;
+}
+
+// Row-pair-interleaved array of one warp: 4 row pairs x 32 positions x (row 0, row 1). The 16-byte chunk ch (two
+// positions) of row pair rp lives in slot ch ^ rp ^ (ch >> 3) of the pair's 256-byte line: the 4 row pairs read at
+// one position hit 4 different bank groups, and so do the 8 chunks {2 c + hh} one quarter-warp writes.
+__device__ __forceinline__ int b2_p_off(int rp, int ch) { return rp * 256 + (((ch ^ rp ^ (ch >> 3)) & 15) << 4); }
+// TMA SWIZZLE_128B tile of 32-float rows: byte offset of the 16-byte chunk c4 of row r
+__device__ __forceinline__ int b2_t_off(int r, int c4) { return r * 128 + (((c4 ^ r) & 7) << 4); }
+
+template <int STRIDE, int CNT, int S>
+struct B2ReduceScatter {
+  static __device__ __forceinline__ void run(float* v, int lane_id) {
+    if constexpr (S >= 1 && CNT > 1) {
+      constexpr int HALF = CNT / 2;
+      const bool up = (lane_id & S) != 0;
+#pragma unroll
+      for (int i = 0; i < HALF; ++i) {
+        const float send = up ? v[i] : v[i + HALF];
+        const float keep = up ? v[i + HALF] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, S * STRIDE);
+      }
+      B2ReduceScatter<STRIDE, HALF, S / 2>::run(v, lane_id);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanParams p, const __grid_constant__ Bwd2Maps maps) {
+  extern __shared__ __align__(16) unsigned char smem_rawb2[];
+  unsigned char* smem = smem_rawb2 + ((1024 - (smem_u32(smem_rawb2) & 1023)) & 1023);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* s_bc = smem;
+  unsigned char* s_rows = smem + B2_OFF_ROWS + warp * (B2_STAGES * B2_WSTAGE);
+  unsigned char* s_up = smem + B2_OFF_UP + warp * 1024;
+  unsigned char* s_hs = smem + B2_OFF_HS + warp * B2_HS_BYTES;
+  unsigned char* s_slab = smem + B2_OFF_SLAB;                      // [2][NW][512]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BARS);
+  uint64_t* full_w = bars + warp * B2_STAGES;                      // [NW][STAGES]
+  uint64_t* full_bc = bars + B2_NW * B2_STAGES;                    // [STAGES]
+  uint64_t* slab_full = full_bc + B2_STAGES;                       // [2]
+  uint64_t* slab_empty = slab_full + 2;                            // [2]
+  int* cnt_bc = reinterpret_cast<int*>(slab_empty + 2);            // [STAGES]
+
+  const int b = blockIdx.z, g = blockIdx.y;
+  const int row0 = blockIdx.x * B2_CH + warp * B2_RPW;             // first row of this warp inside the group
+  const int rows_valid = p.dpg - row0;                              // <= 0: idle warp (still takes part in the hand-offs)
+  const int d0 = g * p.dpg + row0;
+  const int L = p.L;
+  const int dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
+  const bool rev = dir == 3;
+  const int ntiles = (L + 31) / 32;
+  const int ug = p.u_mod > 0 ? g % (p.u_mod / p.dpg) : g;          // group coordinate of u and dout
+  const bool single_cta_group = gridDim.x == 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B2_NW * B2_STAGES; ++i) mbar_init(&bars[i], 1);
+    for (int s = 0; s < B2_STAGES; ++s) { mbar_init(&full_bc[s], 1); cnt_bc[s] = 0; }
+    for (int s = 0; s < 2; ++s) { mbar_init(&slab_full[s], B2_NW); mbar_init(&slab_empty[s], B2_NW); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // tiles are visited last to first: iteration `it` handles tile t = ntiles - 1 - it
+  auto issue_rows = [&](int it) {     // lane 0 of the warp
+    const int s = it % B2_STAGES, t = ntiles - 1 - it;
+    const int m0 = rev ? L - t * 32 - 32 : t * 32;
+    unsigned char* st = s_rows + s * B2_WSTAGE;
+    mbar_arrive_expect_tx(&full_w[s], B2_WSTAGE);
+    tma_load_4d(st, &maps.dl, m0, row0, g, b, &full_w[s]);
+    tma_load_4d(st + 1024, &maps.u, m0, row0, ug, b, &full_w[s]);
+    tma_load_4d(st + 2048, &maps.dy, m0, row0, ug, b, &full_w[s]);
+  };
+  auto issue_bc = [&](int it) {
+    const int s = it % B2_STAGES, t = ntiles - 1 - it;
+    const int m0 = rev ? L - t * 32 - 32 : t * 32;
+    mbar_arrive_expect_tx(&full_bc[s], B2_BC_STAGE);
+    tma_load_4d(s_bc + s * B2_BC_STAGE, &maps.B, m0, 0, g, b, &full_bc[s]);
+    tma_load_4d(s_bc + s * B2_BC_STAGE + 2048, &maps.C, m0, 0, g, b, &full_bc[s]);
+  };
+  if (lane == 0) {
+    if (warp == 0) { tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.C); }
+    tma_prefetch_desc(&maps.dl); tma_prefetch_desc(&maps.u); tma_prefetch_desc(&maps.dy);
+    for (int it = 0; it < B2_STAGES && it < ntiles; ++it) {
+      if (warp == 0) issue_bc(it);
+      issue_rows(it);
+    }
+  }
+
+  const int q = lane & 7, rp = lane >> 3;
+  const bool v0 = 2 * rp < rows_valid, v1 = 2 * rp + 1 < rows_valid;
+  // main role: row pair rp, states n_j = q + 8 j
+  float2 A1p[2], A2p[2], carry2[2], dA2[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int n = q + 8 * j;
+    const bool okn = n < p.N;
+    A1p[j].x = (okn && v0) ? p.A[(int64_t)(d0 + 2 * rp) * p.A_ld + n] : 0.f;
+    A1p[j].y = (okn && v1) ? p.A[(int64_t)(d0 + 2 * rp + 1) * p.A_ld + n] : 0.f;
+    A2p[j] = make_float2(A1p[j].x * kLog2e, A1p[j].y * kLog2e);
+    carry2[j] = make_float2(0.f, 0.f);      // a_(l+1) g_(l+1), zero past the end of the sequence
+    dA2[j] = make_float2(0.f, 0.f);
+  }
+  // finalising role: row fr = 2 rp + (q >> 2), position fe = q & 3 of every group
+  const int rr = q >> 2, fe = q & 3;
+  const bool fvalid = 2 * rp + rr < rows_valid;
+  const float Dr = (p.Dv && fvalid) ? p.Dv[d0 + 2 * rp + rr] : 0.f;
+  float dDacc = 0.f, dbacc = 0.f;
+  // activation role: row pair rp, position quad q
+  float2 biasp;
+  biasp.x = (p.bias && v0) ? p.bias[d0 + 2 * rp] : 0.f;
+  biasp.y = (p.bias && v1) ? p.bias[d0 + 2 * rp + 1] : 0.f;
+  const bool softplus = p.softplus != 0;
+
+  auto load_ckpt = [&](int t, float2* h) {     // state before tile t = checkpoint at the end of tile t - 1
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = q + 8 * j;
+      const bool ok = t > 0 && n < p.N;
+      h[j].x = (ok && v0) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp) * p.nck + (t - 1)) * p.N + n) : 0.f;
+      h[j].y = (ok && v1) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp + 1) * p.nck + (t - 1)) * p.N + n) : 0.f;
+    }
+  };
+  float2 h0_next[2];
+  load_ckpt(ntiles - 1, h0_next);
+
+  // dB / dC of global group kk (all warps wrote their slab): fold the NW slabs, one vector reduction per (state, 4 pos)
+  auto reduce_group = [&](int kk, auto REV) {
+    constexpr bool REVV = decltype(REV)::value;
+    const int buf = kk & 1;
+    mbar_wait(&slab_full[buf], (kk >> 1) & 1);
+    if (lane < 8) {
+      const int o = warp * 8 + lane;                       // [dB | dC][16 states]
+      const unsigned char* src = s_slab + buf * (B2_NW * 512) + o * 16;
+      float4 acc = *reinterpret_cast<const float4*>(src);
+#pragma unroll
+      for (int w = 1; w < B2_NW; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(src + w * 512);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      const int which = o >> 4, n = o & 15;
+      const int t = ntiles - 1 - (kk >> 3), gi = 7 - (kk & 7);
+      const int l = t * 32 + gi * 4;
+      if (n < p.N && l < L) {
+        float* dst = (which == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + n) * L + (REVV ? L - 4 - l : l);
+        if (REVV) acc = make_float4(acc.w, acc.z, acc.y, acc.x);
+        if (single_cta_group) *reinterpret_cast<float4*>(dst) = acc;
+        else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&slab_empty[buf]);
+  };
+
+  auto body = [&](auto REV) {
+    constexpr bool REVV = decltype(REV)::value;
+    for (int it = 0; it < ntiles; ++it) {
+      const int t = ntiles - 1 - it;
+      const int s = it % B2_STAGES;
+      const uint32_t par = (it / B2_STAGES) & 1;
+      const int l0 = t * 32, len = min(32, L - l0);
+      unsigned char* s_dl = s_rows + s * B2_WSTAGE;       // delta  -> delta' pairs -> d(delta)
+      unsigned char* s_du = s_dl + 1024;                  // u      -> (delta' u) pairs
+      unsigned char* s_dy = s_dl + 2048;                  // dout   -> dout' pairs  -> du
+      mbar_wait(&full_w[s], par);
+      // ---- activation + row-pair interleave, in place: this lane handles position quad q of row pair rp ----
+      {
+        const int tc4 = REVV ? 7 - q : q;
+        float4 dv[2], uv[2], yv[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int o = b2_t_off(2 * rp + r, tc4);
+          dv[r] = *reinterpret_cast<const float4*>(s_dl + o);
+          uv[r] = *reinterpret_cast<const float4*>(s_du + o);
+          yv[r] = *reinterpret_cast<const float4*>(s_dy + o);
+          if (REVV) {
+            dv[r] = make_float4(dv[r].w, dv[r].z, dv[r].y, dv[r].x);
+            uv[r] = make_float4(uv[r].w, uv[r].z, uv[r].y, uv[r].x);
+            yv[r] = make_float4(yv[r].w, yv[r].z, yv[r].y, yv[r].x);
+          }
+        }
+        __syncwarp();
+        float dl[2][4], du[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = f4_at(dv[r], e) + (r == 0 ? biasp.x : biasp.y);
+            if (softplus) x = softplus20(x);
+            const bool live = q * 4 + e < len && (r == 0 ? v0 : v1);
+            dl[r][e] = live ? x : 0.f;
+            du[r][e] = live ? x * f4_at(uv[r], e) : 0.f;
+          }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {              // chunk 2 q + hh: positions 4 q + 2 hh, + 1
+          const int off = b2_p_off(rp, 2 * q + hh);
+          *reinterpret_cast<float4*>(s_dl + off) = make_float4(dl[0][2 * hh], dl[1][2 * hh], dl[0][2 * hh + 1], dl[1][2 * hh + 1]);
+          *reinterpret_cast<float4*>(s_du + off) = make_float4(du[0][2 * hh], du[1][2 * hh], du[0][2 * hh + 1], du[1][2 * hh + 1]);
+          *reinterpret_cast<float4*>(s_dy + off) =
+              make_float4(f4_at(yv[0], 2 * hh), f4_at(yv[1], 2 * hh), f4_at(yv[0], 2 * hh + 1), f4_at(yv[1], 2 * hh + 1));
+          *reinterpret_cast<float4*>(s_up + off) =
+              make_float4(f4_at(uv[0], 2 * hh), f4_at(uv[1], 2 * hh), f4_at(uv[0], 2 * hh + 1), f4_at(uv[1], 2 * hh + 1));
+        }
+        __syncwarp();
+      }
+      mbar_wait(&full_bc[s], par);
+      const unsigned char* s_B = s_bc + s * B2_BC_STAGE;
+      const unsigned char* s_C = s_B + 2048;
+
+      // ---- (1) forward recompute of h over the tile from the chunk checkpoint; the state after each of the first
+      //          7 groups is parked in shared memory. The checkpoint of the NEXT tile is fetched a whole tile ahead.
+      float2 h0[2];
+      h0[0] = h0_next[0]; h0[1] = h0_next[1];
+      load_ckpt(t - 1, h0_next);
+      {
+        float2 h[2] = {h0[0], h0[1]};
+#pragma unroll 1
+        for (int gi = 0; gi < 7; ++gi) {
+          const int pofs = b2_p_off(rp, 2 * gi);
+          const float4 d01 = *reinterpret_cast<const float4*>(s_dl + pofs);
+          const float4 d23 = *reinterpret_cast<const float4*>(s_dl + (pofs ^ 16));
+          const float4 u01 = *reinterpret_cast<const float4*>(s_du + pofs);
+          const float4 u23 = *reinterpret_cast<const float4*>(s_du + (pofs ^ 16));
+          const float2 dl2[4] = {make_float2(d01.x, d01.y), make_float2(d01.z, d01.w), make_float2(d23.x, d23.y), make_float2(d23.z, d23.w)};
+          const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
+          const int tc4 = REVV ? 7 - gi : gi;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float4 Bq = *reinterpret_cast<const float4*>(s_B + b2_t_off(q + 8 * j, tc4));
+            if (REVV) Bq = make_float4(Bq.w, Bq.z, Bq.y, Bq.x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float be = f4_at(Bq, e);
+              const float2 arg = __fmul2_rn(dl2[e], A2p[j]);
+              const float2 a = make_float2(ex2f(arg.x), ex2f(arg.y));
+              h[j] = __ffma2_rn(a, h[j], __fmul2_rn(du2[e], make_float2(be, be)));
+            }
+          }
+          *reinterpret_cast<float4*>(s_hs + (gi * 32 + lane) * 16) = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+        }
+      }
+
+      // ---- (2) groups of 4 positions, last to first: re-expand a and h, run the adjoint recurrence ----
+#pragma unroll 1
+      for (int gi = 7; gi >= 0; --gi) {
+        const int k = it * 8 + (7 - gi);                 // global group counter (slab hand-off)
+        const int pofs = b2_p_off(rp, 2 * gi);
+        const float4 d01 = *reinterpret_cast<const float4*>(s_dl + pofs);
+        const float4 d23 = *reinterpret_cast<const float4*>(s_dl + (pofs ^ 16));
+        const float4 u01 = *reinterpret_cast<const float4*>(s_du + pofs);
+        const float4 u23 = *reinterpret_cast<const float4*>(s_du + (pofs ^ 16));
+        const float4 y01 = *reinterpret_cast<const float4*>(s_dy + pofs);
+        const float4 y23 = *reinterpret_cast<const float4*>(s_dy + (pofs ^ 16));
+        const float2 dl2[4] = {make_float2(d01.x, d01.y), make_float2(d01.z, d01.w), make_float2(d23.x, d23.y), make_float2(d23.z, d23.w)};
+        const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
+        const float2 dy2[4] = {make_float2(y01.x, y01.y), make_float2(y01.z, y01.w), make_float2(y23.x, y23.y), make_float2(y23.z, y23.w)};
+        float4 hin4;
+        if (gi > 0) hin4 = *reinterpret_cast<const float4*>(s_hs + ((gi - 1) * 32 + lane) * 16);
+        else hin4 = make_float4(h0[0].x, h0[0].y, h0[1].x, h0[1].y);
+        const int tc4 = REVV ? 7 - gi : gi;
+        float2 sB2[4], sA2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sB2[e] = make_float2(0.f, 0.f); sA2[e] = make_float2(0.f, 0.f); }
+        float part[16];                                  // [dB | dC][j][e], the two rows already added
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float4 Bq = *reinterpret_cast<const float4*>(s_B + b2_t_off(q + 8 * j, tc4));
+          float4 Cq = *reinterpret_cast<const float4*>(s_C + b2_t_off(q + 8 * j, tc4));
+          if (REVV) { Bq = make_float4(Bq.w, Bq.z, Bq.y, Bq.x); Cq = make_float4(Cq.w, Cq.z, Cq.y, Cq.x); }
+          const float2 hprev = j == 0 ? make_float2(hin4.x, hin4.y) : make_float2(hin4.z, hin4.w);
+          float2 a2[4], hh2[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float be = f4_at(Bq, e);
+            const float2 arg = __fmul2_rn(dl2[e], A2p[j]);
+            a2[e] = make_float2(ex2f(arg.x), ex2f(arg.y));
+            hh2[e] = __ffma2_rn(a2[e], e == 0 ? hprev : hh2[e - 1], __fmul2_rn(du2[e], make_float2(be, be)));
+          }
+          float2 carry = carry2[j];
+#pragma unroll
+          for (int e = 3; e >= 0; --e) {
+            const float be = f4_at(Bq, e), ce = f4_at(Cq, e);
+            const float2 g2 = __ffma2_rn(dy2[e], make_float2(ce, ce), carry);     // g_e = C_e dy_e + a_(e+1) g_(e+1)
+            const float2 t2 = __fmul2_rn(g2, a2[e]);                              // a_e g_e
+            carry = t2;
+            const float2 pb = __fmul2_rn(g2, du2[e]);
+            const float2 pc = __fmul2_rn(dy2[e], hh2[e]);
+            part[j * 4 + e] = pb.x + pb.y;
+            part[8 + j * 4 + e] = pc.x + pc.y;
+            sB2[e] = __ffma2_rn(g2, make_float2(be, be), sB2[e]);
+            const float2 w2 = __fmul2_rn(t2, e == 0 ? hprev : hh2[e - 1]);        // g_e (h_e - delta u B_e)
+            sA2[e] = __ffma2_rn(w2, A1p[j], sA2[e]);
+            dA2[j] = __ffma2_rn(w2, dl2[e], dA2[j]);
+          }
+          carry2[j] = carry;
+        }
+        // ---- sum over the 8 state lanes; lane q ends up with (sB, sA) of row parity q >> 2, position q & 3 ----
+        float vals[16];                                  // [row parity][e][sB | sA]
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          vals[e * 2] = sB2[e].x; vals[e * 2 + 1] = sA2[e].x;
+          vals[8 + e * 2] = sB2[e].y; vals[8 + e * 2 + 1] = sA2[e].y;
+        }
+        B2ReduceScatter<1, 16, 4>::run(vals, q);
+        {
+          const int off = b2_p_off(rp, 2 * gi + (fe >> 1)) + ((fe & 1) * 2 + rr) * 4;
+          const float de = *reinterpret_cast<const float*>(s_dl + off);
+          const float dyv = *reinterpret_cast<const float*>(s_dy + off);
+          const float uu = *reinterpret_cast<const float*>(s_up + off);
+          const float sBe = vals[0], sAe = vals[1];
+          const float du_out = fmaf(Dr, dyv, de * sBe);
+          float ddl = fmaf(uu, sBe, sAe);
+          if (softplus) {   // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
+            const float sig = de < 0.015625f ? de * (1.f - de * (0.5f - de * 0.16666667f)) : 1.f - ex2f(-de * kLog2e);
+            ddl *= sig;
+          }
+          if (gi * 4 + fe >= len || !fvalid) ddl = 0.f;
+          dDacc = fmaf(dyv, uu, dDacc);
+          dbacc += ddl;
+          // every lane of the row pair has consumed this group's delta' / dout' (the shuffles above ordered them)
+          *reinterpret_cast<float*>(s_dy + off) = du_out;
+          *reinterpret_cast<float*>(s_dl + off) = ddl;
+        }
+        // ---- sum over the 4 row-pair lanes; lane (rp, q) ends up with 4 positions of tensor rp >> 1, state q + 8 (rp & 1)
+        B2ReduceScatter<8, 16, 2>::run(part, rp);
+        {
+          const int buf = k & 1;
+          mbar_wait(&slab_empty[buf], ((k >> 1) & 1) ^ 1);
+          *reinterpret_cast<float4*>(s_slab + (buf * B2_NW + warp) * 512 + ((rp >> 1) * 16 + q + 8 * (rp & 1)) * 16) =
+              make_float4(part[0], part[1], part[2], part[3]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slab_full[buf]);
+          if (k > 0) reduce_group(k - 1, REV);
+        }
+      }
+      __syncwarp();
+      // ---- tile epilogue: du / d(delta) of this warp's rows, 128-bit row-contiguous stores ----
+      {
+        const int off0 = b2_p_off(rp, 2 * q), off1 = b2_p_off(rp, 2 * q + 1);
+        const float4 ua = *reinterpret_cast<const float4*>(s_dy + off0), ub = *reinterpret_cast<const float4*>(s_dy + off1);
+        const float4 da = *reinterpret_cast<const float4*>(s_dl + off0), db = *reinterpret_cast<const float4*>(s_dl + off1);
+        const int l = l0 + 4 * q;
+        if (l < L) {
+          const int64_t mpos = REVV ? L - 4 - l : l;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (r == 0 ? v0 : v1) {
+              const int d = d0 + 2 * rp + r;
+              float4 uo = r == 0 ? make_float4(ua.x, ua.z, ub.x, ub.z) : make_float4(ua.y, ua.w, ub.y, ub.w);
+              float4 dd = r == 0 ? make_float4(da.x, da.z, db.x, db.z) : make_float4(da.y, da.w, db.y, db.w);
+              if (REVV) { uo = make_float4(uo.w, uo.z, uo.y, uo.x); dd = make_float4(dd.w, dd.z, dd.y, dd.x); }
+              // du has u's strides, except when the groups share u (u_mod > 0): then it is a dense (batch, dim, L) tensor
+              const int64_t duo = p.u_mod > 0 ? ((int64_t)b * p.dim + d) * (int64_t)L : (int64_t)b * p.u_bs + (int64_t)d * p.u_ds;
+              *reinterpret_cast<float4*>(static_cast<float*>(p.du) + duo + mpos) = uo;
+              *reinterpret_cast<float4*>(static_cast<float*>(p.ddelta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds + mpos) = dd;
+            }
+          }
+        }
+      }
+      // release the stage: generic-proxy accesses are ordered before the async-proxy refill
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (it + B2_STAGES < ntiles) issue_rows(it + B2_STAGES);
+        if (b2_atom_add_acqrel_shared(&cnt_bc[s], 1) == B2_NW - 1) {      // last warp to release the B/C stage refills it
+          cnt_bc[s] = 0;
+          if (it + B2_STAGES < ntiles) issue_bc(it + B2_STAGES);
+        }
+      }
+      __syncwarp();
+    }
+    reduce_group(ntiles * 8 - 1, REV);
+  };
+  if (rev) body(std::true_type{}); else body(std::false_type{});
+
+  // ---- per-(batch, channel) partials of dA, dD, d(delta_bias) ----
+  {
+    float dd = dDacc, db = dbacc;
+    dd += __shfl_xor_sync(0xffffffffu, dd, 1); db += __shfl_xor_sync(0xffffffffu, db, 1);
+    dd += __shfl_xor_sync(0xffffffffu, dd, 2); db += __shfl_xor_sync(0xffffffffu, db, 2);
+    if (fvalid && fe == 0) {
+      float* dst = p.part + ((int64_t)b * p.dim + d0 + 2 * rp + rr) * (p.N + 2);
+      dst[p.N] = dd; dst[p.N + 1] = db;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = q + 8 * j;
+      if (n < p.N) {
+        if (v0) p.part[((int64_t)b * p.dim + d0 + 2 * rp) * (p.N + 2) + n] = dA2[j].x;
+        if (v1) p.part[((int64_t)b * p.dim + d0 + 2 * rp + 1) * (p.N + 2) + n] = dA2[j].y;
+      }
+    }
+  }
+}
+
+static bool bwd2_maps(const ScanParams& p, Bwd2Maps* m) {
+  const long long ugroups = p.u_mod > 0 ? p.u_mod / p.dpg : p.G;
+  const long long du[4] = {p.L, p.dpg, ugroups, p.batch}, su[4] = {1, p.u_ds, (long long)p.dpg * p.u_ds, p.u_bs};
+  const long long sy[4] = {1, p.out_ds, (long long)p.dpg * p.out_ds, p.out_bs};
+  const long long dd[4] = {p.L, p.dpg, p.G, p.batch}, sd[4] = {1, p.dl_ds, (long long)p.dpg * p.dl_ds, p.dl_bs};
+  const long long d4[4] = {p.L, p.N, p.G, p.batch};
+  const long long s4B[4] = {1, p.B_ns, p.B_gs, p.B_bs}, s4C[4] = {1, p.C_ns, p.C_gs, p.C_bs};
+  return make_tmap(&m->u, p.u, 4, du, su, B2_RPW) && make_tmap(&m->dl, p.delta, 4, dd, sd, B2_RPW) &&
+         make_tmap(&m->dy, p.dout, 4, du, sy, B2_RPW) && make_tmap(&m->B, p.Bm, 4, d4, s4B, 16) &&
+         make_tmap(&m->C, p.Cm, 4, d4, s4C, 16);
+}
+
+// Returns true when the fast path took the call (*err holds the launch status).
+bool scan_bwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
+  static const int enabled = getenv("SS2D_BWD_V2") ? atoi(getenv("SS2D_BWD_V2")) : 1;
+  if (!enabled || !p.tma_ok || p.N <= 8 || p.N > 16 || p.accum || p.io_dtype != SS2D_F32 || p.out_dtype != SS2D_F32) return false;
+  if (p.u_mod > 0 && p.u_mod % p.dpg != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p.du) & 15) || (reinterpret_cast<uintptr_t>(p.ddelta) & 15) ||
+      (reinterpret_cast<uintptr_t>(p.dB) & 15) || (reinterpret_cast<uintptr_t>(p.dC) & 15))
+    return false;
+  for (int g = 0; g < p.G; ++g) {
+    const int dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
+    if (dir == 2 || dir == 4) return false;
+  }
+  Bwd2Maps maps;
+  if (!bwd2_maps(p, &maps)) return false;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
+    if (e != cudaSuccess) { *err = e; return true; }
+    configured = true;
+  }
+  dim3 grid((p.dpg + B2_CH - 1) / B2_CH, p.G, p.batch);
+  scan_bwd2_kernel<<<grid, B2_NW * 32, B2_SMEM, stream>>>(p, maps);
+  *err = cudaGetLastError();
+  return true;
+}
+
+}  // namespace ss2d
