@@ -42,9 +42,48 @@ constexpr size_t B2_SMEM = B2_OFF_BARS + 256 + 1024;
 
 struct Bwd2Maps { TMap u, dl, dy, B, C; };
 
-__device__ __forceinline__ int b2_atom_add_acqrel_shared(int* addr, int v) {
+// Shared-memory accessors on 32-bit shared-window addresses: no generic-pointer arithmetic inside the loops.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d32(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ int atom_add_acqrel32(uint32_t addr, int v) {
   int old;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
 
@@ -76,17 +115,19 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   extern __shared__ __align__(16) unsigned char smem_rawb2[];
   unsigned char* smem = smem_rawb2 + ((1024 - (smem_u32(smem_rawb2) & 1023)) & 1023);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* s_bc = smem;
-  unsigned char* s_rows = smem + B2_OFF_ROWS + warp * (B2_STAGES * B2_WSTAGE);
-  unsigned char* s_up = smem + B2_OFF_UP + warp * 1024;
-  unsigned char* s_hs = smem + B2_OFF_HS + warp * B2_HS_BYTES;
-  unsigned char* s_slab = smem + B2_OFF_SLAB;                      // [2][NW][512]
+  const uint32_t sm = smem_u32(smem);
+  const uint32_t a_bc = sm;                                                  // [STAGES][B | C]
+  const uint32_t a_rows = sm + B2_OFF_ROWS + warp * (B2_STAGES * B2_WSTAGE);  // [STAGES][delta | u | dout]
+  const uint32_t a_up = sm + B2_OFF_UP + warp * 1024;                        // u pairs of the current tile
+  const uint32_t a_hs = sm + B2_OFF_HS + warp * B2_HS_BYTES + lane * 16;     // this lane's group-boundary states
+  const uint32_t a_slab = sm + B2_OFF_SLAB;                                  // [2][NW][512]
+  const uint32_t a_bars = sm + B2_OFF_BARS;
+  const uint32_t a_full_w = a_bars + warp * (B2_STAGES * 8);                 // [NW][STAGES]
+  const uint32_t a_full_bc = a_bars + B2_NW * B2_STAGES * 8;                 // [STAGES]
+  const uint32_t a_slab_full = a_full_bc + B2_STAGES * 8;                    // [2]
+  const uint32_t a_slab_empty = a_slab_full + 16;                            // [2]
+  const uint32_t a_cnt_bc = a_slab_empty + 16;                               // [STAGES] ints
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BARS);
-  uint64_t* full_w = bars + warp * B2_STAGES;                      // [NW][STAGES]
-  uint64_t* full_bc = bars + B2_NW * B2_STAGES;                    // [STAGES]
-  uint64_t* slab_full = full_bc + B2_STAGES;                       // [2]
-  uint64_t* slab_empty = slab_full + 2;                            // [2]
-  int* cnt_bc = reinterpret_cast<int*>(slab_empty + 2);            // [STAGES]
 
   const int b = blockIdx.z, g = blockIdx.y;
   const int row0 = blockIdx.x * B2_CH + warp * B2_RPW;             // first row of this warp inside the group
@@ -100,9 +141,9 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   const bool single_cta_group = gridDim.x == 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B2_NW * B2_STAGES; ++i) mbar_init(&bars[i], 1);
-    for (int s = 0; s < B2_STAGES; ++s) { mbar_init(&full_bc[s], 1); cnt_bc[s] = 0; }
-    for (int s = 0; s < 2; ++s) { mbar_init(&slab_full[s], B2_NW); mbar_init(&slab_empty[s], B2_NW); }
+    for (int i = 0; i < B2_NW * B2_STAGES + B2_STAGES; ++i) mbar_init(&bars[i], 1);          // full_w, full_bc
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[B2_NW * B2_STAGES + B2_STAGES + i], B2_NW);  // slab_full, slab_empty
+    for (int s = 0; s < B2_STAGES; ++s) reinterpret_cast<int*>(bars + B2_NW * B2_STAGES + B2_STAGES + 4)[s] = 0;
     fence_mbar_init();
   }
   __syncthreads();
@@ -111,18 +152,19 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   auto issue_rows = [&](int it) {     // lane 0 of the warp
     const int s = it % B2_STAGES, t = ntiles - 1 - it;
     const int m0 = rev ? L - t * 32 - 32 : t * 32;
-    unsigned char* st = s_rows + s * B2_WSTAGE;
-    mbar_arrive_expect_tx(&full_w[s], B2_WSTAGE);
-    tma_load_4d(st, &maps.dl, m0, row0, g, b, &full_w[s]);
-    tma_load_4d(st + 1024, &maps.u, m0, row0, ug, b, &full_w[s]);
-    tma_load_4d(st + 2048, &maps.dy, m0, row0, ug, b, &full_w[s]);
+    const uint32_t st = a_rows + s * B2_WSTAGE, bar = a_full_w + s * 8;
+    mbar_expect32(bar, B2_WSTAGE);
+    tma_load_4d32(st, &maps.dl, m0, row0, g, b, bar);
+    tma_load_4d32(st + 1024, &maps.u, m0, row0, ug, b, bar);
+    tma_load_4d32(st + 2048, &maps.dy, m0, row0, ug, b, bar);
   };
   auto issue_bc = [&](int it) {
     const int s = it % B2_STAGES, t = ntiles - 1 - it;
     const int m0 = rev ? L - t * 32 - 32 : t * 32;
-    mbar_arrive_expect_tx(&full_bc[s], B2_BC_STAGE);
-    tma_load_4d(s_bc + s * B2_BC_STAGE, &maps.B, m0, 0, g, b, &full_bc[s]);
-    tma_load_4d(s_bc + s * B2_BC_STAGE + 2048, &maps.C, m0, 0, g, b, &full_bc[s]);
+    const uint32_t bar = a_full_bc + s * 8;
+    mbar_expect32(bar, B2_BC_STAGE);
+    tma_load_4d32(a_bc + s * B2_BC_STAGE, &maps.B, m0, 0, g, b, bar);
+    tma_load_4d32(a_bc + s * B2_BC_STAGE + 2048, &maps.C, m0, 0, g, b, bar);
   };
   if (lane == 0) {
     if (warp == 0) { tma_prefetch_desc(&maps.B); tma_prefetch_desc(&maps.C); }
@@ -136,14 +178,13 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   const int q = lane & 7, rp = lane >> 3;
   const bool v0 = 2 * rp < rows_valid, v1 = 2 * rp + 1 < rows_valid;
   // main role: row pair rp, states n_j = q + 8 j
-  float2 A1p[2], A2p[2], carry2[2], dA2[2];
+  float2 A2p[2], carry2[2], dA2[2];      // A2 = A log2(e)
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int n = q + 8 * j;
     const bool okn = n < p.N;
-    A1p[j].x = (okn && v0) ? p.A[(int64_t)(d0 + 2 * rp) * p.A_ld + n] : 0.f;
-    A1p[j].y = (okn && v1) ? p.A[(int64_t)(d0 + 2 * rp + 1) * p.A_ld + n] : 0.f;
-    A2p[j] = make_float2(A1p[j].x * kLog2e, A1p[j].y * kLog2e);
+    A2p[j].x = (okn && v0) ? p.A[(int64_t)(d0 + 2 * rp) * p.A_ld + n] * kLog2e : 0.f;
+    A2p[j].y = (okn && v1) ? p.A[(int64_t)(d0 + 2 * rp + 1) * p.A_ld + n] * kLog2e : 0.f;
     carry2[j] = make_float2(0.f, 0.f);      // a_(l+1) g_(l+1), zero past the end of the sequence
     dA2[j] = make_float2(0.f, 0.f);
   }
@@ -157,6 +198,17 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   biasp.x = (p.bias && v0) ? p.bias[d0 + 2 * rp] : 0.f;
   biasp.y = (p.bias && v1) ? p.bias[d0 + 2 * rp + 1] : 0.f;
   const bool softplus = p.softplus != 0;
+  // shared-memory offsets as (lane constant) ^ (uniform term): one LOP3 per access inside the loops
+  const int rowc = (rp * 256) | (rp << 4);                                   // b2_p_off(rp, ch) = rowc ^ (su(ch) << 4)
+  const int qc = (q * 128) | (q << 4);                                       // b2_t_off(q + 8 j, c4) = (qc ^ (c4 << 4)) + 1024 j
+  const int fc = (rowc ^ ((fe >> 1) << 4)) | (((fe & 1) * 2 + rr) * 4);      // finaliser's scalar slot
+  const uint32_t slab_w = a_slab + warp * 512 + ((rp >> 1) * 16 + q) * 16 + (rp & 1) * 8;    // state q; q + 8 at + 128
+  const uint32_t slab_r = a_slab + (warp * 8 + (lane & 7)) * 16;
+  // dB / dC destination of this lane in the folding step (lanes 0-7): tensor o >> 4, state o & 15
+  const int ro = warp * 8 + (lane & 7);
+  float* const red_base = ((ro >> 4) == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + (ro & 15)) * L;
+  const bool red_ok = lane < 8 && (ro & 15) < p.N;
+  const int lmax = ntiles * 32 - 4;                                          // scan position of global group 0
 
   auto load_ckpt = [&](int t, float2* h) {     // state before tile t = checkpoint at the end of tile t - 1
 #pragma unroll
@@ -167,35 +219,28 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       h[j].y = (ok && v1) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp + 1) * p.nck + (t - 1)) * p.N + n) : 0.f;
     }
   };
-  float2 h0_next[2];
-  load_ckpt(ntiles - 1, h0_next);
 
   // dB / dC of global group kk (all warps wrote their slab): fold the NW slabs, one vector reduction per (state, 4 pos)
   auto reduce_group = [&](int kk, auto REV) {
     constexpr bool REVV = decltype(REV)::value;
     const int buf = kk & 1;
-    mbar_wait(&slab_full[buf], (kk >> 1) & 1);
-    if (lane < 8) {
-      const int o = warp * 8 + lane;                       // [dB | dC][16 states]
-      const unsigned char* src = s_slab + buf * (B2_NW * 512) + o * 16;
-      float4 acc = *reinterpret_cast<const float4*>(src);
+    mbar_wait32(a_slab_full + buf * 8, (kk >> 1) & 1);
+    const int l = lmax - 4 * kk;                            // first scan position of the group
+    if (red_ok && l < L) {
+      const uint32_t src = slab_r + buf * (B2_NW * 512);
+      float4 acc = lds128(src);
 #pragma unroll
       for (int w = 1; w < B2_NW; ++w) {
-        const float4 v = *reinterpret_cast<const float4*>(src + w * 512);
+        const float4 v = lds128(src + w * 512);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
-      const int which = o >> 4, n = o & 15;
-      const int t = ntiles - 1 - (kk >> 3), gi = 7 - (kk & 7);
-      const int l = t * 32 + gi * 4;
-      if (n < p.N && l < L) {
-        float* dst = (which == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + n) * L + (REVV ? L - 4 - l : l);
-        if (REVV) acc = make_float4(acc.w, acc.z, acc.y, acc.x);
-        if (single_cta_group) *reinterpret_cast<float4*>(dst) = acc;
-        else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
-      }
+      float* dst = red_base + (REVV ? L - 4 - l : l);
+      if (REVV) acc = make_float4(acc.w, acc.z, acc.y, acc.x);
+      if (single_cta_group) *reinterpret_cast<float4*>(dst) = acc;
+      else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&slab_empty[buf]);
+    if (lane == 0) mbar_arrive32(a_slab_empty + buf * 8);
   };
 
   auto body = [&](auto REV) {
@@ -205,20 +250,22 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       const int s = it % B2_STAGES;
       const uint32_t par = (it / B2_STAGES) & 1;
       const int l0 = t * 32, len = min(32, L - l0);
-      unsigned char* s_dl = s_rows + s * B2_WSTAGE;       // delta  -> delta' pairs -> d(delta)
-      unsigned char* s_du = s_dl + 1024;                  // u      -> (delta' u) pairs
-      unsigned char* s_dy = s_dl + 2048;                  // dout   -> dout' pairs  -> du
-      mbar_wait(&full_w[s], par);
+      const uint32_t a_dl = a_rows + s * B2_WSTAGE;       // delta  -> delta' pairs -> d(delta)
+      const uint32_t a_du = a_dl + 1024;                  // u      -> (delta' u) pairs
+      const uint32_t a_dy = a_dl + 2048;                  // dout   -> dout' pairs  -> du
+      float2 h0[2];
+      load_ckpt(t, h0);                                   // in flight during the activation pass
+      mbar_wait32(a_full_w + s * 8, par);
       // ---- activation + row-pair interleave, in place: this lane handles position quad q of row pair rp ----
       {
         const int tc4 = REVV ? 7 - q : q;
         float4 dv[2], uv[2], yv[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const int o = b2_t_off(2 * rp + r, tc4);
-          dv[r] = *reinterpret_cast<const float4*>(s_dl + o);
-          uv[r] = *reinterpret_cast<const float4*>(s_du + o);
-          yv[r] = *reinterpret_cast<const float4*>(s_dy + o);
+          const uint32_t o = b2_t_off(2 * rp + r, tc4);
+          dv[r] = lds128(a_dl + o);
+          uv[r] = lds128(a_du + o);
+          yv[r] = lds128(a_dy + o);
           if (REVV) {
             dv[r] = make_float4(dv[r].w, dv[r].z, dv[r].y, dv[r].x);
             uv[r] = make_float4(uv[r].w, uv[r].z, uv[r].y, uv[r].x);
@@ -239,40 +286,32 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
           }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {              // chunk 2 q + hh: positions 4 q + 2 hh, + 1
-          const int off = b2_p_off(rp, 2 * q + hh);
-          *reinterpret_cast<float4*>(s_dl + off) = make_float4(dl[0][2 * hh], dl[1][2 * hh], dl[0][2 * hh + 1], dl[1][2 * hh + 1]);
-          *reinterpret_cast<float4*>(s_du + off) = make_float4(du[0][2 * hh], du[1][2 * hh], du[0][2 * hh + 1], du[1][2 * hh + 1]);
-          *reinterpret_cast<float4*>(s_dy + off) =
-              make_float4(f4_at(yv[0], 2 * hh), f4_at(yv[1], 2 * hh), f4_at(yv[0], 2 * hh + 1), f4_at(yv[1], 2 * hh + 1));
-          *reinterpret_cast<float4*>(s_up + off) =
-              make_float4(f4_at(uv[0], 2 * hh), f4_at(uv[1], 2 * hh), f4_at(uv[0], 2 * hh + 1), f4_at(uv[1], 2 * hh + 1));
+          const uint32_t off = b2_p_off(rp, 2 * q + hh);
+          sts128(a_dl + off, make_float4(dl[0][2 * hh], dl[1][2 * hh], dl[0][2 * hh + 1], dl[1][2 * hh + 1]));
+          sts128(a_du + off, make_float4(du[0][2 * hh], du[1][2 * hh], du[0][2 * hh + 1], du[1][2 * hh + 1]));
+          sts128(a_dy + off, make_float4(f4_at(yv[0], 2 * hh), f4_at(yv[1], 2 * hh), f4_at(yv[0], 2 * hh + 1), f4_at(yv[1], 2 * hh + 1)));
+          sts128(a_up + off, make_float4(f4_at(uv[0], 2 * hh), f4_at(uv[1], 2 * hh), f4_at(uv[0], 2 * hh + 1), f4_at(uv[1], 2 * hh + 1)));
         }
         __syncwarp();
       }
-      mbar_wait(&full_bc[s], par);
-      const unsigned char* s_B = s_bc + s * B2_BC_STAGE;
-      const unsigned char* s_C = s_B + 2048;
+      mbar_wait32(a_full_bc + s * 8, par);
+      const uint32_t a_B = a_bc + s * B2_BC_STAGE;
 
       // ---- (1) forward recompute of h over the tile from the chunk checkpoint; the state after each of the first
-      //          7 groups is parked in shared memory. The checkpoint of the NEXT tile is fetched a whole tile ahead.
-      float2 h0[2];
-      h0[0] = h0_next[0]; h0[1] = h0_next[1];
-      load_ckpt(t - 1, h0_next);
+      //          7 groups is parked in shared memory. 
       {
         float2 h[2] = {h0[0], h0[1]};
 #pragma unroll 1
         for (int gi = 0; gi < 7; ++gi) {
-          const int pofs = b2_p_off(rp, 2 * gi);
-          const float4 d01 = *reinterpret_cast<const float4*>(s_dl + pofs);
-          const float4 d23 = *reinterpret_cast<const float4*>(s_dl + (pofs ^ 16));
-          const float4 u01 = *reinterpret_cast<const float4*>(s_du + pofs);
-          const float4 u23 = *reinterpret_cast<const float4*>(s_du + (pofs ^ 16));
+          const uint32_t pa = a_dl + (rowc ^ (((2 * gi ^ (gi >> 2)) & 15) << 4));
+          const float4 d01 = lds128(pa), d23 = lds128(pa ^ 16);
+          const float4 u01 = lds128(pa + 1024), u23 = lds128((pa ^ 16) + 1024);
           const float2 dl2[4] = {make_float2(d01.x, d01.y), make_float2(d01.z, d01.w), make_float2(d23.x, d23.y), make_float2(d23.z, d23.w)};
           const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
-          const int tc4 = REVV ? 7 - gi : gi;
+          const uint32_t ba = a_B + (qc ^ ((REVV ? 7 - gi : gi) << 4));
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            float4 Bq = *reinterpret_cast<const float4*>(s_B + b2_t_off(q + 8 * j, tc4));
+            float4 Bq = lds128(ba + 1024 * j);
             if (REVV) Bq = make_float4(Bq.w, Bq.z, Bq.y, Bq.x);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -282,7 +321,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
               h[j] = __ffma2_rn(a, h[j], __fmul2_rn(du2[e], make_float2(be, be)));
             }
           }
-          *reinterpret_cast<float4*>(s_hs + (gi * 32 + lane) * 16) = make_float4(h[0].x, h[0].y, h[1].x, h[1].y);
+          sts128(a_hs + gi * 512, make_float4(h[0].x, h[0].y, h[1].x, h[1].y));
         }
       }
 
@@ -290,28 +329,26 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
 #pragma unroll 1
       for (int gi = 7; gi >= 0; --gi) {
         const int k = it * 8 + (7 - gi);                 // global group counter (slab hand-off)
-        const int pofs = b2_p_off(rp, 2 * gi);
-        const float4 d01 = *reinterpret_cast<const float4*>(s_dl + pofs);
-        const float4 d23 = *reinterpret_cast<const float4*>(s_dl + (pofs ^ 16));
-        const float4 u01 = *reinterpret_cast<const float4*>(s_du + pofs);
-        const float4 u23 = *reinterpret_cast<const float4*>(s_du + (pofs ^ 16));
-        const float4 y01 = *reinterpret_cast<const float4*>(s_dy + pofs);
-        const float4 y23 = *reinterpret_cast<const float4*>(s_dy + (pofs ^ 16));
+        const int su4 = ((2 * gi ^ (gi >> 2)) & 15) << 4;
+        const uint32_t pa = a_dl + (rowc ^ su4);
+        const float4 d01 = lds128(pa), d23 = lds128(pa ^ 16);
+        const float4 u01 = lds128(pa + 1024), u23 = lds128((pa ^ 16) + 1024);
+        const float4 y01 = lds128(pa + 2048), y23 = lds128((pa ^ 16) + 2048);
         const float2 dl2[4] = {make_float2(d01.x, d01.y), make_float2(d01.z, d01.w), make_float2(d23.x, d23.y), make_float2(d23.z, d23.w)};
         const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
         const float2 dy2[4] = {make_float2(y01.x, y01.y), make_float2(y01.z, y01.w), make_float2(y23.x, y23.y), make_float2(y23.z, y23.w)};
         float4 hin4;
-        if (gi > 0) hin4 = *reinterpret_cast<const float4*>(s_hs + ((gi - 1) * 32 + lane) * 16);
+        if (gi > 0) hin4 = lds128(a_hs + (gi - 1) * 512);
         else hin4 = make_float4(h0[0].x, h0[0].y, h0[1].x, h0[1].y);
-        const int tc4 = REVV ? 7 - gi : gi;
+        const uint32_t ba = a_B + (qc ^ ((REVV ? 7 - gi : gi) << 4));
         float2 sB2[4], sA2[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { sB2[e] = make_float2(0.f, 0.f); sA2[e] = make_float2(0.f, 0.f); }
-        float part[16];                                  // [dB | dC][j][e], the two rows already added
+        float pout[2][2];                                // after the row-pair-lane reduction: [j][2 positions]
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          float4 Bq = *reinterpret_cast<const float4*>(s_B + b2_t_off(q + 8 * j, tc4));
-          float4 Cq = *reinterpret_cast<const float4*>(s_C + b2_t_off(q + 8 * j, tc4));
+          float4 Bq = lds128(ba + 1024 * j);
+          float4 Cq = lds128(ba + 2048 + 1024 * j);
           if (REVV) { Bq = make_float4(Bq.w, Bq.z, Bq.y, Bq.x); Cq = make_float4(Cq.w, Cq.z, Cq.y, Cq.x); }
           const float2 hprev = j == 0 ? make_float2(hin4.x, hin4.y) : make_float2(hin4.z, hin4.w);
           float2 a2[4], hh2[4];
@@ -323,6 +360,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
             hh2[e] = __ffma2_rn(a2[e], e == 0 ? hprev : hh2[e - 1], __fmul2_rn(du2[e], make_float2(be, be)));
           }
           float2 carry = carry2[j];
+          float part[8];                                 // [dB | dC][e], the two rows of the pair already added
 #pragma unroll
           for (int e = 3; e >= 0; --e) {
             const float be = f4_at(Bq, e), ce = f4_at(Cq, e);
@@ -331,14 +369,17 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
             carry = t2;
             const float2 pb = __fmul2_rn(g2, du2[e]);
             const float2 pc = __fmul2_rn(dy2[e], hh2[e]);
-            part[j * 4 + e] = pb.x + pb.y;
-            part[8 + j * 4 + e] = pc.x + pc.y;
+            part[e] = pb.x + pb.y;
+            part[4 + e] = pc.x + pc.y;
             sB2[e] = __ffma2_rn(g2, make_float2(be, be), sB2[e]);
             const float2 w2 = __fmul2_rn(t2, e == 0 ? hprev : hh2[e - 1]);        // g_e (h_e - delta u B_e)
-            sA2[e] = __ffma2_rn(w2, A1p[j], sA2[e]);
+            sA2[e] = __ffma2_rn(w2, A2p[j], sA2[e]);                           // scaled by log2(e): undone below
             dA2[j] = __ffma2_rn(w2, dl2[e], dA2[j]);
           }
           carry2[j] = carry;
+          // sum over the 4 row-pair lanes: lane (rp, q) keeps positions 2 (rp & 1), + 1 of tensor rp >> 1, state q + 8 j
+          B2ReduceScatter<8, 8, 2>::run(part, rp);
+          pout[j][0] = part[0]; pout[j][1] = part[1];
         }
         // ---- sum over the 8 state lanes; lane q ends up with (sB, sA) of row parity q >> 2, position q & 3 ----
         float vals[16];                                  // [row parity][e][sB | sA]
@@ -349,11 +390,11 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
         }
         B2ReduceScatter<1, 16, 4>::run(vals, q);
         {
-          const int off = b2_p_off(rp, 2 * gi + (fe >> 1)) + ((fe & 1) * 2 + rr) * 4;
-          const float de = *reinterpret_cast<const float*>(s_dl + off);
-          const float dyv = *reinterpret_cast<const float*>(s_dy + off);
-          const float uu = *reinterpret_cast<const float*>(s_up + off);
-          const float sBe = vals[0], sAe = vals[1];
+          const uint32_t off = fc ^ su4;
+          const float de = lds32(a_dl + off);
+          const float dyv = lds32(a_dy + off);
+          const float uu = lds32(a_up + off);
+          const float sBe = vals[0], sAe = vals[1] * kLn2;
           const float du_out = fmaf(Dr, dyv, de * sBe);
           float ddl = fmaf(uu, sBe, sAe);
           if (softplus) {   // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
@@ -364,27 +405,26 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
           dDacc = fmaf(dyv, uu, dDacc);
           dbacc += ddl;
           // every lane of the row pair has consumed this group's delta' / dout' (the shuffles above ordered them)
-          *reinterpret_cast<float*>(s_dy + off) = du_out;
-          *reinterpret_cast<float*>(s_dl + off) = ddl;
+          sts32(a_dy + off, du_out);
+          sts32(a_dl + off, ddl);
         }
-        // ---- sum over the 4 row-pair lanes; lane (rp, q) ends up with 4 positions of tensor rp >> 1, state q + 8 (rp & 1)
-        B2ReduceScatter<8, 16, 2>::run(part, rp);
+        // ---- park this warp's dB / dC totals of the group in its slab: [dB | dC][16 states][4 positions] ----
         {
           const int buf = k & 1;
-          mbar_wait(&slab_empty[buf], ((k >> 1) & 1) ^ 1);
-          *reinterpret_cast<float4*>(s_slab + (buf * B2_NW + warp) * 512 + ((rp >> 1) * 16 + q + 8 * (rp & 1)) * 16) =
-              make_float4(part[0], part[1], part[2], part[3]);
+          mbar_wait32(a_slab_empty + buf * 8, ((k >> 1) & 1) ^ 1);
+          sts64(slab_w + buf * (B2_NW * 512), make_float2(pout[0][0], pout[0][1]));
+          sts64(slab_w + buf * (B2_NW * 512) + 8 * 16, make_float2(pout[1][0], pout[1][1]));
           __syncwarp();
-          if (lane == 0) mbar_arrive(&slab_full[buf]);
+          if (lane == 0) mbar_arrive32(a_slab_full + buf * 8);
           if (k > 0) reduce_group(k - 1, REV);
         }
       }
       __syncwarp();
       // ---- tile epilogue: du / d(delta) of this warp's rows, 128-bit row-contiguous stores ----
       {
-        const int off0 = b2_p_off(rp, 2 * q), off1 = b2_p_off(rp, 2 * q + 1);
-        const float4 ua = *reinterpret_cast<const float4*>(s_dy + off0), ub = *reinterpret_cast<const float4*>(s_dy + off1);
-        const float4 da = *reinterpret_cast<const float4*>(s_dl + off0), db = *reinterpret_cast<const float4*>(s_dl + off1);
+        const uint32_t off0 = b2_p_off(rp, 2 * q), off1 = b2_p_off(rp, 2 * q + 1);
+        const float4 ua = lds128(a_dy + off0), ub = lds128(a_dy + off1);
+        const float4 da = lds128(a_dl + off0), db = lds128(a_dl + off1);
         const int l = l0 + 4 * q;
         if (l < L) {
           const int64_t mpos = REVV ? L - 4 - l : l;
@@ -408,8 +448,8 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       __syncwarp();
       if (lane == 0) {
         if (it + B2_STAGES < ntiles) issue_rows(it + B2_STAGES);
-        if (b2_atom_add_acqrel_shared(&cnt_bc[s], 1) == B2_NW - 1) {      // last warp to release the B/C stage refills it
-          cnt_bc[s] = 0;
+        if (atom_add_acqrel32(a_cnt_bc + s * 4, 1) == B2_NW - 1) {      // last warp to release the B/C stage refills it
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_cnt_bc + s * 4), "r"(0) : "memory");
           if (it + B2_STAGES < ntiles) issue_bc(it + B2_STAGES);
         }
       }

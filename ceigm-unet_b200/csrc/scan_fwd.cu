@@ -276,11 +276,7 @@ static cudaError_t launch_fwd(ScanParams p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-bool scan_fwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err);   // scan_fwd2.cu
-
 cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream) {
-  cudaError_t e2;
-  if (scan_fwd2_try(p, stream, &e2)) return e2;     // fast path: fp32 + TMA, 8 < N <= 16, contiguous traversal
   const Variant v = pick_variant(p.N);
   if (v.NS == 1) return launch_fwd<1, 1, 1, 3>(p, stream);
   if (v.NS == 2) return launch_fwd<2, 1, 1, 3>(p, stream);
