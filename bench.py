@@ -192,7 +192,12 @@ def run_ours(args, rank, world, local_rank):
         fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
         bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
         ach = bwd_b / (bwd_ms * 1e-3) / 1e9
-        kname = "scan_par_bwd_kernel" if all(c[4] == 1 for c in calls) else "scan_bwd_kernel"
+        if all(c[4] == 1 for c in calls):
+            kname = "scan_par_bwd_kernel"
+        elif all(8 < c[4] <= 16 for c in calls):
+            kname = "scan_bwd2_kernel"         # fp32 + TMA fast path (csrc/scan_bwd2.cu)
+        else:
+            kname = "scan_bwd_kernel"
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tpath):
@@ -203,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"bound": "hbm", "kernel": kname + " (+ finalize and dB/dC memsets inside the bwd call)",
                     "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                     "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": bwd_b, "peak_source": peak_src,
-                    "note": "d_state=16 is MUFU.EX2/FMA-bound on B200, not HBM-bound: see DESIGN.md"}
+                    "note": "d_state=16 is instruction-issue / MUFU.EX2 bound on B200, not HBM-bound: see DESIGN.md §3"}
         extra = {"fwd_ms": round(fwd_ms, 4), "bwd_ms": round(bwd_ms, 4),
                  "fwd_GBps": round(fwd_b / (fwd_ms * 1e-3) / 1e9, 1), "bwd_GBps": round(ach, 1),
                  "fwd_frac_of_peak": round(fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, 4)}
