@@ -201,13 +201,19 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   // shared-memory offsets as (lane constant) ^ (uniform term): one LOP3 per access inside the loops
   const int rowc = (rp * 256) | (rp << 4);                                   // b2_p_off(rp, ch) = rowc ^ (su(ch) << 4)
   const int qc = (q * 128) | (q << 4);                                       // b2_t_off(q + 8 j, c4) = (qc ^ (c4 << 4)) + 1024 j
-  const int fc = (rowc ^ ((fe >> 1) << 4)) | (((fe & 1) * 2 + rr) * 4);      // finaliser's scalar slot
-  const uint32_t slab_w = a_slab + warp * 512 + ((rp >> 1) * 16 + q) * 16 + (rp & 1) * 8;    // state q; q + 8 at + 128
-  const uint32_t slab_r = a_slab + (warp * 8 + (lane & 7)) * 16;
-  // dB / dC destination of this lane in the folding step (lanes 0-7): tensor o >> 4, state o & 15
-  const int ro = warp * 8 + (lane & 7);
+  // Lane constants of the finishing / folding steps, packed into ONE opaque register: at the 128-register cap ptxas
+  // otherwise re-derives each of them from %tid in every group (~35 instructions per group).
+  //   bits 0-9: finisher's scalar slot; 10-21: slab write offset; 22-26: slab read slot; 27-30: dB/dC state; 31: folds
+  const int ro = warp * 8 + (lane & 7);                                      // folding step (lanes 0-7): tensor ro >> 4, state ro & 15
+  uint32_t pk;
+  {
+    const uint32_t fc0 = (rowc ^ ((fe >> 1) << 4)) | (((fe & 1) * 2 + rr) * 4);
+    const uint32_t sw0 = warp * 512 + ((rp >> 1) * 16 + q) * 16 + (rp & 1) * 8;   // state q; q + 8 at + 128
+    const uint32_t ok0 = (lane < 8 && (ro & 15) < p.N) ? 1u : 0u;
+    const uint32_t v = fc0 | (sw0 << 10) | ((uint32_t)ro << 22) | (ok0 << 31);
+    asm volatile("mov.b32 %0, %1;" : "=r"(pk) : "r"(v));
+  }
   float* const red_base = ((ro >> 4) == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + (ro & 15)) * L;
-  const bool red_ok = lane < 8 && (ro & 15) < p.N;
   const int lmax = ntiles * 32 - 4;                                          // scan position of global group 0
 
   auto load_ckpt = [&](int t, float2* h) {     // state before tile t = checkpoint at the end of tile t - 1
@@ -226,8 +232,8 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
     const int buf = kk & 1;
     mbar_wait32(a_slab_full + buf * 8, (kk >> 1) & 1);
     const int l = lmax - 4 * kk;                            // first scan position of the group
-    if (red_ok && l < L) {
-      const uint32_t src = slab_r + buf * (B2_NW * 512);
+    if ((int)pk < 0 && l < L) {
+      const uint32_t src = a_slab + ((pk >> 22) & 31) * 16 + buf * (B2_NW * 512);
       float4 acc = lds128(src);
 #pragma unroll
       for (int w = 1; w < B2_NW; ++w) {
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
         }
         B2ReduceScatter<1, 16, 4>::run(vals, q);
         {
-          const uint32_t off = fc ^ su4;
+          const uint32_t off = (pk & 1023) ^ su4;
           const float de = lds32(a_dl + off);
           const float dyv = lds32(a_dy + off);
           const float uu = lds32(a_up + off);
@@ -412,8 +418,9 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
         {
           const int buf = k & 1;
           mbar_wait32(a_slab_empty + buf * 8, ((k >> 1) & 1) ^ 1);
-          sts64(slab_w + buf * (B2_NW * 512), make_float2(pout[0][0], pout[0][1]));
-          sts64(slab_w + buf * (B2_NW * 512) + 8 * 16, make_float2(pout[1][0], pout[1][1]));
+          const uint32_t slab_w = a_slab + ((pk >> 10) & 4095) + buf * (B2_NW * 512);
+          sts64(slab_w, make_float2(pout[0][0], pout[0][1]));
+          sts64(slab_w + 8 * 16, make_float2(pout[1][0], pout[1][1]));
           __syncwarp();
           if (lane == 0) mbar_arrive32(a_slab_full + buf * 8);
           if (k > 0) reduce_group(k - 1, REV);
