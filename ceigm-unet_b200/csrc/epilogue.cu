@@ -121,9 +121,12 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
   float* s_g = s_y + (size_t)D * (kEpiTL + 1);     // [D][33] d(yn) = dout * gate * w
   __shared__ float s_stat[kEpiTL][4];              // mean, rstd, mean(g), mean(g * yn)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float s_red[2][kEpiThreads];          // pixel-lane partials of the LayerNorm weight / bias gradients
   float acc_dw[kEpiMaxDPT], acc_db[kEpiMaxDPT];
 #pragma unroll
   for (int m = 0; m < kEpiMaxDPT; ++m) { acc_dw[m] = 0.f; acc_db[m] = 0.f; }
+  const int PP = D >= kEpiThreads ? 1 : (kEpiThreads / D < kEpiTL ? kEpiThreads / D : kEpiTL);   // pixel lanes
+  const int pl = threadIdx.x / D, dl = threadIdx.x - pl * D;
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
     const int b = tile / tiles_per_batch, tib = tile - b * tiles_per_batch;
     __syncthreads();
@@ -134,33 +137,44 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       s_stat[px][1] = l >= 0 ? mean_rstd[((int64_t)b * L + l) * 2 + 1] : 0.f;
     }
     __syncthreads();
-    // pass 1 (threads along D, coalesced): gate grads and d(yn). Thread t always meets channels t, t+256, ... so
-    // the LayerNorm weight/bias gradients accumulate in registers, without atomics.
-#pragma unroll 4
-    for (int px = 0; px < kEpiTL; ++px) {
+    // pass 1 (threads along D, coalesced): gate grads and d(yn). A thread always meets the same channels, so the
+    // LayerNorm weight/bias gradients accumulate in registers, without atomics. For D < 256 (the live GM-UNet regime:
+    // D = 16 ... 112) the block is folded into PP = 256 / D pixel lanes x D channels so that every thread has work and
+    // a warp still reads whole contiguous pixel rows of dout / z (consecutive pixels are consecutive in memory);
+    // the pixel lanes' partials are summed once, at the end of the kernel.
+    auto pass1 = [&](int px, int d, int m) {
       const int l = pi.pixel(tib, px);
-#pragma unroll
-      for (int m = 0; m < kEpiMaxDPT; ++m) {
-        const int d = threadIdx.x + m * kEpiThreads;
-        if (d >= D) break;
-        float g = 0.f;
-        if (l >= 0) {
-          const float yn = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
-          const float w = lnw ? __ldg(lnw + d) : 1.f;
-          const float lin = lnw ? fmaf(yn, w, lnb ? __ldg(lnb + d) : 0.f) : yn;
-          float go = load1(dout, ((int64_t)b * L + l) * D + d, out_dtype);
-          if (z) {
-            const float zr = load1(z, ((int64_t)b * L + l) * z_rs + d, z_dtype);
-            const float gate = z_act ? silu_f(zr) : zr;
-            if (dz) store1(dz, ((int64_t)b * L + l) * dz_rs + d, z_dtype, go * lin * (z_act ? silu_grad_f(zr) : 1.f));
-            go *= gate;
-          }
-          acc_dw[m] = fmaf(go, yn, acc_dw[m]);
-          acc_db[m] += go;
-          g = go * w;
+      float g = 0.f;
+      if (l >= 0) {
+        const float yn = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
+        const float w = lnw ? __ldg(lnw + d) : 1.f;
+        const float lin = lnw ? fmaf(yn, w, lnb ? __ldg(lnb + d) : 0.f) : yn;
+        float go = load1(dout, ((int64_t)b * L + l) * D + d, out_dtype);
+        if (z) {
+          const float zr = load1(z, ((int64_t)b * L + l) * z_rs + d, z_dtype);
+          const float gate = z_act ? silu_f(zr) : zr;
+          if (dz) store1(dz, ((int64_t)b * L + l) * dz_rs + d, z_dtype, go * lin * (z_act ? silu_grad_f(zr) : 1.f));
+          go *= gate;
         }
-        s_g[d * (kEpiTL + 1) + px] = g;
+        acc_dw[m] = fmaf(go, yn, acc_dw[m]);
+        acc_db[m] += go;
+        g = go * w;
       }
+      s_g[d * (kEpiTL + 1) + px] = g;
+    };
+    if (PP == 1) {
+#pragma unroll 4
+      for (int px = 0; px < kEpiTL; ++px) {
+#pragma unroll
+        for (int m = 0; m < kEpiMaxDPT; ++m) {
+          const int d = threadIdx.x + m * kEpiThreads;
+          if (d >= D) break;
+          pass1(px, d, m);
+        }
+      }
+    } else if (pl < PP) {
+#pragma unroll 4
+      for (int px = pl; px < kEpiTL; px += PP) pass1(px, dl, 0);
     }
     __syncthreads();
     for (int px = warp; px < kEpiTL; px += kEpiThreads / 32) {
@@ -186,12 +200,24 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       dy[((int64_t)b * D + d) * L + l] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
     }
   }
+  if (PP == 1) {
 #pragma unroll
-  for (int m = 0; m < kEpiMaxDPT; ++m) {
-    const int d = threadIdx.x + m * kEpiThreads;
-    if (d < D) {
-      dw_part[(int64_t)blockIdx.x * D + d] = acc_dw[m];
-      db_part[(int64_t)blockIdx.x * D + d] = acc_db[m];
+    for (int m = 0; m < kEpiMaxDPT; ++m) {
+      const int d = threadIdx.x + m * kEpiThreads;
+      if (d < D) {
+        dw_part[(int64_t)blockIdx.x * D + d] = acc_dw[m];
+        db_part[(int64_t)blockIdx.x * D + d] = acc_db[m];
+      }
+    }
+  } else {
+    s_red[0][threadIdx.x] = acc_dw[0];
+    s_red[1][threadIdx.x] = acc_db[0];
+    __syncthreads();
+    if (threadIdx.x < D) {
+      float sw = 0.f, sb = 0.f;
+      for (int i = 0; i < PP; ++i) { sw += s_red[0][i * D + threadIdx.x]; sb += s_red[1][i * D + threadIdx.x]; }
+      dw_part[(int64_t)blockIdx.x * D + threadIdx.x] = sw;
+      db_part[(int64_t)blockIdx.x * D + threadIdx.x] = sb;
     }
   }
 }

@@ -152,8 +152,9 @@ class ScanProblem:
         du = torch.empty((self.batch, self.dim, self.L), dtype=u.dtype, device=dev) if self.u_mod else torch.empty_like(u)
         ddelta = torch.empty_like(delta)
         dA = torch.empty_like(self.A)
-        dB = torch.zeros((self.batch, self.G, self.N, self.L), dtype=torch.float32, device=dev)
-        dC = torch.zeros_like(dB)
+        # one zero-fill launch for both accumulators (the live GM-UNet regime is launch-bound: 104 scan calls per step)
+        dBC = torch.zeros((2, self.batch, self.G, self.N, self.L), dtype=torch.float32, device=dev)
+        dB, dC = dBC[0], dBC[1]
         dD = torch.empty_like(self.D) if self.D is not None else None
         dbias = torch.empty_like(self.bias) if self.bias is not None else None
         ckpt = self._ckpt_from_x(x)

@@ -118,3 +118,40 @@ def test_dropin_modules_serve_the_reference_functions():
     assert rel_err(out, g["out"]) < 1e-3
     for k in ("u", "delta", "A", "B", "C", "D", "delta_bias"):
         assert rel_err(t[k].grad, g["grad_" + k]) < 1e-3, k
+
+
+def test_group_mamba_layer_cuda_graphs_match_eager():
+    """P.graphed(): forward and backward of a whole GroupMambaLayer replayed from CUDA graphs give the eager result
+    (outputs, input gradient and every parameter gradient)."""
+    import copy
+
+    import ceigm_unet_b200 as P
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, layer):
+            super().__init__()
+            self.layer = layer
+
+        def forward(self, x):
+            return self.layer(x, 14, 14)
+
+    torch.manual_seed(0)
+    eager = Wrap(P.GroupMambaLayer(64, 64)).cuda()
+    captured = copy.deepcopy(eager)               # graphed() must see the module before its first eager backward
+    x = torch.randn(3, 196, 64, device="cuda", requires_grad=True)
+    gy = torch.randn(3, 196, 64, device="cuda")
+    g = P.graphed(captured, (x.detach().clone().requires_grad_(True),))
+    outs = []
+    for fn, mod in ((g, captured), (eager, eager)):
+        for _ in range(2):                        # replay twice: static buffers are reused
+            x.grad = None
+            for p_ in mod.parameters():
+                p_.grad = None
+            y = fn(x)
+            y.backward(gy)
+        outs.append((y.detach().clone(), x.grad.clone(), [p_.grad.clone() for p_ in mod.parameters()]))
+    (y1, gx1, gp1), (y2, gx2, gp2) = outs
+    assert rel_err(y1, y2.cpu().numpy()) < 1e-5
+    assert rel_err(gx1, gx2.cpu().numpy()) < 1e-5
+    for a, b in zip(gp1, gp2):
+        assert rel_err(a, b.cpu().numpy()) < 1e-4
