@@ -218,7 +218,7 @@ def run_ours(args, rank, world, local_rank):
     #      kernels and D2H of different chunks overlap (samples are independent; dA/dD/dbias are summed on the host).
     pinned = [(c, {k: v.pin_memory() for k, v in inp.items()}) for c, inp in host_sets]
     h2d = sum(c * sum(v.numel() * 4 for v in inp.values()) for c, inp in pinned)
-    streams = [torch.cuda.Stream(device) for _ in range(2)]
+    streams = [torch.cuda.Stream(device) for _ in range(args.e2e_streams)]
     res_host = {}
     BATCHED = ("u", "delta", "B", "C", "dout")
 
@@ -226,11 +226,11 @@ def run_ours(args, rank, world, local_rank):
         d2h = 0
         for ci, (count, inp) in enumerate(pinned):
             nb = inp["u"].shape[0]
-            nchunk = 4 if nb >= 8 else 1
+            nchunk = min(args.e2e_chunks, nb) if nb >= 8 else 1
             for rep in range(count):
                 for ch in range(nchunk):
                     a, bnd = D.shard_batch(nb, ch, nchunk)
-                    st = streams[ch % 2]
+                    st = streams[ch % len(streams)]
                     with torch.cuda.stream(st):
                         t_ = {k: (v[a:bnd] if k in BATCHED else v).to(device, non_blocking=True) for k, v in inp.items()}
                         out, x = core.fwd(t_["u"], t_["delta"], t_["A"], t_["B"], t_["C"], t_["D"], t_["delta_bias"], True, 1)
@@ -268,7 +268,7 @@ def run_ours(args, rank, world, local_rank):
                    "alg_bytes_fwd": fwd_b, "alg_bytes_bwd": bwd_b, "per_gpu_batch": calls[0][1]},
         "frac_of_hbm_peak": round(value / world / peak, 4),
         "e2e": {"value": round(e2e_val, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "note": "pinned host buffers; every input copied in and every result copied out per step; batch chunks pipelined over 2 streams"},
+                "steps": e2e_steps, "note": "pinned host buffers; every input copied in and every result copied out per step; %d batch chunks pipelined over %d streams (PCIe-bound)" % (args.e2e_chunks, args.e2e_streams)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
     line.update(extra)
@@ -427,6 +427,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="batch chunks of the end-to-end leg (H2D / scan / D2H pipelining)")
+    ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--no-extras", action="store_true", help="skip the other_workloads context block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
