@@ -34,6 +34,11 @@ cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const 
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
                                 int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream);
 int epi_bwd_partials(int batch, int L);
+bool wgrad_ts_supported(int M, int N);
+size_t wgrad_ts_workspace_floats(int64_t total_rows, int M, int N);
+cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch, int rows, int M, int N, int64_t y_bs,
+                            int64_t y_rs, int64_t y_cs, int64_t x_bs, int64_t x_rs, int64_t x_cs, int y_dt, int x_dt,
+                            float* workspace, cudaStream_t stream);
 int epi_max_D(bool backward);
 
 thread_local char g_cuda_err[256] = "";
@@ -274,6 +279,29 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                                       z_dtype, out_dtype, H, W, transposed_mask, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
+  return SS2D_OK;
+}
+
+size_t ss2d_wgrad_ts_workspace_bytes(int32_t batch, int32_t rows, int32_t M, int32_t N) {
+  if (batch <= 0 || rows <= 0 || !wgrad_ts_supported(M, N)) return 0;
+  return wgrad_ts_workspace_floats((int64_t)batch * rows, M, N) * sizeof(float);
+}
+
+int ss2d_wgrad_ts(const void* dY, const void* X, float* dW, int32_t batch, int32_t rows, int32_t M, int32_t N,
+                  int64_t dy_batch_stride, int64_t dy_row_stride, int64_t dy_col_stride, int64_t x_batch_stride,
+                  int64_t x_row_stride, int64_t x_col_stride, int32_t dy_dtype, int32_t x_dtype, void* workspace,
+                  size_t workspace_bytes, ss2d_stream_t stream) {
+  if (!dY || !X || !dW) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || rows <= 0 || M <= 0 || N <= 0) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dy_dtype) || !dtype_ok(x_dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (!wgrad_ts_supported(M, N)) return SS2D_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < ss2d_wgrad_ts_workspace_bytes(batch, rows, M, N) || !aligned(workspace, 16))
+    return SS2D_ERR_WORKSPACE;
+  cudaError_t e = wgrad_ts_launch(dY, X, dW, batch, rows, M, N, dy_batch_stride, dy_row_stride, dy_col_stride,
+                                  x_batch_stride, x_row_stride, x_col_stride, dy_dtype, x_dtype,
+                                  static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 2;
   return SS2D_OK;
 }
 

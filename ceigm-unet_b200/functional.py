@@ -194,3 +194,76 @@ class _OutGate(torch.autograd.Function):
         dys = base.unsqueeze(1).expand(Bn, G, P, D, L)
         return (dys, (dw if ln_w is not None else None), (db if ln_b is not None else None), dz,
                 None, None, None, None, None, None)
+
+
+# ---- small projections with a tall-skinny weight gradient -------------------------------------------
+_TS_MIN_ROWS = 8192      # below this a library GEMM is as good (measured on the four GM-UNet stage shapes)
+
+
+class _LinearTS(torch.autograd.Function):
+    """y = F.linear(x, W, b) (cuBLAS; runs under the ambient autocast like nn.Linear). Backward: dx by cuBLAS, dW by
+    ops.wgrad_ts when W is tiny and the number of rows huge (in_proj / out_proj / proj of the live GM-UNet stages)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, W, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        M, N = W.shape
+        dy2, x2 = dy.reshape(-1, M), x.reshape(-1, N)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.matmul(dy2, W.to(dy2.dtype)).view(x.shape).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            if dy2.is_cuda and dy2.shape[0] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N):
+                dW = ops.wgrad_ts(dy2.unsqueeze(0), x2.unsqueeze(0)).to(W.dtype)
+            else:
+                dW = torch.matmul(dy2.t(), x2.to(dy2.dtype)).to(W.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(dim=0)
+        return dx, dW, db
+
+
+def _ts_eligible(rows: int, M: int, N: int, t: torch.Tensor) -> bool:
+    return t.is_cuda and rows >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N)
+
+
+def linear_ts(x, W, bias=None):
+    """nn.Linear's forward; its weight gradient comes from ops.wgrad_ts when the shape is tall and skinny."""
+    if not _ts_eligible(x.numel() // max(x.shape[-1], 1), W.shape[0], W.shape[1], x):
+        return torch.nn.functional.linear(x, W, bias)
+    return _LinearTS.apply(x, W, bias)
+
+
+class _ProjCM(torch.autograd.Function):
+    """out (B, M, L) = W (M, D) @ u (B, D, L): the 1 x 1 projections of SS2D.forward_core on channel-major tensors
+    (x_proj, dt_proj; ss2d.py:465-477). Backward: du by cuBLAS, dW by ops.wgrad_ts on the operands in place."""
+
+    @staticmethod
+    def forward(ctx, W, u):
+        ctx.save_for_backward(W, u)
+        return torch.matmul(W, u)
+
+    @staticmethod
+    def backward(ctx, dout):
+        W, u = ctx.saved_tensors
+        M, D = W.shape
+        dW = du = None
+        if ctx.needs_input_grad[1]:
+            du = torch.matmul(W.t().to(dout.dtype), dout).to(u.dtype)
+        if ctx.needs_input_grad[0]:
+            if dout.is_cuda and dout.shape[0] * dout.shape[2] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, D):
+                dW = ops.wgrad_ts(dout.transpose(1, 2), u.transpose(1, 2)).to(W.dtype)
+            else:
+                dW = torch.matmul(dout, u.transpose(1, 2).to(dout.dtype)).sum(dim=0).to(W.dtype)
+        return dW, du
+
+
+def proj_cm(W, u):
+    if not _ts_eligible(u.shape[0] * u.shape[2], W.shape[0], W.shape[1], u):
+        return torch.matmul(W, u)
+    return _ProjCM.apply(W, u)

@@ -139,13 +139,16 @@ class SS2D(nn.Module, mamba_init):
         Wx = self.x_proj_weight.to(x.dtype)
         if P == 1:
             u = planes[0]
-            x_dbl = torch.matmul(Wx.reshape(K * C, D), u).view(Bn, K, C, L)
+            x_dbl = Fn.proj_cm(Wx.reshape(K * C, D), u).view(Bn, K, C, L)
         else:
             u = torch.cat(planes, dim=1)                                                     # (B, 2D, L)
-            per_plane = [torch.matmul(Wx[j::2].reshape((K // 2) * C, D), planes[j]).view(Bn, K // 2, C, L) for j in range(2)]
+            per_plane = [Fn.proj_cm(Wx[j::2].reshape((K // 2) * C, D), planes[j]).view(Bn, K // 2, C, L) for j in range(2)]
             x_dbl = torch.stack(per_plane, dim=2).view(Bn, K, C, L)                          # group order restored
         dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-        dts = torch.matmul(self.dt_projs_weight.to(dts_r.dtype).unsqueeze(0), dts_r).reshape(Bn, K * D, L)
+        if K == 1:
+            dts = Fn.proj_cm(self.dt_projs_weight[0].to(dts_r.dtype), dts_r[:, 0])            # (B, D, L)
+        else:
+            dts = torch.matmul(self.dt_projs_weight.to(dts_r.dtype).unsqueeze(0), dts_r).reshape(Bn, K * D, L)
         As = -torch.exp(self.A_logs.float())
         Ds = self.Ds.float()
         bias = self.dt_projs_bias.reshape(-1).float()
@@ -167,14 +170,14 @@ class SS2D(nn.Module, mamba_init):
             dirs = Fn.directions_of(CrossScan, CrossMerge)
             if dirs is None:
                 raise NotImplementedError("SS2D.forward needs a matching (CrossScan*, CrossMerge*) pair")
-        xz = self.in_proj(x)                                      # ss2d.py:504
+        xz = Fn.linear_ts(x, self.in_proj.weight, self.in_proj.bias)    # ss2d.py:504 (tall-skinny weight gradient)
         xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
         xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
         if self.with_dconv:
             xi = self.conv2d(xi)                                  # :512
         xi = self.act(xi)                                         # :513
         y = self.forward_core(xi, z, dirs)                        # :514-517 (scan, merge, out_norm, gate)
-        return self.dropout(self.out_proj(y))                     # :518
+        return self.dropout(Fn.linear_ts(y, self.out_proj.weight, self.out_proj.bias))    # :518
 
 
 class GroupMambaLayer(nn.Module):
@@ -208,4 +211,4 @@ class GroupMambaLayer(nn.Module):
         xm = torch.cat(outs, dim=-1) * self.skip_scale * x4                     # :149
         xm = xm.view(Bn, L, C) * aff.unsqueeze(1)                               # :154
         xm = self.norm(xm)                                                      # :156 (same LayerNorm, shared weights)
-        return self.proj(xm)                                                    # :157
+        return Fn.linear_ts(xm, self.proj.weight, self.proj.bias)               # :157

@@ -256,3 +256,30 @@ def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[t
     _lib.check(rc, "ss2d_out_gate_bwd")
     sums = part.sum(dim=1)
     return dy, sums[0], sums[1]
+
+
+# ---- tall-skinny weight gradient ---------------------------------------------------------------
+def wgrad_ts_supported(M: int, N: int) -> bool:
+    return 0 < M <= 256 and 0 < N <= 256 and ((M + 3) // 4) * ((N + 3) // 4) <= 256
+
+
+def wgrad_ts(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW (M, N) fp32 = sum over (b, r) of dy[b, r, :, None] * x[b, r, None, :].
+    dy (B, R, M), x (B, R, N): arbitrary strided views (a (B, C, L) tensor is passed as .transpose(1, 2))."""
+    _require(dy.is_cuda and x.is_cuda and dy.dim() == 3 and x.dim() == 3 and dy.shape[:2] == x.shape[:2],
+             "wgrad_ts: dy (B, R, M) and x (B, R, N) must be CUDA tensors with the same leading sizes")
+    _require(dy.dtype in _DT and x.dtype in _DT, "wgrad_ts: float32, float16 or bfloat16 operands")
+    Bn, R, M = dy.shape
+    N = x.shape[2]
+    _require(wgrad_ts_supported(M, N), "wgrad_ts: M x N too large for the tall-skinny kernel (use a library GEMM)")
+    dev = dy.device
+    L = _lib.lib()
+    ws_bytes = int(L.ss2d_wgrad_ts_workspace_bytes(Bn, R, M, N))
+    ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=dev)
+    dW = torch.empty((M, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.ss2d_wgrad_ts(_ptr(dy), _ptr(x), _ptr(dW), Bn, R, M, N, dy.stride(0), dy.stride(1), dy.stride(2),
+                             x.stride(0), x.stride(1), x.stride(2), _DT[dy.dtype], _DT[x.dtype], _ptr(ws),
+                             ctypes.c_size_t(ws_bytes), _stream(dev))
+    _lib.check(rc, "ss2d_wgrad_ts")
+    return dW

@@ -156,6 +156,21 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                       uint32_t transposed_mask, ss2d_stream_t stream);
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
 
+/* ---- weight gradient of the small projections around the scan ("tall-skinny" reduction) -----------------
+ * dW[m][n] = sum over (b, r) of dY(b, r, m) * X(b, r, n), fp32 (M, N) contiguous, fully overwritten, deterministic.
+ * Replaces the weight-gradient GEMMs autograd/cuBLAS run for in_proj / out_proj (nn.Linear, model/gm/ss2d.py:294,
+ * 335, 504, 518), x_proj / dt_proj (the einsums of ss2d.py:465-477) and GroupMambaLayer.proj (groupmamba.py:157)
+ * when M x N is tiny and batch * rows huge. Element (b, r, m) of dY lives at
+ * dY[b * dy_batch_stride + r * dy_row_stride + m * dy_col_stride] (element strides; either the row or the column
+ * stride should be 1 for coalesced reads), likewise X. dtypes: ss2d_dtype of dY / X (fp32 accumulation).
+ * Supported: M, N <= 256 and ceil(M/4) * ceil(N/4) <= 256, else SS2D_ERR_UNSUPPORTED (use a library GEMM).
+ * workspace: ss2d_wgrad_ts_workspace_bytes(batch, rows, M, N) bytes, 16-byte aligned (0 = unsupported shape). */
+int ss2d_wgrad_ts(const void* dY, const void* X, float* dW, int32_t batch, int32_t rows, int32_t M, int32_t N,
+                  int64_t dy_batch_stride, int64_t dy_row_stride, int64_t dy_col_stride, int64_t x_batch_stride,
+                  int64_t x_row_stride, int64_t x_col_stride, int32_t dy_dtype, int32_t x_dtype, void* workspace,
+                  size_t workspace_bytes, ss2d_stream_t stream);
+size_t ss2d_wgrad_ts_workspace_bytes(int32_t batch, int32_t rows, int32_t M, int32_t N);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* ss2d_strerror(int status);
 const char* ss2d_last_cuda_error(void);   /* thread-local text of the last SS2D_ERR_CUDA */

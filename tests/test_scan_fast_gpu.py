@@ -22,7 +22,7 @@ def _flip_groups(x, per_group, flip):
     return np.concatenate([p[..., ::-1] if flip[i] else p for i, p in enumerate(parts)], axis=1)
 
 
-def _case(b, dt, L, N, G, hw=None, dirs=None, u_mod=0, softplus=True, seed=0):
+def _case(b, dt, L, N, G, hw=None, dirs=None, u_mod=0, softplus=True, seed=0, has_D=True, has_bias=True):
     from ceigm_unet_b200 import ops
     from oracle import c_oracle
     gen = torch.Generator(device="cuda").manual_seed(seed)
@@ -30,8 +30,8 @@ def _case(b, dt, L, N, G, hw=None, dirs=None, u_mod=0, softplus=True, seed=0):
     A = -0.5 * torch.rand(dt, N, device=dev, generator=gen)
     B = torch.randn(b, G, N, L, device=dev, generator=gen)
     C = torch.randn(b, G, N, L, device=dev, generator=gen)
-    D = torch.randn(dt, device=dev, generator=gen)
-    bias = 0.5 * torch.rand(dt, device=dev, generator=gen)
+    D = torch.randn(dt, device=dev, generator=gen) if has_D else None
+    bias = 0.5 * torch.rand(dt, device=dev, generator=gen) if has_bias else None
     uch = u_mod if u_mod else dt
     u = torch.randn(b, uch, L, device=dev, generator=gen)
     dl = 0.5 * torch.rand(b, dt, L, device=dev, generator=gen)
@@ -46,7 +46,7 @@ def _case(b, dt, L, N, G, hw=None, dirs=None, u_mod=0, softplus=True, seed=0):
     dpg = dt // G
     flip = [k == 3 for k in dirs] if dirs is not None else [False] * G
     rep = dt // uch
-    n = lambda t: t.float().cpu().numpy()
+    n = lambda t: None if t is None else t.float().cpu().numpy()
     un, dyn = np.tile(n(u), (1, rep, 1)), np.tile(n(dout), (1, rep, 1))
     args = (_flip_groups(un, dpg, flip), _flip_groups(n(dl), dpg, flip), n(A), _flip_groups(n(B), 1, flip),
             _flip_groups(n(C), 1, flip), n(D), n(bias))
@@ -64,6 +64,9 @@ def _case(b, dt, L, N, G, hw=None, dirs=None, u_mod=0, softplus=True, seed=0):
     assert rel(out, ref_out) < 1e-3
     assert rel(x[:, :, -1, 1::2], ref_last) < 1e-3
     for name, g, g2 in zip(NAMES, grads, grads_nockpt):
+        if ref[name] is None:
+            assert g is None and g2 is None, name
+            continue
         assert rel(g, ref[name]) < 1e-3, name               # du stays per direction when u is shared: same layout as ref
         assert rel(g2, ref[name]) < 1e-3, name + " (no checkpoints)"
 
@@ -93,6 +96,30 @@ def test_fast_path_reversed_with_tail_and_shared_input():
 
 def test_fast_path_reversed_long():
     _case(1, 40, 1000, 16, 1, hw=(25, 40), dirs=[3])
+
+
+def _fuzz_cases():
+    rng = np.random.RandomState(4321)
+    out = []
+    for i in range(24):
+        G = int(rng.choice([1, 2, 3, 4]))
+        dpg = int(rng.choice([1, 2, 7, 8, 9, 16, 24, 31, 32, 33, 48, 70]))
+        N = int(rng.randint(9, 17))
+        H, W = int(rng.choice([2, 4, 6, 8, 10, 14, 20])), int(rng.choice([2, 4, 6, 10, 16, 18]))
+        nb = int(rng.choice([1, 2, 3]))
+        natural = bool(rng.randint(2))
+        dirs = [int(rng.choice([1, 3])) for _ in range(G)] if natural else None
+        shared = natural and bool(rng.randint(2))
+        out.append(dict(b=nb, dt=G * dpg, L=H * W, N=N, G=G, hw=(H, W) if natural else None, dirs=dirs,
+                        u_mod=dpg if shared else 0, softplus=bool(rng.randint(4) > 0), seed=i,
+                        has_D=bool(rng.randint(4) > 0), has_bias=bool(rng.randint(4) > 0)))
+    return out
+
+
+@pytest.mark.parametrize("kw", _fuzz_cases(), ids=lambda k: "b%d_d%d_l%d_n%d_g%d_%s_u%d_%d" % (
+    k["b"], k["dt"], k["L"], k["N"], k["G"], "".join(map(str, k["dirs"])) if k["dirs"] else "scan", k["u_mod"], k["seed"]))
+def test_fast_path_fuzz(kw):
+    _case(**kw)
 
 
 def test_full_size_adjoint_identity():

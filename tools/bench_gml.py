@@ -10,6 +10,7 @@ import ceigm_unet_b200 as P
 
 Bn = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 STAGES = [(64, 56, 5), (128, 28, 6), (348, 14, 12), (448, 7, 3)]      # (channels C = 4 d_model, H = W, layers per forward)
+torch.set_float32_matmul_precision("medium")      # what the reference trains with (train_synapse.py:21)
 torch.manual_seed(0)
 
 

@@ -8,6 +8,7 @@ import ceigm_unet_b200 as P
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 56
 Bn = int(sys.argv[3]) if len(sys.argv) > 3 else 24
+torch.set_float32_matmul_precision("medium")      # what the reference trains with (train_synapse.py:21)
 torch.manual_seed(0)
 m = P.GroupMambaLayer(C, C).cuda()
 x = torch.randn(Bn, H * H, C, device="cuda", requires_grad=True)

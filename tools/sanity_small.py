@@ -14,7 +14,7 @@ def case(b, d, L, n, g, dtype=torch.float32):
     out, x = core.fwd(u, dl, A, Bm, Cm, D_, bias, True, 1)
     core.bwd(u, dl, A, Bm, Cm, D_, bias, torch.randn_like(out), x, True, 1)
     core.bwd(u, dl, A, Bm, Cm, D_, bias, torch.randn_like(out), None, True, 1)
-for args in [(2, 40, 100, 16, 2), (1, 24, 64, 16, 1), (2, 12, 77, 3, 1), (2, 16, 196, 1, 1), (1, 8, 49, 1, 1), (1, 6, 40, 48, 1),
+for args in [(2, 40, 100, 16, 2), (1, 24, 64, 16, 1), (1, 72, 160, 12, 2), (2, 12, 77, 3, 1), (2, 16, 196, 1, 1), (1, 8, 49, 1, 1), (1, 6, 40, 48, 1),
              (2, 40, 128, 16, 2, torch.bfloat16), (2, 16, 196, 1, 1, torch.bfloat16), (1, 70, 3136, 1, 1)]:
     case(*args)
 for k, N, dm in [(4, 16, 8), (1, 1, 8)]:
