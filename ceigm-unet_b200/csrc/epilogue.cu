@@ -197,7 +197,10 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       if (l < 0) continue;
       const float mean = s_stat[px][0], rstd = s_stat[px][1];
       const float yn = (s_y[d * (kEpiTL + 1) + px] - mean) * rstd;
-      dy[((int64_t)b * D + d) * L + l] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
+      // K == 1: the gradient belongs to the single plane and is written in ITS pixel order (transposed when tmask is set)
+      int lo = l;
+      if (K == 1 && pi.tmask) { const int h = l / pi.W, w = l - h * pi.W; lo = w * pi.H + h; }
+      dy[((int64_t)b * D + d) * L + lo] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
     }
   }
   if (PP == 1) {
@@ -222,6 +225,145 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
   }
 }
 
+// ---- live GM-UNet regime: one plane (K = 1), D <= 32 ------------------------------------------------------------
+// With 16 or 32 channels a pixel's LayerNorm fits one thread's registers: thread = pixel, visited in the PLANE's own
+// order (so the channel-major reads / writes of ys and dy are coalesced across the warp whether or not the plane is
+// transposed), while the channels-last rows of z / out / dout are whole 64- or 128-byte rows per thread. No shared
+// memory, no barrier in the pixel loop. (The tiled kernels above need three barriers per 32 pixels: 28 us forward and
+// 50 us backward at D = 16, B = 24, 56^2 against 15 MB of traffic.)
+template <int DP>
+__device__ __forceinline__ void row_load(const void* base, int64_t off, int dt, int D, float* v) {
+  if (dt == SS2D_F32 && (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) + off * 4) & 15) == 0) {
+#pragma unroll
+    for (int d = 0; d < DP; d += 4)
+      if (d < D) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off + d));
+        v[d] = t.x; v[d + 1] = t.y; v[d + 2] = t.z; v[d + 3] = t.w;
+      }
+  } else {
+#pragma unroll
+    for (int d = 0; d < DP; ++d)
+      if (d < D) v[d] = load1(base, off + d, dt);
+  }
+}
+template <int DP>
+__device__ __forceinline__ void row_store(void* base, int64_t off, int dt, int D, const float* v) {
+  if (dt == SS2D_F32 && (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) + off * 4) & 15) == 0) {
+#pragma unroll
+    for (int d = 0; d < DP; d += 4)
+      if (d < D) *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off + d) = make_float4(v[d], v[d + 1], v[d + 2], v[d + 3]);
+  } else {
+#pragma unroll
+    for (int d = 0; d < DP; ++d)
+      if (d < D) store1(base, off + d, dt, v[d]);
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kEpiThreads)
+out_gate_fwd_small_kernel(const float* __restrict__ ys, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                          const void* __restrict__ z, int64_t z_rs, int z_act, void* __restrict__ out,
+                          float* __restrict__ mean_rstd, int batch, int D, int L, float eps, int z_dtype, int out_dtype,
+                          int H, int W, int transposed) {
+  const int64_t total = (int64_t)batch * L;
+  for (int64_t idx = (int64_t)blockIdx.x * kEpiThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kEpiThreads) {
+    const int b = (int)(idx / L), lp = (int)(idx - (int64_t)b * L);          // pixel in plane order
+    int l = lp;
+    if (transposed) { const int w = lp / H, h = lp - w * H; l = h * W + w; }
+    float y[DP];
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { y[d] = d < D ? __ldg(ys + ((int64_t)b * D + d) * L + lp) : 0.f; s += y[d]; }
+    const float mean = s / D;
+    float v = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) { const float t = d < D ? y[d] - mean : 0.f; v = fmaf(t, t, v); }
+    const float rstd = rsqrtf(v / D + eps);
+    const int64_t row = (int64_t)b * L + l;
+    if (mean_rstd) { mean_rstd[row * 2] = mean; mean_rstd[row * 2 + 1] = rstd; }
+    float zz[DP];
+    if (z) row_load<DP>(z, row * z_rs, z_dtype, D, zz);
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      if (d < D) {
+        float o = (y[d] - mean) * rstd;
+        o = lnw ? fmaf(o, __ldg(lnw + d), lnb ? __ldg(lnb + d) : 0.f) : o;
+        if (z) o *= z_act ? silu_f(zz[d]) : zz[d];
+        y[d] = o;
+      }
+    }
+    row_store<DP>(out, row * D, out_dtype, D, y);
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kEpiThreads)
+out_gate_bwd_small_kernel(const float* __restrict__ ys, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                          const void* __restrict__ z, int64_t z_rs, int z_act, const void* __restrict__ dout,
+                          const float* __restrict__ mean_rstd, float* __restrict__ dy, void* __restrict__ dz, int64_t dz_rs,
+                          float* __restrict__ dw_part, float* __restrict__ db_part, int batch, int D, int L, int z_dtype,
+                          int out_dtype, int H, int W, int transposed) {
+  __shared__ float s_red[kEpiThreads / 32][2 * DP];
+  float acc_dw[DP], acc_db[DP];
+#pragma unroll
+  for (int d = 0; d < DP; ++d) { acc_dw[d] = 0.f; acc_db[d] = 0.f; }
+  const int64_t total = (int64_t)batch * L;
+  for (int64_t idx = (int64_t)blockIdx.x * kEpiThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kEpiThreads) {
+    const int b = (int)(idx / L), lp = (int)(idx - (int64_t)b * L);
+    int l = lp;
+    if (transposed) { const int w = lp / H, h = lp - w * H; l = h * W + w; }
+    const int64_t row = (int64_t)b * L + l;
+    const float mean = mean_rstd[row * 2], rstd = mean_rstd[row * 2 + 1];
+    float g[DP], yn[DP], zz[DP];
+    row_load<DP>(dout, row * D, out_dtype, D, g);
+    if (z) row_load<DP>(z, row * z_rs, z_dtype, D, zz);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < DP; ++d) {
+      if (d < D) {
+        yn[d] = (__ldg(ys + ((int64_t)b * D + d) * L + lp) - mean) * rstd;
+        const float w = lnw ? __ldg(lnw + d) : 1.f;
+        const float lin = lnw ? fmaf(yn[d], w, lnb ? __ldg(lnb + d) : 0.f) : yn[d];
+        float go = g[d];
+        if (z) {
+          const float zr = zz[d];
+          zz[d] = go * lin * (z_act ? silu_grad_f(zr) : 1.f);       // d z
+          go *= z_act ? silu_f(zr) : zr;
+        }
+        acc_dw[d] = fmaf(go, yn[d], acc_dw[d]);
+        acc_db[d] += go;
+        g[d] = go * w;
+        s1 += g[d];
+        s2 = fmaf(g[d], yn[d], s2);
+      } else { g[d] = 0.f; yn[d] = 0.f; }
+    }
+    if (z && dz) row_store<DP>(dz, row * dz_rs, z_dtype, D, zz);
+    s1 /= D; s2 /= D;
+    // gradient of the single plane, written in ITS pixel order (coalesced across the warp)
+#pragma unroll
+    for (int d = 0; d < DP; ++d)
+      if (d < D) dy[((int64_t)b * D + d) * L + lp] = rstd * (g[d] - s1 - yn[d] * s2);
+  }
+  // LayerNorm weight / bias gradients: warp butterflies, then the block's warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < DP; ++d) {
+    float a = acc_dw[d], c = acc_db[d];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if (lane == 0) { s_red[warp][d] = a; s_red[warp][DP + d] = c; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * DP) {
+    float t = 0.f;
+    for (int w = 0; w < kEpiThreads / 32; ++w) t += s_red[w][threadIdx.x];
+    const int d = threadIdx.x < DP ? threadIdx.x : threadIdx.x - DP;
+    if (d < D) (threadIdx.x < DP ? dw_part : db_part)[(int64_t)blockIdx.x * D + d] = t;
+  }
+}
+
+static bool epi_small(int K, int D) { return K == 1 && D <= 32; }
+
 static int epi_tiles_per_batch(int L, int H, int W, unsigned tmask) {
   return tmask ? ((H + 3) / 4) * ((W + 7) / 8) : (L + kEpiTL - 1) / kEpiTL;
 }
@@ -234,6 +376,17 @@ int epi_max_D(bool backward) { return backward ? 832 : 1664; }   // keeps the ti
 cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
                                 int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
                                 int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
+  if (epi_small(K, D)) {
+    const int64_t total = (int64_t)batch * L;
+    const int grid = (int)((total + kEpiThreads - 1) / kEpiThreads < 148 * 8 ? (total + kEpiThreads - 1) / kEpiThreads : 148 * 8);
+    if (D <= 16)
+      out_gate_fwd_small_kernel<16><<<grid, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
+                                                                       eps, z_dtype, out_dtype, H, W, (int)(tmask & 1u));
+    else
+      out_gate_fwd_small_kernel<32><<<grid, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
+                                                                       eps, z_dtype, out_dtype, H, W, (int)(tmask & 1u));
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -250,6 +403,17 @@ cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const 
                                 int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
                                 int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
+  if (epi_small(K, D)) {
+    if (D <= 16)
+      out_gate_bwd_small_kernel<16><<<n_partials, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
+                                                                             dz_rs, dw_part, db_part, batch, D, L, z_dtype,
+                                                                             out_dtype, H, W, (int)(tmask & 1u));
+    else
+      out_gate_bwd_small_kernel<32><<<n_partials, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
+                                                                             dz_rs, dw_part, db_part, batch, D, L, z_dtype,
+                                                                             out_dtype, H, W, (int)(tmask & 1u));
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)2 * D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -189,6 +189,9 @@ class _OutGate(torch.autograd.Function):
         dy, dw, db = ops.out_gate_bwd(ys.view(Bn, G * P, D, L), ln_w, ln_b, z, z_act, dout, stats, dz, (H, W), tmask)
         # dy is the gradient of the merged y in natural pixel order; every group receives it (transposed for the groups
         # that ran on the transposed image). Returned as a stride-0 expansion over the K/P repeats: no K-fold copy.
+        if G * P == 1:      # a single plane: the kernel already wrote dy in that plane's own (possibly transposed) pixel order
+            return (dy.view(Bn, 1, 1, D, L), (dw if ln_w is not None else None), (db if ln_b is not None else None), dz,
+                    None, None, None, None, None, None)
         planes = [dy.view(Bn, D, H, W).transpose(2, 3).reshape(Bn, D, L) if (tplanes >> j) & 1 else dy for j in range(P)]
         base = planes[0].unsqueeze(1) if P == 1 else torch.stack(planes, dim=1)          # (B, P, D, L)
         dys = base.unsqueeze(1).expand(Bn, G, P, D, L)

@@ -144,7 +144,9 @@ int ss2d_out_gate_fwd(const float* ys, int32_t K, const float* ln_weight, const 
                       const void* z, int64_t z_row_stride, int32_t z_act, void* out, float* mean_rstd,
                       int32_t batch, int32_t D, int32_t L, float eps, int32_t z_dtype, int32_t out_dtype,
                       int32_t H, int32_t W, uint32_t transposed_mask, ss2d_stream_t stream);
-/* dy: (batch, D, L) fp32 gradient of the MERGED y (every direction receives the same gradient: pass it to
+/* dy: (batch, D, L) fp32 gradient of the MERGED y in natural pixel order — except for K == 1, where it is the
+ *     gradient of the single plane and is written in THAT plane's pixel order (transposed when bit 0 of
+ *     transposed_mask is set) — (every direction receives the same gradient: pass it to
  *     ss2d_scan_bwd as a shared dout through u_dim_modulo). dz: gradient of the RAW z when z_act != 0, rows
  *     strided by dz_row_stride, or NULL. dln_*_partial: (n_partials, D) fp32, n_partials =
  *     ss2d_out_gate_bwd_partials(batch, L); the caller sums over the first axis. */
