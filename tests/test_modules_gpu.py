@@ -155,3 +155,28 @@ def test_group_mamba_layer_cuda_graphs_match_eager():
     assert rel_err(gx1, gx2.cpu().numpy()) < 1e-5
     for a, b in zip(gp1, gp2):
         assert rel_err(a, b.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("D", [16, 40])          # 16: thread-per-pixel epilogue kernels; 40: tiled kernels (K = 1, transposed plane)
+@pytest.mark.parametrize("pair", [(2, 1), (4, 3)])
+def test_column_major_directions_equal_row_major_on_the_transposed_image(D, pair):
+    """SS2D.forward_core in direction 2 (4) on an image == direction 1 (3) on the transposed image, transposed back —
+    CrossScan_2/_4 are CrossScan_1/_3 of the transposed input (csms6s.py:95-129, 172-206). Checks values and the
+    gradients w.r.t. the input and the gate on a non-square map, through both epilogue kernel families."""
+    import ceigm_unet_b200 as P
+    torch.manual_seed(D)
+    col, row = pair
+    m = P.SS2D(d_model=D, d_state=1, ssm_ratio=1, d_conv=3).cuda()
+    Bn, H, W = 2, 6, 10
+    x = torch.randn(Bn, D, H, W, device="cuda", requires_grad=True)
+    z = torch.randn(Bn, H, W, D, device="cuda", requires_grad=True)
+    gy = torch.randn(Bn, H, W, D, device="cuda")
+    y_c = m.forward_core(x, z, (col,))
+    gx_c, gz_c = torch.autograd.grad(y_c, (x, z), gy)
+    xt = x.detach().transpose(2, 3).contiguous().requires_grad_(True)
+    zt = z.detach().transpose(1, 2).contiguous().requires_grad_(True)
+    y_r = m.forward_core(xt, zt, (row,))                                   # (B, W, H, D)
+    gx_r, gz_r = torch.autograd.grad(y_r, (xt, zt), gy.transpose(1, 2).contiguous())
+    assert rel_err(y_c, y_r.transpose(1, 2).detach().cpu().numpy()) < 1e-5
+    assert rel_err(gx_c, gx_r.transpose(2, 3).cpu().numpy()) < 1e-4
+    assert rel_err(gz_c, gz_r.transpose(1, 2).cpu().numpy()) < 1e-4
