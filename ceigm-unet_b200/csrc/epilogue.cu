@@ -51,6 +51,8 @@ __device__ __forceinline__ void load_merged_tile(float* s_y, const float* __rest
                                                  int tib, const PlaneIdx pi) {
   const int64_t plane = (int64_t)D * L;
   const float* base = ys + (int64_t)b * K * plane;
+  // unrolled by 4: 4 K independent loads in flight per thread (with one element per iteration the kernel ran at 1.5 TB/s)
+#pragma unroll 4
   for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
     const int d = i / kEpiTL, px = i - d * kEpiTL;
     const int l = pi.pixel(tib, px);
@@ -94,6 +96,7 @@ out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
     }
     __syncthreads();
     // normalise, gate, write channels-last (threads run along D: coalesced)
+#pragma unroll 4
     for (int i = threadIdx.x; i < kEpiTL * D; i += kEpiThreads) {
       const int px = i / D, d = i - px * D;
       const int l = pi.pixel(tib, px);
@@ -369,7 +372,7 @@ static int epi_tiles_per_batch(int L, int H, int W, unsigned tmask) {
 }
 int epi_bwd_partials(int batch, int L) {     // an upper bound that does not depend on the tiling mode
   const int tiles = batch * ((L + kEpiTL - 1) / kEpiTL);
-  return tiles < 148 * 2 ? tiles : 148 * 2;
+  return tiles < 148 * 4 ? tiles : 148 * 4;      // 4 CTAs per SM fit (2 x D x 33 floats of shared memory each at D = 192)
 }
 int epi_max_D(bool backward) { return backward ? 832 : 1664; }   // keeps the tile(s) within 227 KB of shared memory
 
@@ -392,7 +395,7 @@ cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const 
   if (e != cudaSuccess) return e;
   const int tpb = epi_tiles_per_batch(L, H, W, tmask);
   const int tiles = batch * tpb;
-  const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
+  const int grid = tiles < 148 * 8 ? tiles : 148 * 8;
   const PlaneIdx pi{L, H, W, tmask, tmask ? (W + 7) / 8 : 0};
   out_gate_fwd_kernel<<<grid, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
                                                           eps, z_dtype, out_dtype, tpb, pi);

@@ -51,7 +51,7 @@ def test_descriptor_validation_needs_no_gpu():
     d.layout, d.H, d.W = 1, 8, 8
     d.dirs[0], d.dirs[1], d.dirs[2], d.dirs[3] = 1, 2, 3, 9
     assert L.ss2d_scan_fwd(ctypes.byref(d), None, None, None, None, None, None, None, None, None, None, None) == -5
-    assert L.ss2d_out_gate_bwd_partials(24, 3136) == 296
+    assert L.ss2d_out_gate_bwd_partials(24, 3136) == 592
 
 
 def test_struct_layout_matches_header():
