@@ -34,6 +34,13 @@ cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const 
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
                                 int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream);
 int epi_bwd_partials(int batch, int L);
+int layernorm_bwd_partials(int64_t rows);
+int layernorm_max_C();
+cudaError_t layernorm_fwd_launch(const void* x, const float* w, const float* b, void* y, float* mean_rstd, int64_t rows,
+                                 int C, float eps, int dt, cudaStream_t stream);
+cudaError_t layernorm_bwd_launch(const void* x, const float* w, const void* dy, const float* mean_rstd, void* dx,
+                                 float* dw_part, float* db_part, int n_partials, int64_t rows, int C, int dt,
+                                 cudaStream_t stream);
 bool wgrad_ts_supported(int M, int N);
 size_t wgrad_ts_workspace_floats(int64_t total_rows, int M, int N);
 cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch, int rows, int M, int N, int64_t y_bs,
@@ -277,6 +284,35 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
   cudaError_t e = out_gate_bwd_launch(ys, K, ln_weight, ln_bias, z, z_row_stride, z_act, dout, mean_rstd, dy, dz,
                                       dz_row_stride, dln_weight_partial, dln_bias_partial, n_partials, batch, D, L,
                                       z_dtype, out_dtype, H, W, transposed_mask, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int32_t ss2d_layernorm_bwd_partials(int64_t rows) { return rows > 0 ? layernorm_bwd_partials(rows) : 0; }
+
+int ss2d_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean_rstd, int64_t rows,
+                       int32_t C, float eps, int32_t dtype, ss2d_stream_t stream) {
+  if (!x || !y) return SS2D_ERR_NULL_POINTER;
+  if (rows <= 0 || C <= 0) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (C > layernorm_max_C()) return SS2D_ERR_UNSUPPORTED;
+  cudaError_t e = layernorm_fwd_launch(x, weight, bias, y, mean_rstd, rows, C, eps, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int ss2d_layernorm_bwd(const void* x, const float* weight, const void* dy, const float* mean_rstd, void* dx,
+                       float* dweight_partial, float* dbias_partial, int32_t n_partials, int64_t rows, int32_t C,
+                       int32_t dtype, ss2d_stream_t stream) {
+  if (!x || !dy || !mean_rstd || !dx || !dweight_partial || !dbias_partial) return SS2D_ERR_NULL_POINTER;
+  if (rows <= 0 || C <= 0) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (C > layernorm_max_C()) return SS2D_ERR_UNSUPPORTED;
+  if (n_partials != layernorm_bwd_partials(rows)) return SS2D_ERR_WORKSPACE;
+  cudaError_t e = layernorm_bwd_launch(x, weight, dy, mean_rstd, dx, dweight_partial, dbias_partial, n_partials, rows, C,
+                                       dtype, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
   return SS2D_OK;

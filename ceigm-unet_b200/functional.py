@@ -270,3 +270,33 @@ def proj_cm(W, u):
     if not _ts_eligible(u.shape[0] * u.shape[2], W.shape[0], W.shape[1], u):
         return torch.matmul(W, u)
     return _ProjCM.apply(W, u)
+
+
+# ---- row-wise LayerNorm (GroupMambaLayer.norm) ------------------------------------------------------
+class _LayerNormRows(torch.autograd.Function):
+    """nn.LayerNorm over the last dimension (C <= 512) of a channels-last tensor: ops.layernorm_fwd/bwd. Runs in the
+    dtype of x with fp32 statistics (under autocast nn.LayerNorm runs in fp32 as well; x is fp32 there)."""
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, x, weight, bias, eps):
+        xc = x.contiguous()
+        w = weight.float() if weight is not None else None
+        b = bias.float() if bias is not None else None
+        y, stats = ops.layernorm_fwd(xc, w, b, eps)
+        ctx.save_for_backward(xc, w, stats)
+        ctx.has = (weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    @_custom_bwd
+    def backward(ctx, dy):
+        xc, w, stats = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(xc, w, dy.to(xc.dtype), stats)
+        return dx, (dw if ctx.has[0] else None), (db if ctx.has[1] else None), None
+
+
+def layer_norm_rows(x, weight, bias, eps):
+    if not x.is_cuda or x.shape[-1] > ops.LN_MAX_C or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+    return _LayerNormRows.apply(x, weight, bias, eps)

@@ -201,7 +201,7 @@ class GroupMambaLayer(nn.Module):
         if x.dtype == torch.float16:
             x = x.type(torch.float32)
         Bn, L, C = x.shape
-        x = self.norm(x)                                                        # :131
+        x = Fn.layer_norm_rows(x, self.norm.weight, self.norm.bias, self.norm.eps)   # :131 (row-wise LN kernel)
         aff = self.sigmoid(self.fc2(self.relu(self.fc1(x.mean(dim=1)))))        # :134-137 channel affinity
         x4 = x.view(Bn, H, W, C)
         parts = torch.chunk(x4, 4, dim=-1)
@@ -210,5 +210,5 @@ class GroupMambaLayer(nn.Module):
         outs = [getattr(self, f"mamba_g{i + 1}")(parts[i], CrossScan=pairs[i][0], CrossMerge=pairs[i][1]) for i in range(4)]
         xm = torch.cat(outs, dim=-1) * self.skip_scale * x4                     # :149
         xm = xm.view(Bn, L, C) * aff.unsqueeze(1)                               # :154
-        xm = self.norm(xm)                                                      # :156 (same LayerNorm, shared weights)
+        xm = Fn.layer_norm_rows(xm, self.norm.weight, self.norm.bias, self.norm.eps)   # :156 (same LayerNorm, shared weights)
         return Fn.linear_ts(xm, self.proj.weight, self.proj.bias)               # :157

@@ -283,3 +283,40 @@ def wgrad_ts(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
                              ctypes.c_size_t(ws_bytes), _stream(dev))
     _lib.check(rc, "ss2d_wgrad_ts")
     return dW
+
+
+# ---- row-wise LayerNorm ------------------------------------------------------------------------
+LN_MAX_C = 512
+
+
+def layernorm_fwd(x: torch.Tensor, weight, bias, eps: float):
+    """x (..., C) contiguous CUDA tensor, C <= 512 -> (y, mean_rstd (rows, 2) fp32)."""
+    _require(x.is_cuda and x.dtype in _DT and x.is_contiguous(), "layernorm: contiguous CUDA float tensor expected")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    _require(0 < C <= LN_MAX_C and rows > 0, "layernorm: 0 < C <= 512 and at least one row")
+    y = torch.empty_like(x)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_layernorm_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _ptr(stats), rows, C,
+                                           ctypes.c_float(eps), _DT[x.dtype], _stream(x.device))
+    _lib.check(rc, "ss2d_layernorm_fwd")
+    return y, stats
+
+
+def layernorm_bwd(x: torch.Tensor, weight, dy: torch.Tensor, stats: torch.Tensor):
+    """-> dx (like x), dweight (C) fp32, dbias (C) fp32."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dy = dy.contiguous()
+    _require(dy.dtype == x.dtype and dy.shape == x.shape, "layernorm: dy must match x")
+    dx = torch.empty_like(x)
+    L = _lib.lib()
+    npart = int(L.ss2d_layernorm_bwd_partials(rows))
+    part = torch.empty((2, npart, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.ss2d_layernorm_bwd(_ptr(x), _ptr(weight), _ptr(dy), _ptr(stats), _ptr(dx), _ptr(part[0]), _ptr(part[1]), npart,
+                                  rows, C, _DT[x.dtype], _stream(x.device))
+    _lib.check(rc, "ss2d_layernorm_bwd")
+    sums = part.sum(dim=1)
+    return dx, sums[0], sums[1]

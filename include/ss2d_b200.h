@@ -158,6 +158,19 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                       uint32_t transposed_mask, ss2d_stream_t stream);
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
 
+/* ---- row-wise LayerNorm over C <= 512 channels of channels-last rows --------------------------------
+ * Replaces nn.LayerNorm as used by GroupMambaLayer.norm (model/gm/groupmamba.py:131, 156; two applications per layer
+ * call with shared weights). x, y, dy, dx: (rows, C) contiguous, dtype = ss2d_dtype; weight / bias: (C) fp32 or NULL.
+ * mean_rstd: (rows, 2) fp32, written by the forward (may be NULL there), read by the backward.
+ * dweight_partial / dbias_partial: (n_partials, C) fp32 with n_partials = ss2d_layernorm_bwd_partials(rows); the caller
+ * sums over the first axis (deterministic). C > 512: SS2D_ERR_UNSUPPORTED. */
+int ss2d_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean_rstd, int64_t rows,
+                       int32_t C, float eps, int32_t dtype, ss2d_stream_t stream);
+int ss2d_layernorm_bwd(const void* x, const float* weight, const void* dy, const float* mean_rstd, void* dx,
+                       float* dweight_partial, float* dbias_partial, int32_t n_partials, int64_t rows, int32_t C,
+                       int32_t dtype, ss2d_stream_t stream);
+int32_t ss2d_layernorm_bwd_partials(int64_t rows);
+
 /* ---- weight gradient of the small projections around the scan ("tall-skinny" reduction) -----------------
  * dW[m][n] = sum over (b, r) of dY(b, r, m) * X(b, r, n), fp32 (M, N) contiguous, fully overwritten, deterministic.
  * Replaces the weight-gradient GEMMs autograd/cuBLAS run for in_proj / out_proj (nn.Linear, model/gm/ss2d.py:294,

@@ -71,3 +71,32 @@ def test_linear_ts_and_proj_cm_gradients_match_torch():
     o0 = torch.matmul(Wp, u)
     gWp0, gu0 = torch.autograd.grad(o0, (Wp, u), go)
     assert rel(o, o0) < 1e-6 and rel(gu, gu0) < 1e-4 and rel(gWp, gWp0) < 1e-3
+
+
+@pytest.mark.parametrize("rows,C", [(75264, 64), (18816, 128), (4704, 348), (1176, 448), (7, 5), (33, 512), (100, 33)])
+def test_layer_norm_rows_matches_torch(rows, C):
+    """Row-wise LayerNorm kernel (csrc/layernorm.cu) against F.layer_norm in fp64: output and all three gradients."""
+    from ceigm_unet_b200 import functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    x = (torch.randn(rows, C, device="cuda", generator=g) * 2 + 0.5).requires_grad_(True)
+    w = torch.randn(C, device="cuda", generator=g).requires_grad_(True)
+    b = torch.randn(C, device="cuda", generator=g).requires_grad_(True)
+    gy = torch.randn(rows, C, device="cuda", generator=g)
+    y = Fn.layer_norm_rows(x, w, b, 1e-5)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), gy)
+    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    y0 = torch.nn.functional.layer_norm(x64, (C,), w64, b64, 1e-5)
+    gx0, gw0, gb0 = torch.autograd.grad(y0, (x64, w64, b64), gy.double())
+    assert rel(y, y0.detach()) < 1e-5 and rel(gx, gx0) < 1e-4 and rel(gw, gw0) < 1e-3 and rel(gb, gb0) < 1e-3
+
+
+def test_layer_norm_rows_bf16_and_fallback():
+    from ceigm_unet_b200 import functional as Fn
+    x = torch.randn(300, 96, device="cuda", dtype=torch.bfloat16)
+    w, b = torch.rand(96, device="cuda") + 0.5, torch.randn(96, device="cuda")
+    y = Fn.layer_norm_rows(x, w, b, 1e-5)
+    y0 = torch.nn.functional.layer_norm(x.float(), (96,), w, b, 1e-5)
+    assert y.dtype == torch.bfloat16 and rel(y.float(), y0) < 2e-2
+    xl = torch.randn(10, 600, device="cuda")              # C > 512: library LayerNorm
+    wl, bl = torch.ones(600, device="cuda"), torch.zeros(600, device="cuda")
+    assert rel(Fn.layer_norm_rows(xl, wl, bl, 1e-5), torch.nn.functional.layer_norm(xl, (600,), wl, bl, 1e-5)) < 1e-6
