@@ -23,7 +23,8 @@ EXPORTS = [
     "ss2d_scan_fwd", "ss2d_scan_ckpt_floats", "ss2d_scan_bwd", "ss2d_scan_bwd_workspace_bytes",
     "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_out_gate_fwd", "ss2d_out_gate_bwd",
     "ss2d_out_gate_bwd_partials", "ss2d_wgrad_ts", "ss2d_wgrad_ts_workspace_bytes",
-    "ss2d_layernorm_fwd", "ss2d_layernorm_bwd", "ss2d_layernorm_bwd_partials", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count",
+    "ss2d_layernorm_fwd", "ss2d_layernorm_bwd", "ss2d_layernorm_bwd_partials",
+    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count",
 ]
 
 
@@ -95,6 +96,10 @@ def lib() -> ctypes.CDLL:
     L.ss2d_wgrad_ts.restype = ctypes.c_int
     L.ss2d_wgrad_ts_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.ss2d_wgrad_ts_workspace_bytes.restype = sz
+    L.ss2d_dwconv3_wgrad.argtypes = [fp, fp, fp, fp, i32, i32, i32, i32, vp, sz, vp]
+    L.ss2d_dwconv3_wgrad.restype = ctypes.c_int
+    L.ss2d_dwconv3_wgrad_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.ss2d_dwconv3_wgrad_workspace_bytes.restype = sz
     L.ss2d_layernorm_fwd.argtypes = [vp, fp, fp, vp, fp, i64, i32, ctypes.c_float, i32, vp]
     L.ss2d_layernorm_fwd.restype = ctypes.c_int
     L.ss2d_layernorm_bwd.argtypes = [vp, fp, vp, fp, vp, fp, fp, i32, i64, i32, i32, vp]

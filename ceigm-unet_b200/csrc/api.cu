@@ -41,6 +41,9 @@ cudaError_t layernorm_fwd_launch(const void* x, const float* w, const float* b, 
 cudaError_t layernorm_bwd_launch(const void* x, const float* w, const void* dy, const float* mean_rstd, void* dx,
                                  float* dw_part, float* db_part, int n_partials, int64_t rows, int C, int dt,
                                  cudaStream_t stream);
+int dwconv3_wgrad_slabs(int batch, int C, int H, int W);
+cudaError_t dwconv3_wgrad_launch(const float* x, const float* dy, float* dW, float* db, float* workspace, int batch, int C,
+                                 int H, int W, cudaStream_t stream);
 bool wgrad_ts_supported(int M, int N);
 size_t wgrad_ts_workspace_floats(int64_t total_rows, int M, int N);
 cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch, int rows, int M, int N, int64_t y_bs,
@@ -286,6 +289,24 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                                       z_dtype, out_dtype, H, W, transposed_mask, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
+  return SS2D_OK;
+}
+
+size_t ss2d_dwconv3_wgrad_workspace_bytes(int32_t batch, int32_t C, int32_t H, int32_t W) {
+  if (batch <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)C * dwconv3_wgrad_slabs(batch, C, H, W) * 10 * sizeof(float);
+}
+
+int ss2d_dwconv3_wgrad(const float* x, const float* dy, float* dweight, float* dbias, int32_t batch, int32_t C, int32_t H,
+                       int32_t W, void* workspace, size_t workspace_bytes, ss2d_stream_t stream) {
+  if (!x || !dy || !dweight) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || C <= 0 || H <= 0 || W <= 0 || C > 65535) return SS2D_ERR_BAD_SHAPE;
+  if (!workspace || workspace_bytes < ss2d_dwconv3_wgrad_workspace_bytes(batch, C, H, W) || !aligned(workspace, 4))
+    return SS2D_ERR_WORKSPACE;
+  cudaError_t e = dwconv3_wgrad_launch(x, dy, dweight, dbias, static_cast<float*>(workspace), batch, C, H, W,
+                                       static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 2;
   return SS2D_OK;
 }
 

@@ -300,3 +300,34 @@ def layer_norm_rows(x, weight, bias, eps):
     if not x.is_cuda or x.shape[-1] > ops.LN_MAX_C or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
     return _LayerNormRows.apply(x, weight, bias, eps)
+
+
+# ---- SS2D's depthwise 3 x 3 convolution with a reduction-shaped parameter gradient -----------------------
+class _DWConv3(torch.autograd.Function):
+    """y = conv2d(x, W (C,1,3,3), b, padding=1, groups=C) (library forward and input gradient); dW / db by
+    ops.dwconv3_wgrad (ss2d.py:316-325, 512)."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.conv2d(x, W, bias, padding=1, groups=W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.nn.grad.conv2d_input(x.shape, W.to(dy.dtype), dy, padding=1, groups=W.shape[0]).to(x.dtype)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW, db = ops.dwconv3_wgrad(x.float().contiguous(), dy.float().contiguous(), ctx.has_bias)
+            dW = dW.to(W.dtype)
+        return dx, dW, db
+
+
+def dwconv3(x, conv: "torch.nn.Conv2d"):
+    """SS2D.conv2d through _DWConv3 when it is the reference's depthwise 3 x 3 / padding 1 layer on a CUDA tensor."""
+    ok = (x.is_cuda and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and
+          conv.dilation == (1, 1) and conv.groups == conv.in_channels == conv.out_channels and conv.padding_mode == "zeros" and
+          x.shape[0] * x.shape[2] * x.shape[3] >= _TS_MIN_ROWS)
+    return _DWConv3.apply(x, conv.weight, conv.bias) if ok else conv(x)

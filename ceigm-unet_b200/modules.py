@@ -174,7 +174,7 @@ class SS2D(nn.Module, mamba_init):
         xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
         xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
         if self.with_dconv:
-            xi = self.conv2d(xi)                                  # :512
+            xi = Fn.dwconv3(xi, self.conv2d)                      # :512 (reduction-shaped parameter gradient)
         xi = self.act(xi)                                         # :513
         y = self.forward_core(xi, z, dirs)                        # :514-517 (scan, merge, out_norm, gate)
         return self.dropout(Fn.linear_ts(y, self.out_proj.weight, self.out_proj.bias))    # :518

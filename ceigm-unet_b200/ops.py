@@ -320,3 +320,21 @@ def layernorm_bwd(x: torch.Tensor, weight, dy: torch.Tensor, stats: torch.Tensor
     _lib.check(rc, "ss2d_layernorm_bwd")
     sums = part.sum(dim=1)
     return dx, sums[0], sums[1]
+
+
+# ---- depthwise 3 x 3 convolution: parameter gradients ---------------------------------------------
+def dwconv3_wgrad(x: torch.Tensor, dy: torch.Tensor, want_bias: bool):
+    """x, dy: fp32 (B, C, H, W) contiguous CUDA tensors -> dweight (C, 1, 3, 3), dbias (C) or None."""
+    _require(x.is_cuda and dy.is_cuda and x.dtype == torch.float32 and dy.dtype == torch.float32 and x.shape == dy.shape
+             and x.dim() == 4 and x.is_contiguous() and dy.is_contiguous(), "dwconv3_wgrad: contiguous fp32 (B, C, H, W) tensors")
+    Bn, C, H, W = x.shape
+    L = _lib.lib()
+    ws_bytes = int(L.ss2d_dwconv3_wgrad_workspace_bytes(Bn, C, H, W))
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=x.device)
+    dW = torch.empty((C, 1, 3, 3), dtype=torch.float32, device=x.device)
+    db = torch.empty((C,), dtype=torch.float32, device=x.device) if want_bias else None
+    with torch.cuda.device(x.device):
+        rc = L.ss2d_dwconv3_wgrad(_ptr(x), _ptr(dy), _ptr(dW), _ptr(db), Bn, C, H, W, _ptr(ws), ctypes.c_size_t(ws_bytes),
+                                  _stream(x.device))
+    _lib.check(rc, "ss2d_dwconv3_wgrad")
+    return dW, db

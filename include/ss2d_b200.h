@@ -158,6 +158,15 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                       uint32_t transposed_mask, ss2d_stream_t stream);
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
 
+/* ---- weight / bias gradient of SS2D's depthwise 3 x 3 convolution -----------------------------------
+ * dweight[c][ky][kx] = sum_(b,h,w) dy[b,c,h,w] * x[b,c,h+ky-1,w+kx-1] (zero padding 1), dbias[c] = sum dy[b,c,h,w]:
+ * the backward of nn.Conv2d(D, D, groups=D, kernel_size=3, padding=1, bias=True) w.r.t. its parameters
+ * (model/gm/ss2d.py:316-325, 512). x, dy: fp32 (batch, C, H, W) contiguous; dweight: (C, 1, 3, 3) fp32; dbias: (C) fp32
+ * or NULL. Fully overwritten, deterministic. workspace: ss2d_dwconv3_wgrad_workspace_bytes(batch, C, H, W) bytes. */
+int ss2d_dwconv3_wgrad(const float* x, const float* dy, float* dweight, float* dbias, int32_t batch, int32_t C, int32_t H,
+                       int32_t W, void* workspace, size_t workspace_bytes, ss2d_stream_t stream);
+size_t ss2d_dwconv3_wgrad_workspace_bytes(int32_t batch, int32_t C, int32_t H, int32_t W);
+
 /* ---- row-wise LayerNorm over C <= 512 channels of channels-last rows --------------------------------
  * Replaces nn.LayerNorm as used by GroupMambaLayer.norm (model/gm/groupmamba.py:131, 156; two applications per layer
  * call with shared weights). x, y, dy, dx: (rows, C) contiguous, dtype = ss2d_dtype; weight / bias: (C) fp32 or NULL.

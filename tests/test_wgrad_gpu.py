@@ -100,3 +100,32 @@ def test_layer_norm_rows_bf16_and_fallback():
     xl = torch.randn(10, 600, device="cuda")              # C > 512: library LayerNorm
     wl, bl = torch.ones(600, device="cuda"), torch.zeros(600, device="cuda")
     assert rel(Fn.layer_norm_rows(xl, wl, bl, 1e-5), torch.nn.functional.layer_norm(xl, (600,), wl, bl, 1e-5)) < 1e-6
+
+
+@pytest.mark.parametrize("B,C,H,W", [(24, 16, 56, 56), (3, 87, 14, 14), (2, 5, 7, 9), (1, 1, 1, 1), (2, 192, 20, 12)])
+def test_dwconv3_parameter_gradients_match_torch(B, C, H, W):
+    """ss2d_dwconv3_wgrad against autograd of F.conv2d (fp64): weight and bias gradients of the depthwise 3 x 3 conv."""
+    from ceigm_unet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B + C + H + W)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g)
+    dy = torch.randn(B, C, H, W, device="cuda", generator=g)
+    Wt = torch.randn(C, 1, 3, 3, device="cuda", dtype=torch.float64, requires_grad=True)
+    bt = torch.randn(C, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.double(), Wt, bt, padding=1, groups=C)
+    gW0, gb0 = torch.autograd.grad(y, (Wt, bt), dy.double())
+    gW, gb = ops.dwconv3_wgrad(x, dy, True)
+    assert gW.shape == (C, 1, 3, 3) and rel(gW, gW0) < 1e-3 and rel(gb, gb0) < 1e-3
+    assert ops.dwconv3_wgrad(x, dy, False)[1] is None
+
+
+def test_dwconv3_function_matches_conv_module():
+    from ceigm_unet_b200 import functional as Fn
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(16, 16, 3, padding=1, groups=16, bias=True).cuda()
+    x = torch.randn(8, 16, 40, 40, device="cuda", requires_grad=True)          # 12 800 pixels per channel: kernel path
+    gy = torch.randn(8, 16, 40, 40, device="cuda")
+    y = Fn.dwconv3(x, conv)
+    gx, gW, gb = torch.autograd.grad(y, (x, conv.weight, conv.bias), gy)
+    y0 = conv(x)
+    gx0, gW0, gb0 = torch.autograd.grad(y0, (x, conv.weight, conv.bias), gy)
+    assert rel(y, y0) < 1e-6 and rel(gx, gx0) < 1e-4 and rel(gW, gW0) < 1e-3 and rel(gb, gb0) < 1e-3
