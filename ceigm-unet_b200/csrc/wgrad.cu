@@ -47,6 +47,38 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, int pitch, c
   }
 }
 
+// Asynchronous variant for fp32 operands: cp.async (LDGSTS) straight into the other shared-memory buffer while the current
+// tile is being multiplied; out-of-range elements are zero-filled through the src-size operand.
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gmem_src, int bytes, bool valid) {
+  const int src = valid ? bytes : 0;
+  if (bytes == 16)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src) : "memory");
+}
+__device__ __forceinline__ void stage_tile_async(float* __restrict__ dst, int pitch, const float* __restrict__ src, int C, int CP,
+                                                 int64_t cs, bool flat, const int64_t* __restrict__ rowoff, int64_t g0,
+                                                 int64_t g_end, int tid) {
+  if (flat) {
+    const float* base = src + g0 * C;
+    const int nvec = kWgRows * C / 4, c4n = C / 4;
+    const int64_t valid = (g_end - g0) * C;
+    for (int v = tid; v < nvec; v += kWgThreads) {
+      const int r = v / c4n, c = (v - r * c4n) * 4;
+      const bool ok = (int64_t)v * 4 < valid;
+      cp_async_zfill(dst + r * pitch + c, ok ? base + (int64_t)v * 4 : src, 16, ok);
+    }
+    return;
+  }
+  for (int i = tid; i < kWgRows * CP; i += kWgThreads) {
+    int r, c;
+    if (cs == 1) { r = i / CP; c = i - r * CP; } else { c = i / kWgRows; r = i - c * kWgRows; }
+    const int64_t ro = rowoff[r];
+    const bool ok = ro >= 0 && c < C;
+    cp_async_zfill(dst + r * pitch + c, ok ? src + ro + (int64_t)c * cs : src, 4, ok);
+  }
+}
+
 __global__ void __launch_bounds__(kWgThreads)
 wgrad_ts_kernel(const void* __restrict__ dY, const void* __restrict__ X, float* __restrict__ part, int64_t total_rows,
                 int rows, int M, int N, int64_t y_bs, int64_t y_rs, int64_t y_cs, int64_t x_bs, int64_t x_rs, int64_t x_cs,
@@ -56,7 +88,7 @@ wgrad_ts_kernel(const void* __restrict__ dY, const void* __restrict__ X, float* 
   const int MQ = MP + 4, NQ = NP + 4;       // row pitches: + 4 floats spreads the transposed staging stores over banks
   float* sY = s_wg;                         // [kWgRows][MQ]
   float* sX = sY + kWgRows * MQ;            // [kWgRows][NQ]
-  __shared__ int64_t s_rowY[kWgRows], s_rowX[kWgRows];
+  __shared__ int64_t s_rowY[2][kWgRows], s_rowX[2][kWgRows];
   const int tid = threadIdx.x;
   const int tn_cnt = NP / 4, tpg = (MP / 4) * tn_cnt;          // threads per row group
   const int RG = kWgThreads / tpg;                              // row groups (>= 1)
@@ -76,33 +108,65 @@ wgrad_ts_kernel(const void* __restrict__ dY, const void* __restrict__ X, float* 
 
   const int64_t g_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t g_end = g_begin + rows_per_cta < total_rows ? g_begin + rows_per_cta : total_rows;
-  for (int64_t g0 = g_begin; g0 < g_end; g0 += kWgRows) {
-    __syncthreads();
-    if (tid < kWgRows) {
-      const int64_t g = g0 + tid;
-      if (g < g_end) {
-        const int64_t b = g / rows, r = g - b * rows;
-        s_rowY[tid] = b * y_bs + r * y_rs;
-        s_rowX[tid] = b * x_bs + r * x_rs;
-      } else {
-        s_rowY[tid] = -1; s_rowX[tid] = -1;
-      }
-    }
-    __syncthreads();
-    // stage the tile, threads running along whichever index is contiguous in memory
-    stage_tile(sY, MQ, dY, y_dt, M, MP, y_cs, y_flat, s_rowY, g0, g_end, tid);
-    stage_tile(sX, NQ, X, x_dt, N, NP, x_cs, x_flat, s_rowX, g0, g_end, tid);
-    __syncthreads();
+  auto multiply = [&](const float* tY, const float* tX) {
     if (worker) {
       for (int r = rg; r < kWgRows; r += RG) {
-        const float4 y4 = *reinterpret_cast<const float4*>(sY + r * MQ + tm * 4);
-        const float4 x4 = *reinterpret_cast<const float4*>(sX + r * NQ + tn * 4);
+        const float4 y4 = *reinterpret_cast<const float4*>(tY + r * MQ + tm * 4);
+        const float4 x4 = *reinterpret_cast<const float4*>(tX + r * NQ + tn * 4);
         const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yv[i], xv[j], acc[i][j]);
       }
+    }
+  };
+  auto row_offsets = [&](int buf, int64_t g0) {        // threads 0 .. kWgRows-1
+    const int64_t g = g0 + tid;
+    if (g < g_end) {
+      const int64_t b = g / rows, r = g - b * rows;
+      s_rowY[buf][tid] = b * y_bs + r * y_rs;
+      s_rowX[buf][tid] = b * x_bs + r * x_rs;
+    } else {
+      s_rowY[buf][tid] = -1; s_rowX[buf][tid] = -1;
+    }
+  };
+  if (y_dt == SS2D_F32 && x_dt == SS2D_F32) {
+    // double-buffered: tile t + 1 streams into the other buffer (cp.async) while tile t is multiplied; one barrier per tile
+    const int tile_floats = kWgRows * (MQ + NQ);
+    const float* fY = reinterpret_cast<const float*>(dY);
+    const float* fX = reinterpret_cast<const float*>(X);
+    if (tid < kWgRows) row_offsets(0, g_begin);
+    __syncthreads();
+    if (g_begin < g_end) {
+      stage_tile_async(sY, MQ, fY, M, MP, y_cs, y_flat, s_rowY[0], g_begin, g_end, tid);
+      stage_tile_async(sX, NQ, fX, N, NP, x_cs, x_flat, s_rowX[0], g_begin, g_end, tid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int cur = 0;
+    for (int64_t g0 = g_begin; g0 < g_end; g0 += kWgRows, cur ^= 1) {
+      const bool has_next = g0 + kWgRows < g_end;
+      if (has_next && tid < kWgRows) row_offsets(cur ^ 1, g0 + kWgRows);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();          // tile g0 has landed; everybody is done multiplying the tile that used the other buffer
+      if (has_next) {
+        float* nY = s_wg + (cur ^ 1) * tile_floats;
+        stage_tile_async(nY, MQ, fY, M, MP, y_cs, y_flat, s_rowY[cur ^ 1], g0 + kWgRows, g_end, tid);
+        stage_tile_async(nY + kWgRows * MQ, NQ, fX, N, NP, x_cs, x_flat, s_rowX[cur ^ 1], g0 + kWgRows, g_end, tid);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const float* tY = s_wg + cur * tile_floats;
+      multiply(tY, tY + kWgRows * MQ);
+    }
+  } else {
+    for (int64_t g0 = g_begin; g0 < g_end; g0 += kWgRows) {
+      __syncthreads();
+      if (tid < kWgRows) row_offsets(0, g0);
+      __syncthreads();
+      stage_tile(sY, MQ, dY, y_dt, M, MP, y_cs, y_flat, s_rowY[0], g0, g_end, tid);
+      stage_tile(sX, NQ, X, x_dt, N, NP, x_cs, x_flat, s_rowX[0], g0, g_end, tid);
+      __syncthreads();
+      multiply(sY, sX);
     }
   }
   // fold the row groups (fixed order), then write this CTA's M x N partial
@@ -155,7 +219,7 @@ cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch,
   int64_t rpc = (total + ctas - 1) / ctas;
   rpc = (rpc + kWgRows - 1) / kWgRows * kWgRows;
   const int MP = (M + 3) & ~3, NP = (N + 3) & ~3;
-  size_t smem = (size_t)kWgRows * (MP + NP + 8) * 4;
+  size_t smem = (size_t)2 * kWgRows * (MP + NP + 8) * 4;      // two tile buffers
   const size_t red = (size_t)kWgThreads * 16 * 4;
   if (smem < red) smem = red;
   static size_t configured = 0;
