@@ -180,3 +180,29 @@ def test_column_major_directions_equal_row_major_on_the_transposed_image(D, pair
     assert rel_err(y_c, y_r.transpose(1, 2).detach().cpu().numpy()) < 1e-5
     assert rel_err(gx_c, gx_r.transpose(2, 3).cpu().numpy()) < 1e-4
     assert rel_err(gz_c, gz_r.transpose(1, 2).cpu().numpy()) < 1e-4
+
+
+def test_group_mamba_layer_bf16_autocast_at_live_size():
+    """bf16 autocast through the module-level kernels at a size where they are all taken (tall-skinny weight gradients,
+    depthwise-conv parameter gradients, LayerNorm, small-D epilogue): outputs and parameter gradients within 2e-2 /
+    5e-2 of the fp32 run (bf16 GEMM and conv inputs, fp32 scan: ss2d.py:287, 479-480)."""
+    import copy
+
+    import ceigm_unet_b200 as P
+    torch.manual_seed(0)
+    m32 = P.GroupMambaLayer(64, 64).cuda()
+    m16 = copy.deepcopy(m32)
+    x = torch.randn(4, 48 * 48, 64, device="cuda")             # 9 216 rows
+    gy = torch.randn(4, 48 * 48, 64, device="cuda")
+    x32 = x.clone().requires_grad_(True)
+    y32 = m32(x32, 48, 48)
+    y32.backward(gy)
+    x16 = x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = m16(x16, 48, 48)
+    y16.float().backward(gy)
+    assert rel_err(y16.float(), y32.detach().cpu().numpy()) < 2e-2
+    assert rel_err(x16.grad, x32.grad.cpu().numpy()) < 5e-2
+    for (n, a), (_, b) in zip(m16.named_parameters(), m32.named_parameters()):
+        assert a.grad is not None and a.grad.dtype == a.dtype and torch.isfinite(a.grad).all(), n
+        assert rel_err(a.grad, b.grad.cpu().numpy()) < 8e-2, n
