@@ -222,7 +222,7 @@ class _LinearTS(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.matmul(dy2, W.to(dy2.dtype)).view(x.shape).to(x.dtype)
         if ctx.needs_input_grad[1]:
-            if dy2.is_cuda and dy2.shape[0] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N):
+            if dy2.shape[0] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N):
                 dW = ops.wgrad_ts(dy2.unsqueeze(0), x2.unsqueeze(0)).to(W.dtype)
             else:
                 dW = torch.matmul(dy2.t(), x2.to(dy2.dtype)).to(W.dtype)
@@ -231,8 +231,14 @@ class _LinearTS(torch.autograd.Function):
         return dx, dW, db
 
 
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:      # the modules have no CPU path: fail here rather than silently run a library op on the host
+        raise RuntimeError(f"{what}: CUDA tensor expected (ceigm_unet_b200 has no CPU fallback)")
+
+
 def _ts_eligible(rows: int, M: int, N: int, t: torch.Tensor) -> bool:
-    return t.is_cuda and rows >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N)
+    _need_cuda(t, "projection")
+    return rows >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N)
 
 
 def linear_ts(x, W, bias=None):
@@ -259,7 +265,7 @@ class _ProjCM(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             du = torch.matmul(W.t().to(dout.dtype), dout).to(u.dtype)
         if ctx.needs_input_grad[0]:
-            if dout.is_cuda and dout.shape[0] * dout.shape[2] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, D):
+            if dout.shape[0] * dout.shape[2] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, D):
                 dW = ops.wgrad_ts(dout.transpose(1, 2), u.transpose(1, 2)).to(W.dtype)
             else:
                 dW = torch.matmul(dout, u.transpose(1, 2).to(dout.dtype)).sum(dim=0).to(W.dtype)
@@ -297,8 +303,9 @@ class _LayerNormRows(torch.autograd.Function):
 
 
 def layer_norm_rows(x, weight, bias, eps):
-    if not x.is_cuda or x.shape[-1] > ops.LN_MAX_C or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-        return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+    _need_cuda(x, "layer_norm_rows")
+    if x.shape[-1] > ops.LN_MAX_C or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)      # wide rows: library kernel
     return _LayerNormRows.apply(x, weight, bias, eps)
 
 
@@ -327,7 +334,8 @@ class _DWConv3(torch.autograd.Function):
 
 def dwconv3(x, conv: "torch.nn.Conv2d"):
     """SS2D.conv2d through _DWConv3 when it is the reference's depthwise 3 x 3 / padding 1 layer on a CUDA tensor."""
-    ok = (x.is_cuda and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and
+    _need_cuda(x, "dwconv3")
+    ok = (conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and
           conv.dilation == (1, 1) and conv.groups == conv.in_channels == conv.out_channels and conv.padding_mode == "zeros" and
           x.shape[0] * x.shape[2] * x.shape[3] >= _TS_MIN_ROWS)
     return _DWConv3.apply(x, conv.weight, conv.bias) if ok else conv(x)
