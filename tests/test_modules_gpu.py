@@ -206,3 +206,31 @@ def test_group_mamba_layer_bf16_autocast_at_live_size():
     for (n, a), (_, b) in zip(m16.named_parameters(), m32.named_parameters()):
         assert a.grad is not None and a.grad.dtype == a.dtype and torch.isfinite(a.grad).all(), n
         assert rel_err(a.grad, b.grad.cpu().numpy()) < 8e-2, n
+
+
+def test_ss2d_vmamba_regime_cuda_graphs_match_eager():
+    """graphed() around the K = 4, d_state = 16 SS2D: the TMA tensor maps of scan_fwd / scan_bwd2 are kernel parameters
+    baked at capture time over the graph's static buffers; replays must reproduce the eager forward and backward."""
+    import copy
+
+    import ceigm_unet_b200 as P
+    torch.manual_seed(1)
+    eager = P.SS2D(d_model=24, d_state=16, ssm_ratio=2.0, k_group=4).cuda()
+    captured = copy.deepcopy(eager)
+    x = torch.randn(3, 12, 16, 24, device="cuda", requires_grad=True)
+    gy = torch.randn(3, 12, 16, 24, device="cuda")
+    g = P.graphed(captured, (x.detach().clone().requires_grad_(True),))
+    res = []
+    for fn, mod in ((g, captured), (eager, eager)):
+        for rep in range(2):
+            xin = (x.detach() * (1.0 + 0.5 * rep)).requires_grad_(True)         # new values, same buffers on replay
+            for p_ in mod.parameters():
+                p_.grad = None
+            y = fn(xin)
+            y.backward(gy)
+        res.append((y.detach().clone(), xin.grad.clone(), [p_.grad.clone() for p_ in mod.parameters()]))
+    (y1, gx1, gp1), (y2, gx2, gp2) = res
+    assert rel_err(y1, y2.cpu().numpy()) < 1e-5
+    assert rel_err(gx1, gx2.cpu().numpy()) < 1e-4
+    for a, b in zip(gp1, gp2):
+        assert rel_err(a, b.cpu().numpy()) < 1e-3
