@@ -13,9 +13,10 @@
 //     reversed traversals cost nothing afterwards); du / d(delta) are written over dout' / delta' and leave as
 //     128-bit row-contiguous stores at the end of the tile.
 //   * sum over states (du, d delta): shuffle reduce-scatter over the 8 state lanes; sum over rows (dB, dC): x+y of
-//     the packed halves, reduce-scatter over the 4 row-pair lanes, then a 512-byte slab per warp and group that the
-//     four warps fold together one group later (mbarrier hand-off, no CTA barrier) into one red.global.add.v4.f32
-//     per (state, 4 positions) and CTA.
+//     the packed halves, reduce-scatter over the 4 row-pair lanes, then one red.global.add.v2.f32 per lane and state
+//     straight from registers: each warp adds the totals of its 8 rows to dB / dC in L2. (A first version folded the
+//     four warps' totals through shared-memory slabs with an mbarrier hand-off per group to issue a quarter of the
+//     reductions; the hand-off coupled the warps and cost 10 % of the kernel, the extra L2 reductions cost nothing.)
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -32,12 +33,11 @@ constexpr int B2_CH = B2_NW * B2_RPW;       // rows per CTA
 constexpr int B2_STAGES = 2;
 constexpr int B2_WSTAGE = 3 * 1024;         // delta | u | dout tiles of one warp (8 rows x 128 bytes each)
 constexpr int B2_BC_STAGE = 4096;           // B | C tiles, 16 state rows each
-constexpr int B2_HS_BYTES = 7 * 512;        // per warp: states at the 7 inner group boundaries of a tile
+constexpr int B2_HS_BYTES = 8 * 512;        // per warp: states at the 7 inner group boundaries of a tile + the tile's entry state
 constexpr int B2_OFF_ROWS = B2_STAGES * B2_BC_STAGE;
 constexpr int B2_OFF_UP = B2_OFF_ROWS + B2_NW * B2_STAGES * B2_WSTAGE;
 constexpr int B2_OFF_HS = B2_OFF_UP + B2_NW * 1024;
-constexpr int B2_OFF_SLAB = B2_OFF_HS + B2_NW * B2_HS_BYTES;
-constexpr int B2_OFF_BARS = B2_OFF_SLAB + 2 * B2_NW * 512;
+constexpr int B2_OFF_BARS = B2_OFF_HS + B2_NW * B2_HS_BYTES;
 constexpr size_t B2_SMEM = B2_OFF_BARS + 256 + 1024;
 
 struct Bwd2Maps { TMap u, dl, dy, B, C; };
@@ -120,13 +120,10 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   const uint32_t a_rows = sm + B2_OFF_ROWS + warp * (B2_STAGES * B2_WSTAGE);  // [STAGES][delta | u | dout]
   const uint32_t a_up = sm + B2_OFF_UP + warp * 1024;                        // u pairs of the current tile
   const uint32_t a_hs = sm + B2_OFF_HS + warp * B2_HS_BYTES + lane * 16;     // this lane's group-boundary states
-  const uint32_t a_slab = sm + B2_OFF_SLAB;                                  // [2][NW][512]
   const uint32_t a_bars = sm + B2_OFF_BARS;
   const uint32_t a_full_w = a_bars + warp * (B2_STAGES * 8);                 // [NW][STAGES]
   const uint32_t a_full_bc = a_bars + B2_NW * B2_STAGES * 8;                 // [STAGES]
-  const uint32_t a_slab_full = a_full_bc + B2_STAGES * 8;                    // [2]
-  const uint32_t a_slab_empty = a_slab_full + 16;                            // [2]
-  const uint32_t a_cnt_bc = a_slab_empty + 16;                               // [STAGES] ints
+  const uint32_t a_cnt_bc = a_full_bc + B2_STAGES * 8;                      // [STAGES] ints
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_OFF_BARS);
 
   const int b = blockIdx.z, g = blockIdx.y;
@@ -138,12 +135,10 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   const bool rev = dir == 3;
   const int ntiles = (L + 31) / 32;
   const int ug = p.u_mod > 0 ? g % (p.u_mod / p.dpg) : g;          // group coordinate of u and dout
-  const bool single_cta_group = gridDim.x == 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < B2_NW * B2_STAGES + B2_STAGES; ++i) mbar_init(&bars[i], 1);          // full_w, full_bc
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[B2_NW * B2_STAGES + B2_STAGES + i], B2_NW);  // slab_full, slab_empty
-    for (int s = 0; s < B2_STAGES; ++s) reinterpret_cast<int*>(bars + B2_NW * B2_STAGES + B2_STAGES + 4)[s] = 0;
+    for (int s = 0; s < B2_STAGES; ++s) reinterpret_cast<int*>(bars + B2_NW * B2_STAGES + B2_STAGES)[s] = 0;
     fence_mbar_init();
   }
   __syncthreads();
@@ -201,20 +196,15 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   // shared-memory offsets as (lane constant) ^ (uniform term): one LOP3 per access inside the loops
   const int rowc = (rp * 256) | (rp << 4);                                   // b2_p_off(rp, ch) = rowc ^ (su(ch) << 4)
   const int qc = (q * 128) | (q << 4);                                       // b2_t_off(q + 8 j, c4) = (qc ^ (c4 << 4)) + 1024 j
-  // Lane constants of the finishing / folding steps, packed into ONE opaque register: at the 128-register cap ptxas
-  // otherwise re-derives each of them from %tid in every group (~35 instructions per group).
-  //   bits 0-9: finisher's scalar slot; 10-21: slab write offset; 22-26: slab read slot; 27-30: dB/dC state; 31: folds
-  const int ro = warp * 8 + (lane & 7);                                      // folding step (lanes 0-7): tensor ro >> 4, state ro & 15
+  // The finisher's scalar slot, kept in an opaque register: at the 128-register cap ptxas otherwise re-derives it from
+  // %tid in every group.
   uint32_t pk;
   {
-    const uint32_t fc0 = (rowc ^ ((fe >> 1) << 4)) | (((fe & 1) * 2 + rr) * 4);
-    const uint32_t sw0 = warp * 512 + ((rp >> 1) * 16 + q) * 16 + (rp & 1) * 8;   // state q; q + 8 at + 128
-    const uint32_t ok0 = (lane < 8 && (ro & 15) < p.N) ? 1u : 0u;
-    const uint32_t v = fc0 | (sw0 << 10) | ((uint32_t)ro << 22) | (ok0 << 31);
+    const uint32_t v = (rowc ^ ((fe >> 1) << 4)) | (((fe & 1) * 2 + rr) * 4);
     asm volatile("mov.b32 %0, %1;" : "=r"(pk) : "r"(v));
   }
-  float* const red_base = ((ro >> 4) == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + (ro & 15)) * L;
-  const int lmax = ntiles * 32 - 4;                                          // scan position of global group 0
+  // dB / dC destination of this lane: tensor rp >> 1, state q (state q + 8 lies 8 L further)
+  float* const red_lane = ((rp >> 1) == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + q) * L;
 
   auto load_ckpt = [&](int t, float2* h) {     // state before tile t = checkpoint at the end of tile t - 1
 #pragma unroll
@@ -224,29 +214,6 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       h[j].x = (ok && v0) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp) * p.nck + (t - 1)) * p.N + n) : 0.f;
       h[j].y = (ok && v1) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp + 1) * p.nck + (t - 1)) * p.N + n) : 0.f;
     }
-  };
-
-  // dB / dC of global group kk (all warps wrote their slab): fold the NW slabs, one vector reduction per (state, 4 pos)
-  auto reduce_group = [&](int kk, auto REV) {
-    constexpr bool REVV = decltype(REV)::value;
-    const int buf = kk & 1;
-    mbar_wait32(a_slab_full + buf * 8, (kk >> 1) & 1);
-    const int l = lmax - 4 * kk;                            // first scan position of the group
-    if ((int)pk < 0 && l < L) {
-      const uint32_t src = a_slab + ((pk >> 22) & 31) * 16 + buf * (B2_NW * 512);
-      float4 acc = lds128(src);
-#pragma unroll
-      for (int w = 1; w < B2_NW; ++w) {
-        const float4 v = lds128(src + w * 512);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      float* dst = red_base + (REVV ? L - 4 - l : l);
-      if (REVV) acc = make_float4(acc.w, acc.z, acc.y, acc.x);
-      if (single_cta_group) *reinterpret_cast<float4*>(dst) = acc;
-      else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive32(a_slab_empty + buf * 8);
   };
 
   auto body = [&](auto REV) {
@@ -307,6 +274,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       //          7 groups is parked in shared memory. 
       {
         float2 h[2] = {h0[0], h0[1]};
+        sts128(a_hs + 7 * 512, make_float4(h0[0].x, h0[0].y, h0[1].x, h0[1].y));     // read back by the last group (gi = 0)
 #pragma unroll 1
         for (int gi = 0; gi < 7; ++gi) {
           const uint32_t pa = a_dl + (rowc ^ (((2 * gi ^ (gi >> 2)) & 15) << 4));
@@ -336,7 +304,6 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       // head of the next (1.234 -> 1.180 ms; by 8 the instruction cache gives it back: 1.258 ms)
 #pragma unroll 4
       for (int gi = 7; gi >= 0; --gi) {
-        const int k = it * 8 + (7 - gi);                 // global group counter (slab hand-off)
         const int su4 = ((2 * gi ^ (gi >> 2)) & 15) << 4;
         const uint32_t pa = a_dl + (rowc ^ su4);
         const float4 d01 = lds128(pa), d23 = lds128(pa ^ 16);
@@ -346,8 +313,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
         const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
         const float2 dy2[4] = {make_float2(y01.x, y01.y), make_float2(y01.z, y01.w), make_float2(y23.x, y23.y), make_float2(y23.z, y23.w)};
         float4 hin4;
-        if (gi > 0) hin4 = lds128(a_hs + (gi - 1) * 512);
-        else hin4 = make_float4(h0[0].x, h0[0].y, h0[1].x, h0[1].y);
+        hin4 = lds128(a_hs + ((gi + 7) & 7) * 512);       // state before the group; slot 7 holds the tile's entry state
         const uint32_t ba = a_B + (qc ^ ((REVV ? 7 - gi : gi) << 4));
         float2 sB2[4], sA2[4];
 #pragma unroll
@@ -398,7 +364,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
         }
         B2ReduceScatter<1, 16, 4>::run(vals, q);
         {
-          const uint32_t off = (pk & 1023) ^ su4;
+          const uint32_t off = pk ^ su4;
           const float de = lds32(a_dl + off);
           const float dyv = lds32(a_dy + off);
           const float uu = lds32(a_up + off);
@@ -416,16 +382,20 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
           sts32(a_dy + off, du_out);
           sts32(a_dl + off, ddl);
         }
-        // ---- park this warp's dB / dC totals of the group in its slab: [dB | dC][16 states][4 positions] ----
+        // ---- dB / dC: this warp's totals go straight to global memory, one red.global.add.v2.f32 per lane and state
+        //      (lane (rp, q): tensor rp >> 1, positions 2 (rp & 1), + 1 of the group, states q and q + 8) ----
         {
-          const int buf = k & 1;
-          mbar_wait32(a_slab_empty + buf * 8, ((k >> 1) & 1) ^ 1);
-          const uint32_t slab_w = a_slab + ((pk >> 10) & 4095) + buf * (B2_NW * 512);
-          sts64(slab_w, make_float2(pout[0][0], pout[0][1]));
-          sts64(slab_w + 8 * 16, make_float2(pout[1][0], pout[1][1]));
-          __syncwarp();
-          if (lane == 0) mbar_arrive32(a_slab_full + buf * 8);
-          if (k > 0) reduce_group(k - 1, REV);
+          const int l = l0 + gi * 4 + 2 * (rp & 1);
+          if (rows_valid > 0 && l < L) {
+            float* dst = red_lane + (REVV ? L - 2 - l : l);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (q + 8 * j < p.N) {
+                const float a = REVV ? pout[j][1] : pout[j][0], c = REVV ? pout[j][0] : pout[j][1];
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + (int64_t)8 * j * L), "f"(a), "f"(c) : "memory");
+              }
+            }
+          }
         }
       }
       __syncwarp();
@@ -464,7 +434,6 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       }
       __syncwarp();
     }
-    reduce_group(ntiles * 8 - 1, REV);
   };
   if (rev) body(std::true_type{}); else body(std::false_type{});
 
@@ -514,6 +483,7 @@ bool scan_bwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   }
   Bwd2Maps maps;
   if (!bwd2_maps(p, &maps)) return false;
+
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(scan_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
