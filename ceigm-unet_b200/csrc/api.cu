@@ -1,6 +1,8 @@
 // C ABI of libss2d_b200.so: argument validation, parameter packing, variant dispatch. No torch, no allocation.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -15,12 +17,8 @@ cudaError_t scan_bwd_finalize(const ScanParams& p, float* dA, float* dD, float* 
 cudaError_t scan_par_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_par_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
 
-// d_state == 1 (the live GM-UNet regime) runs the parallel-along-L kernels (scan_par.cu); SS2D_FORCE_SEQ=1 keeps the
-// row-sequential kernels for comparison.
-static bool use_par(const ScanParams& p) {
-  static const bool force_seq = getenv("SS2D_FORCE_SEQ") != nullptr;
-  return p.N == 1 && p.A_ld == 1 && !force_seq;
-}
+// d_state == 1 (the live GM-UNet regime) runs the parallel-along-L kernels (scan_par.cu)
+static bool use_par(const ScanParams& p) { return p.N == 1 && p.A_ld == 1; }
 cudaError_t cross_scan_launch(const void* x, void* xs, int batch, int channels, int H, int W, int K, const int* dirs,
                               int dtype, cudaStream_t stream);
 cudaError_t cross_merge_launch(const void* ys, void* y, int batch, int channels, int H, int W, int K, const int* dirs,
@@ -52,7 +50,8 @@ cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch,
 int epi_max_D(bool backward);
 
 thread_local char g_cuda_err[256] = "";
-thread_local int64_t g_launches = 0;
+// process-wide: the autograd engine launches the backward kernels from its own per-device threads
+static std::atomic<int64_t> g_launches{0};
 
 static int cuda_fail(cudaError_t e) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -190,6 +189,13 @@ int ss2d_scan_bwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
   if (!workspace || workspace_bytes < ss2d_scan_bwd_workspace_bytes(d, ckpt != nullptr) || !aligned(workspace, 16))
     return SS2D_ERR_WORKSPACE;
   if (ckpt && !aligned(ckpt, 16)) return SS2D_ERR_ALIGNMENT;
+  // element alignment as in the forward; dB / dC are accumulated with 128-bit red.global / vector stores when L % 4 == 0
+  const size_t bc_al = (d->seqlen & 3) ? 4 : 16;
+  if (!aligned(u, esize(d->io_dtype)) || !aligned(delta, esize(d->io_dtype)) || !aligned(Bmat, esize(d->io_dtype)) ||
+      !aligned(Cmat, esize(d->io_dtype)) || !aligned(A, 4) || !aligned(dout, esize(d->out_dtype)) ||
+      !aligned(du, esize(d->io_dtype)) || !aligned(ddelta, esize(d->io_dtype)) || !aligned(dA, 4) ||
+      !aligned(dB, bc_al) || !aligned(dC, bc_al))
+    return SS2D_ERR_ALIGNMENT;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(workspace);
   const int nmax = d->dstate < kStatesPerPass ? d->dstate : kStatesPerPass;
@@ -251,6 +257,8 @@ int ss2d_cross_merge(const void* ys, void* y, int32_t batch, int32_t channels, i
   ++g_launches;
   return SS2D_OK;
 }
+
+int32_t ss2d_out_gate_max_width(int32_t backward) { return epi_max_D(backward != 0); }
 
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L) {
   if (batch <= 0 || L <= 0) return 0;
@@ -373,7 +381,7 @@ const char* ss2d_strerror(int status) {
     case SS2D_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
     case SS2D_ERR_CUDA: return "CUDA runtime error (see ss2d_last_cuda_error)";
     case SS2D_ERR_UNSUPPORTED: return "unsupported combination";
-    case SS2D_ERR_ALIGNMENT: return "pointer not aligned to its element size";
+    case SS2D_ERR_ALIGNMENT: return "pointer not aligned to its element size (checkpoints, and dB / dC when L % 4 == 0: 16 bytes)";
     default: return "unknown status";
   }
 }
@@ -381,9 +389,7 @@ const char* ss2d_strerror(int status) {
 const char* ss2d_last_cuda_error(void) { return g_cuda_err; }
 const char* ss2d_version(void) { return "ss2d_b200 0.1.0 sm_100a"; }
 int64_t ss2d_launch_count(int reset) {
-  const int64_t v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 }  // extern "C"

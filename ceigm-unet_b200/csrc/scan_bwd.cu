@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "scan_params.h"
+#include "host_util.h"
 #include "scan_tile.cuh"
 #include "tma_host.h"
 
@@ -537,12 +538,9 @@ template <int NS, int R, int RPT>
 static cudaError_t launch_bwd(ScanParams p, cudaStream_t stream) {
   using S = BwdShape<NS, R, RPT>;
   auto kern = scan_bwd_kernel<NS, R, RPT>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  cudaError_t ea = func_attr_once(once, reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
+  if (ea != cudaSuccess) return ea;
   TmaMaps maps;
   if (p.tma_ok && !(p.u_mod == 0 || p.u_mod % p.dpg == 0)) p.tma_ok = 0;
   if (p.tma_ok && !make_scan_maps(p, S::CH, S::NPB, true, &maps)) p.tma_ok = 0;
@@ -566,10 +564,9 @@ cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream) {
     // Two rows per thread amortise the B/C loads and the dB/dC row reduction (best on big grids); one row per thread
     // needs fewer registers / shared memory (4 CTAs per SM instead of 3) and halves the CTA size, which wins when the
     // two-row grid would not fill ~2.5 waves (measured on vm_d96 / vm_d192 / vm_d384, B200).
-    static const int forced = getenv("SS2D_BWD_RPT") ? atoi(getenv("SS2D_BWD_RPT")) : 0;     // tuning knob
-    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    const int sms = sm_count_current_device();
     const long ctas2 = (long)((p.dpg + 31) / 32) * p.G * p.batch;
-    const int rpt = forced ? forced : (ctas2 * 2 < 5L * 3 * sms ? 1 : 2);
+    const int rpt = ctas2 * 2 < 5L * 3 * sms ? 1 : 2;
     return rpt == 1 ? launch_bwd<2, 8, 1>(p, stream) : launch_bwd<2, 8, 2>(p, stream);
   }
   return launch_bwd<4, 8, 1>(p, stream);

@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "scan_params.h"
+#include "host_util.h"
 #include "common.cuh"
 #include "tma_host.h"
 
@@ -471,8 +472,7 @@ static bool bwd2_maps(const ScanParams& p, Bwd2Maps* m) {
 
 // Returns true when the fast path took the call (*err holds the launch status).
 bool scan_bwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
-  static const int enabled = getenv("SS2D_BWD_V2") ? atoi(getenv("SS2D_BWD_V2")) : 1;
-  if (!enabled || !p.tma_ok || p.N <= 8 || p.N > 16 || p.accum || p.io_dtype != SS2D_F32 || p.out_dtype != SS2D_F32) return false;
+  if (!p.tma_ok || p.N <= 8 || p.N > 16 || p.accum || p.io_dtype != SS2D_F32 || p.out_dtype != SS2D_F32) return false;
   if (p.u_mod > 0 && p.u_mod % p.dpg != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p.du) & 15) || (reinterpret_cast<uintptr_t>(p.ddelta) & 15) ||
       (reinterpret_cast<uintptr_t>(p.dB) & 15) || (reinterpret_cast<uintptr_t>(p.dC) & 15))
@@ -484,11 +484,10 @@ bool scan_bwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   Bwd2Maps maps;
   if (!bwd2_maps(p, &maps)) return false;
 
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(scan_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
+  static PerDeviceOnce once;
+  {
+    cudaError_t e = func_attr_once(once, reinterpret_cast<const void*>(scan_bwd2_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
     if (e != cudaSuccess) { *err = e; return true; }
-    configured = true;
   }
   dim3 grid((p.dpg + B2_CH - 1) / B2_CH, p.G, p.batch);
   scan_bwd2_kernel<<<grid, B2_NW * 32, B2_SMEM, stream>>>(p, maps);

@@ -13,6 +13,7 @@
 #include <type_traits>
 
 #include "scan_params.h"
+#include "host_util.h"
 #include "scan_tile.cuh"
 #include "tma_host.h"
 
@@ -261,12 +262,9 @@ template <int NS, int R, int RPT, int STAGES>
 static cudaError_t launch_fwd(ScanParams p, cudaStream_t stream) {
   using S = FwdShape<NS, R, RPT, STAGES>;
   auto kern = scan_fwd_kernel<NS, R, RPT, STAGES>;
-  static bool configured = false;     // per instantiation; the attribute is per-function and sticky
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce once;     // per instantiation and per device (the attribute is per-function, per-device and sticky)
+  cudaError_t ea = func_attr_once(once, reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
+  if (ea != cudaSuccess) return ea;
   TmaMaps maps;
   if (p.tma_ok && !(p.u_mod == 0 || p.u_mod % p.dpg == 0)) p.tma_ok = 0;
   if (p.tma_ok && !make_scan_maps(p, S::CH, S::NPB, false, &maps)) p.tma_ok = 0;
@@ -282,12 +280,7 @@ cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream) {
   if (v.NS == 2) return launch_fwd<2, 1, 1, 3>(p, stream);
   if (v.R == 1) return launch_fwd<4, 1, 1, 3>(p, stream);
   if (v.R == 2) return launch_fwd<4, 2, 1, 3>(p, stream);
-  if (v.R == 4) {
-    static const int rpt = getenv("SS2D_FWD_RPT") ? atoi(getenv("SS2D_FWD_RPT")) : 1;     // tuning knob
-    static const int stg = getenv("SS2D_FWD_STAGES") ? atoi(getenv("SS2D_FWD_STAGES")) : 3;
-    if (rpt == 2) return stg == 2 ? launch_fwd<4, 4, 2, 2>(p, stream) : launch_fwd<4, 4, 2, 3>(p, stream);
-    return stg == 2 ? launch_fwd<4, 4, 1, 2>(p, stream) : stg == 4 ? launch_fwd<4, 4, 1, 4>(p, stream) : launch_fwd<4, 4, 1, 3>(p, stream);
-  }
+  if (v.R == 4) return launch_fwd<4, 4, 1, 3>(p, stream);     // measured best of RPT in {1, 2} x STAGES in {2, 3, 4}
   return launch_fwd<4, 8, 1, 3>(p, stream);
 }
 

@@ -9,6 +9,7 @@
 // 32/64 contiguous bytes. Longer rows are walked in chunks of T*P positions with the carry kept on chip.
 // Replaces the same reference code as scan_fwd.cu / scan_bwd.cu (selective_scan_{fwd,bwd}_kernel.cuh) for N = 1.
 #include "scan_params.h"
+#include "host_util.h"
 #include "scan_tile.cuh"
 
 namespace ss2d {
@@ -426,11 +427,8 @@ static cudaError_t launch_par_fwd(const ScanParams& p, cudaStream_t stream) {
 template <int T>
 static cudaError_t launch_par_bwd(const ScanParams& p, cudaStream_t stream) {
   dim3 grid((p.dpg + ParShape<T>::RT - 1) / ParShape<T>::RT, p.G, p.batch);
-  static bool configured = false;
-  if (!configured) {   // 16.6 KB of static shared memory per CTA: ask for a carve-out that fits several CTAs per SM
-    cudaFuncSetAttribute(scan_par_bwd_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    configured = true;
-  }
+  static PerDeviceOnce once;   // 16.6 KB of static shared memory per CTA: ask for a carve-out that fits several CTAs per SM
+  func_attr_once(once, reinterpret_cast<const void*>(scan_par_bwd_kernel<T>), cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   scan_par_bwd_kernel<T><<<grid, kParThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }

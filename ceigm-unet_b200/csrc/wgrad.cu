@@ -10,6 +10,7 @@
 // channel-major (B, C, L) operands of the 1 x 1 projections are read in place, coalesced along whichever index is
 // contiguous. fp32 / fp16 / bf16 operands, fp32 accumulation and result.
 #include "common.cuh"
+#include "host_util.h"
 
 namespace ss2d {
 
@@ -222,11 +223,11 @@ cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch,
   size_t smem = (size_t)2 * kWgRows * (MP + NP + 8) * 4;      // two tile buffers
   const size_t red = (size_t)kWgThreads * 16 * 4;
   if (smem < red) smem = red;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024) {      // one opt-in to the kernel's largest footprint per device (MP, NP <= 256)
+    static PerDeviceOnce once;
+    const int max_smem = 2 * kWgRows * (272 + 8) * 4;      // MP * NP <= 4096 and MP, NP <= 256 -> MP + NP <= 272
+    cudaError_t e = func_attr_once(once, reinterpret_cast<const void*>(wgrad_ts_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   wgrad_ts_kernel<<<ctas, kWgThreads, smem, stream>>>(dY, X, workspace, total, rows, M, N, y_bs, y_rs, y_cs, x_bs, x_rs,
                                                        x_cs, y_dt, x_dt, rpc);

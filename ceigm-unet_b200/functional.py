@@ -304,6 +304,8 @@ class _LayerNormRows(torch.autograd.Function):
 
 def layer_norm_rows(x, weight, bias, eps):
     _need_cuda(x, "layer_norm_rows")
+    if torch.is_autocast_enabled() and x.dtype in (torch.float16, torch.bfloat16):
+        x = x.float()      # nn.LayerNorm is on autocast's fp32 list: 16-bit inputs are normalised in, and returned as, fp32
     if x.shape[-1] > ops.LN_MAX_C or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)      # wide rows: library kernel
     return _LayerNormRows.apply(x, weight, bias, eps)

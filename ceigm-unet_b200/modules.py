@@ -158,6 +158,22 @@ class SS2D(nn.Module, mamba_init):
             dts, Bs, Cs = dts.to(u.dtype), Bs.to(u.dtype), Cs.to(u.dtype)
         ys = Fn._SS2DScanNatural.apply(u.contiguous(), dts, As, Bs, Cs, Ds, bias, H, W, kdirs, P)   # (B, K/P, P, D, L)
         zz = z.reshape(Bn, L, D) if z is not None else None
+        if D > Fn.ops.out_gate_max_D(backward=torch.is_grad_enabled()):
+            # rows wider than the fused epilogue's shared-memory tiles (VMamba stage 4: d_inner = 1536): merge, LayerNorm and
+            # gate as separate passes, exactly the reference's sequence (ss2d.py:486-498, 515-517)
+            planes_y = [ys[:, i, j].reshape(Bn, D, W, H).transpose(2, 3).reshape(Bn, D, L) if tflags[j] else ys[:, i, j]
+                        for i in range(K // P) for j in range(P)]
+            if len(planes_y) == 4:
+                ym = (planes_y[0] + planes_y[2]) + (planes_y[1] + planes_y[3])                   # csms6s.py:38-39
+            else:
+                ym = planes_y[0]
+                for q in planes_y[1:]:
+                    ym = ym + q
+            y = F.layer_norm(ym.transpose(1, 2), (D,), self.out_norm.weight.float(), self.out_norm.bias.float(),
+                             self.out_norm.eps).to(x.dtype)
+            if zz is not None:
+                y = y * F.silu(zz)
+            return y.view(Bn, H, W, D)
         tplanes = sum(1 << j for j, t in enumerate(tflags) if t)
         y = Fn._OutGate.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, True,
                               self.out_norm.eps, x.dtype, H, W, tplanes)

@@ -205,6 +205,10 @@ def cross_merge(ys: torch.Tensor, hw: Tuple[int, int], dirs: Sequence[int]) -> t
 
 
 # ---- fused epilogue ----------------------------------------------------------------------------
+def out_gate_max_D(backward: bool) -> int:
+    return int(_lib.lib().ss2d_out_gate_max_width(1 if backward else 0))
+
+
 def out_gate_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, out_dtype, hw=(0, 0), tmask: int = 0):
     """ys (B, K, D, L) fp32 natural order; z (B, L, D) view with stride(-1)==1 or None -> out (B, L, D), mean_rstd."""
     _require(ys.is_cuda and ys.dtype == torch.float32 and ys.is_contiguous(), "ys must be contiguous CUDA fp32")

@@ -105,7 +105,8 @@ size_t ss2d_scan_ckpt_floats(const ss2d_scan_desc* desc);
  * dout has out's dtype/strides; du, ddelta have u's / delta's dtype and strides.
  * dA (dim, dstate), dD (dim) or NULL, ddelta_bias (dim) or NULL: fp32, fully overwritten.
  * dB, dC: fp32 (batch, group, dstate, L | H, W) contiguous accumulators that the caller has ZEROED
- *         (the reference does the same: torch::zeros_like(B, fp32), selective_scan.cpp:322-323).
+ *         (the reference does the same: torch::zeros_like(B, fp32), selective_scan.cpp:322-323); 16-byte aligned
+ *         when L % 4 == 0 (they are then updated with 128-bit accesses), else SS2D_ERR_ALIGNMENT.
  * ckpt: the buffer written by ss2d_scan_fwd for the same inputs, or NULL: the states are then
  *       recomputed by an extra forward sweep into `workspace`.
  * workspace: ss2d_scan_bwd_workspace_bytes(desc, ckpt != NULL) bytes, 16-byte aligned. */
@@ -121,12 +122,15 @@ size_t ss2d_scan_bwd_workspace_bytes(const ss2d_scan_desc* desc, int have_ckpt);
  * cross_scan : x (batch, channels, H, W) -> xs (batch, K, channels, L), xs[:,k] in direction dirs[k].
  * cross_merge: ys (batch, K, channels, L) in scan order -> y (batch, channels, L) natural order,
  *              summed over k in the reference's association ((k0 + k2) + (k1 + k3)) when K == 4.
- * With transpose_adjoint != 0 the same kernels compute the adjoints (backward of merge = scan,
- * backward of scan = merge). */
+ * The two are each other's adjoints: the backward of merge is scan and the backward of scan is merge. */
 int ss2d_cross_scan(const void* x, void* xs, int32_t batch, int32_t channels, int32_t H, int32_t W,
                     int32_t K, const int32_t* dirs, int32_t dtype, ss2d_stream_t stream);
 int ss2d_cross_merge(const void* ys, void* y, int32_t batch, int32_t channels, int32_t H, int32_t W,
                      int32_t K, const int32_t* dirs, int32_t dtype, ss2d_stream_t stream);
+
+/* Largest D the fused epilogue handles (its tiles live in shared memory): forward 1664, backward 832. Wider rows return
+ * SS2D_ERR_UNSUPPORTED; the caller composes merge + LayerNorm + gate from separate passes instead (modules.SS2D does). */
+int32_t ss2d_out_gate_max_width(int32_t backward);
 
 /* ---- fused epilogue: merge over K + (B,D,L)->(B,L,D) + LayerNorm(D) + SiLU gate ------------------
  * Replaces CrossMerge + the transpose copy + out_norm + act(z) + `y * z` of model/gm/ss2d.py:486-498,

@@ -21,6 +21,15 @@ import torch.nn.functional as F
 from .cross_scan import cross_merge_k, cross_scan_k
 from .selective_scan_ref import selective_scan_ref
 
+# Module-level checks at the live shapes swap in the C-backed scan (oracle/fast_scan.py: same function, analytic backward);
+# the default stays the restated reference loop so that the golden-pinned tests exercise it.
+_SCAN = [selective_scan_ref]
+
+
+def use_fast_scan(on: bool = True) -> None:
+    from .fast_scan import selective_scan_fast
+    _SCAN[0] = selective_scan_fast if on else selective_scan_ref
+
 
 def ss2d_core(x, p, directions, force_fp32=True):
     """x: (B, D, H, W) -> (B, H, W, D) after out_norm. p: mapping with x_proj_weight (K,R+2N,D),
@@ -40,7 +49,7 @@ def ss2d_core(x, p, directions, force_fp32=True):
     bias = p["dt_projs_bias"].reshape(-1).float()
     if force_fp32:                                                                # :479-480
         u, dts, Bs, Cs = u.float(), dts.float(), Bs.float(), Cs.float()
-    ys = selective_scan_ref(u, dts, As, Bs.contiguous(), Cs.contiguous(), Ds, None, bias, True)
+    ys = _SCAN[0](u, dts, As, Bs.contiguous(), Cs.contiguous(), Ds, None, bias, True)
     ys = ys.view(Bn, K, D, H, W)                                                  # :484
     parts = [cross_merge_k(ys[:, i:i + 1], k) for i, k in enumerate(directions)]  # :486
     if len(parts) == 4:

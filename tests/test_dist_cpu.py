@@ -43,6 +43,25 @@ def _worker(rank, world, port, out_dir):
     D.allreduce_module_grads_(lin)
     for p, q in zip(lin.parameters(), full.parameters()):
         assert torch.allclose(p.grad, q.grad, atol=1e-6)
+    # 4. the overlapped bucketed reducer gives the same averaged gradients, step after step, with an unused parameter
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    net.unused = torch.nn.Parameter(torch.ones(7))
+    ref_net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    ref_net.load_state_dict({k: v for k, v in net.state_dict().items() if k != "unused"})
+    red = D.GradReducer(net, bucket_bytes=64)            # tiny buckets: several collectives in flight
+    assert len(red.buckets) >= 2
+    for step in range(2):
+        xb = torch.randn(8, 6, generator=torch.Generator().manual_seed(10 + step))
+        ref_net.zero_grad()
+        ref_net(xb).square().mean().backward()
+        red.zero_grad()
+        net(xb[a:b]).square().mean().backward()
+        red.finish()
+        for (n1, p), (n2, q) in zip(list(net.named_parameters())[1:], ref_net.named_parameters()):
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), (step, n1)
+        assert float(net.unused.grad.abs().sum()) == 0.0
+    red.remove()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 

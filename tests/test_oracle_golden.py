@@ -128,3 +128,46 @@ def test_ss2d_vm_restatement():
 
 def test_group_layer_restatement():
     _module_case(os.path.join(GOLDEN, "group_mamba_layer.npz"), lambda x, p: ss2d_ref.group_layer(x, p, 6, 6))
+
+
+def test_fast_scan_matches_ref():
+    """oracle/fast_scan.py (C oracle behind an autograd.Function) == autograd through the restated reference loop."""
+    from oracle.fast_scan import selective_scan_fast
+    from oracle.selective_scan_ref import make_inputs
+    for (b, d, L, n, g) in ((2, 8, 37, 1, 1), (2, 12, 64, 16, 4), (1, 6, 50, 4, 2)):
+        a = make_inputs(b, d, L, n, groups=g, seed=3, requires_grad=True)
+        c = {k: (v.detach().clone().requires_grad_(v.requires_grad) if v is not None else None) for k, v in a.items()}
+        o1 = selective_scan_ref(a["u"], a["delta"], a["A"], a["B"], a["C"], a["D"], None, a["delta_bias"], True)
+        o2 = selective_scan_fast(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], None, c["delta_bias"], True)
+        o1.backward(a["dout"]); o2.backward(c["dout"])
+        assert rel_err(o2.detach().numpy(), o1.detach().numpy()) < 1e-5
+        for k in ("u", "delta", "A", "B", "C", "D", "delta_bias"):
+            assert rel_err(c[k].grad.numpy(), a[k].grad.numpy()) < 2e-5, k
+
+
+def test_group_layer_oracle_matches_reference_module_live_shape():
+    """The restated GroupMambaLayer with the fast scan against the UNMODIFIED reference module (python scan) at a live-sized
+    channel count (C = 64 as in stage 1, a 12 x 12 map to keep the python loop short). Needs the reference tree."""
+    from harness import refmodel
+    if not refmodel.available():
+        pytest.skip("reference tree not installed (baseline/_ref)")
+    refmodel.load_reference(scan="cpu_ref")
+    _, _, gmb = refmodel.reference_modules()
+    torch.manual_seed(5)
+    layer = gmb.GroupMambaLayer(64, 64)
+    x = torch.randn(2, 144, 64, requires_grad=True)
+    y = layer(x, 12, 12)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ss2d_ref.use_fast_scan(True)
+    try:
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+        x2 = x.detach().clone().requires_grad_(True)
+        y2 = ss2d_ref.group_layer(x2, p, 12, 12)
+        y2.backward(dy)
+    finally:
+        ss2d_ref.use_fast_scan(False)
+    assert rel_err(y2.detach().numpy(), y.detach().numpy()) < 1e-5
+    assert rel_err(x2.grad.numpy(), x.grad.numpy()) < 1e-4
+    for n, prm in layer.named_parameters():
+        assert rel_err(p[n].grad.numpy(), prm.grad.numpy()) < 1e-4, n
