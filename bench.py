@@ -53,7 +53,12 @@ for _i, (_c, _b, _d, _l, _n, _g) in enumerate(WORKLOADS["gm_live"], 1):
     WORKLOADS[f"gm_s{_i}"] = [(1, _b, _d, _l, _n, _g)]
     WORKLOADS[f"gm_s{_i}_g4"] = [(1, _b, 4 * _d, _l, _n, 4)]
 WORKLOADS["gm_s1_b64_512"] = [(1, 64, 64, 16384, 1, 4)]
+# small-batch points of the north-star shape (BASELINE config 1 runs batch 1): grid-fill regime
+WORKLOADS["vm_d192_b1"] = [(1, 1, 768, 3136, 16, 4)]
+WORKLOADS["vm_d192_b2"] = [(1, 2, 768, 3136, 16, 4)]
 DEFAULT_WORKLOAD = "vm_d192"
+# BASELINE config 4: the whole sweep goes into the driver-run line (other_workloads)
+SWEEP_CONFIG4 = ["vm_d96", "vm_d192", "vm_d384", "vm_d192_l80", "vm_d192_l112", "vm_d768_l112"]
 
 
 def alg_bytes(calls, esize=4):
@@ -117,16 +122,19 @@ class ClockSampler:
                 "samples": len(sm), "scope": scope, "reasons": reasons}
 
 
-def build_inputs(calls, device):
-    """One input set per distinct shape (reused across the `count` repetitions of that shape)."""
+def build_inputs(calls, device, on_device=False):
+    """One input set per distinct shape (reused across the `count` repetitions of that shape). Host tensors by default (the
+    end-to-end leg starts from pinned host memory); on_device=True draws the same recipe with the device generator (the
+    sweep's largest point is 11 GB of inputs)."""
     sets = []
-    gen = torch.Generator(device="cpu").manual_seed(0)
+    gen = torch.Generator(device=device if on_device else "cpu").manual_seed(0)
+    kw = dict(generator=gen, device=device if on_device else "cpu")
     for count, b, dt, L, n, g in calls:
-        A = (-0.5 * torch.rand(dt, n, generator=gen)).float()
-        inp = dict(A=A, B=torch.randn(b, g, n, L, generator=gen), C=torch.randn(b, g, n, L, generator=gen),
-                   D=torch.randn(dt, generator=gen), delta_bias=0.5 * torch.rand(dt, generator=gen),
-                   u=torch.randn(b, dt, L, generator=gen), delta=0.5 * torch.rand(b, dt, L, generator=gen),
-                   dout=torch.randn(b, dt, L, generator=gen))
+        A = (-0.5 * torch.rand(dt, n, **kw)).float()
+        inp = dict(A=A, B=torch.randn(b, g, n, L, **kw), C=torch.randn(b, g, n, L, **kw),
+                   D=torch.randn(dt, **kw), delta_bias=0.5 * torch.rand(dt, **kw),
+                   u=torch.randn(b, dt, L, **kw), delta=0.5 * torch.rand(b, dt, L, **kw),
+                   dout=torch.randn(b, dt, L, **kw))
         sets.append((count, inp))
     return sets
 
@@ -261,11 +269,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "selective-scan fwd+bwd algorithmic HBM GB/s", "value": round(value, 1), "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "calls_per_step": [list(c) for c in calls],
-                   "call_fields": ["count", "batch", "Dt=K*D", "L", "d_state", "groups"],
-                   "api": "selective_scan_cuda_core.fwd/bwd drop-in -> C ABI ss2d_scan_fwd/bwd",
-                   "l2_policy": "inputs larger than L2 (resident working set %.0f MB vs 126 MB L2)" % (resident / 1e6),
-                   "alg_bytes_fwd": fwd_b, "alg_bytes_bwd": bwd_b, "per_gpu_batch": calls[0][1]},
+        "config": our_config(args.workload),
         "frac_of_hbm_peak": round(value / world / peak, 4),
         "e2e": {"value": round(e2e_val, 1), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "pinned host buffers; every input copied in and every result copied out per step; %d batch chunks pipelined over %d streams (PCIe-bound)" % (args.e2e_chunks, args.e2e_streams)},
@@ -279,6 +283,9 @@ def run_ours(args, rank, world, local_rank):
                              "frac": round(ex2 / 4.6e12 * 1e3 / ms_per_step, 4)}
     if rank == 0 and world == 1 and not args.no_extras:
         line["other_workloads"] = other_workloads(core, device, peak, exclude=args.workload)
+    if not args.no_model:
+        # every rank takes part (batch-sharded data parallel, gradient all-reduce on NCCL); rank 0 reports
+        line["model"] = model_workloads(device, rank, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_port(args.workload)
     return line
@@ -310,27 +317,84 @@ def graph_time_ms(core, sets, iters=10, with_bwd=True):
 
 
 def other_workloads(core, device, peak, exclude):
-    """Context numbers in the same run (not the headline): the live GM-UNet regime (d_state = 1; the scan calls of one
-    224^2 batch-24 training step, and the 512^2 batch-64 stage-1 shape of config 5) and two more config-4 points.
-    Each is one CUDA-graph replay of fwd+bwd, median of 10."""
+    """Context numbers in the same run (not the headline), each one CUDA-graph replay of fwd+bwd, median of 10:
+    the whole BASELINE config-4 sweep, two small-batch points, the live GM-UNet regime (d_state = 1: the scan calls of one
+    224^2 batch-24 training step, one layer's grouped call, the 512^2 batch-64 stage-1 shape of config 5), and — when
+    baseline/_ref/ext holds it — the REFERENCE's own CUDA kernel recompiled for sm_100 on the same box and inputs."""
     out = []
-    for name in ("gm_live", "gm_s1_g4", "gm_s1_b64_512", "vm_d96", "vm_d384"):
-        if name == exclude:
-            continue
+    names = [n for n in SWEEP_CONFIG4 if n != exclude] + ["vm_d192_b1", "vm_d192_b2", "gm_live", "gm_s1_g4", "gm_s1_b64_512"]
+    ref_ext = None
+    try:
+        from harness import refmodel
+        ref_ext = refmodel.load_ref_cuda_ext()
+    except Exception:      # noqa: BLE001  (the baseline column is optional; never let it break the bench line)
+        ref_ext = None
+    ref_points = {"vm_d192", "gm_live", "gm_s1_b64_512"}
+    for name in names + ([exclude] if exclude in ref_points else []):
         calls = WORKLOADS[name]
-        sets = [(c, {k: v.to(device) for k, v in inp.items()}) for c, inp in build_inputs(calls, device)]
+        sets = build_inputs(calls, device, on_device=True)
         fb, bb = alg_bytes(calls)
-        ms_f = graph_time_ms(core, sets, with_bwd=False)
-        ms = graph_time_ms(core, sets, with_bwd=True)
-        rec = {"workload": name, "calls_per_step": [list(c) for c in calls], "fwd_ms": round(ms_f, 4),
-               "fwd_bwd_ms": round(ms, 4), "fwd_GBps": round(fb / ms_f / 1e6, 1), "fwd_bwd_GBps": round((fb + bb) / ms / 1e6, 1),
-               "frac_of_hbm_peak": round((fb + bb) / ms / 1e6 / peak, 4), "timing": "CUDA graph replay"}
-        if name == "gm_live":
-            rec["scan_only_slices_per_s"] = round(calls[0][1] / (ms * 1e-3), 1)
+        rec = {"workload": name, "calls_per_step": [list(c) for c in calls]}
+        if name != exclude:
+            ms_f = graph_time_ms(core, sets, with_bwd=False)
+            ms = graph_time_ms(core, sets, with_bwd=True)
+            rec.update({"fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms, 4), "fwd_GBps": round(fb / ms_f / 1e6, 1),
+                        "fwd_bwd_GBps": round((fb + bb) / ms / 1e6, 1), "frac_of_hbm_peak": round((fb + bb) / ms / 1e6 / peak, 4),
+                        "timing": "CUDA graph replay"})
+            if name == "gm_live":
+                rec["scan_only_slices_per_s"] = round(calls[0][1] / (ms * 1e-3), 1)
+        if ref_ext is not None and name in ref_points:
+            try:
+                rf = graph_time_ms(ref_ext, sets, with_bwd=False)
+                rfb = graph_time_ms(ref_ext, sets, with_bwd=True)
+                rec["ref_cuda_kernel"] = {"fwd_ms": round(rf, 4), "fwd_bwd_ms": round(rfb, 4),
+                                          "fwd_bwd_GBps": round((fb + bb) / rfb / 1e6, 1),
+                                          "what": "reference cus/ extension (setup.py flags) recompiled for sm_100, same inputs, CUDA graph replay"}
+                if "fwd_bwd_ms" in rec:
+                    rec["speedup_vs_ref_cuda_kernel"] = round(rfb / rec["fwd_bwd_ms"], 2)
+            except Exception as e:      # noqa: BLE001
+                rec["ref_cuda_kernel"] = {"error": str(e)[:200]}
         out.append(rec)
         del sets
         torch.cuda.empty_cache()
     return out
+
+
+def model_workloads(device, rank, world):
+    """BASELINE configs 2 / 3 / 5 (and 1 as the CPU column): the UNMODIFIED reference GM-UNet through the drop-in
+    (harness/workloads.py) — 224^2 batch-24 bf16 training slices/s (with the NCCL gradient all-reduce inside the timed
+    region when world > 1) and 512^2 batch-64 inference slices/s. Needs baseline/_ref (harness/install_ref.py)."""
+    try:
+        from harness import refmodel, workloads as W
+        if not refmodel.available():
+            return {"unavailable": "baseline/_ref not installed (harness/install_ref.py)"}
+        res = {}
+        for key, kw in (("train_224_b24_dropin_eager", dict(level="dropin", graphs=False)),
+                        ("train_224_b24_fused_graphs", dict(level="fused", graphs=True))):
+            try:
+                res[key] = W.train_bench(device, rank, world, per_gpu_batch=24, steps=5, warmup=3, **kw)
+            except Exception as e:      # noqa: BLE001
+                res[key] = {"error": repr(e)[:300]}
+        if world > 1:
+            try:
+                res["train_acdc_224_b24_fused_graphs"] = W.train_bench(device, rank, world, per_gpu_batch=24, num_classes=4, steps=5,
+                                                                        warmup=3, level="fused", graphs=True, weight_decay=1e-4)
+            except Exception as e:      # noqa: BLE001
+                res["train_acdc_224_b24_fused_graphs"] = {"error": repr(e)[:300]}
+        for key, kw in (("infer_512_b64_dropin_eager", dict(level="dropin", graphs=False)),
+                        ("infer_512_b64_fused_graphs", dict(level="fused", graphs=True))):
+            try:
+                res[key] = W.infer_bench(device, rank, world, per_gpu_batch=64, size=512, steps=3, warmup=2, **kw)
+            except Exception as e:      # noqa: BLE001
+                res[key] = {"error": repr(e)[:300]}
+        if rank == 0 and world == 1:
+            try:
+                res["cpu_reference_224_b1"] = W.cpu_reference_step()
+            except Exception as e:      # noqa: BLE001
+                res["cpu_reference_224_b1"] = {"error": repr(e)[:300]}
+        return res
+    except Exception as e:      # noqa: BLE001
+        return {"error": repr(e)[:300]}
 
 
 def cpu_baseline_port(workload, sample_batch=8, min_seconds=10.0):
@@ -362,16 +426,36 @@ def cpu_baseline_port(workload, sample_batch=8, min_seconds=10.0):
                       f"(Dt={dt}, L={L}, N={n}, G={g}), {reps} repetitions"}
 
 
+def our_config(workload):
+    """The `config` object of a bench line: identical in the `ours` and the `reference` arm (the driver compares them)."""
+    calls = WORKLOADS[workload]
+    fwd_b, bwd_b = alg_bytes(calls)
+    resident = sum(4 * (3 * b * dt * L + 2 * b * g * n * L + 2 * dt + dt * n) for c, b, dt, L, n, g in calls)
+    return {"workload": workload, "calls_per_step": [list(c) for c in calls],
+            "call_fields": ["count", "batch", "Dt=K*D", "L", "d_state", "groups"],
+            "api": "selective_scan_cuda_core.fwd/bwd drop-in -> C ABI ss2d_scan_fwd/bwd",
+            "l2_policy": "inputs larger than L2 (resident working set %.0f MB vs 126 MB L2)" % (resident / 1e6),
+            "alg_bytes_fwd": fwd_b, "alg_bytes_bwd": bwd_b, "per_gpu_batch": calls[0][1]}
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU path for the scan — its pure-PyTorch `selective_scan_ref`
     (kernels/selective_scan/test_selective_scan.py:168-234) forward + autograd backward, restated in
-    oracle/selective_scan_ref.py (the reference tree does not travel to the GPU box). Bounded sample per step."""
+    oracle/selective_scan_ref.py (the reference has no native CPU code to compile: DESIGN.md §4) — on all host threads.
+
+    Same workload and metric as the `ours` arm. One step processes a BOUNDED SAMPLE of it: a slab of whole channel rows of one
+    (batch, group) — a quarter of the group's rows with their shared B / C, the way the workload itself amortises B / C over
+    the rows of a group (a whole 192-row group takes 70 s per step in this implementation: its autograd backward moves
+    O(L^2) memory). The value is the workload's algorithmic bytes x (rows processed / rows in the workload) /
+    time, i.e. the speed at which this implementation would get through the SAME step."""
     from oracle.selective_scan_ref import selective_scan_ref
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     calls = WORKLOADS[args.workload]
     count, b, dt, L, n, g = max(calls, key=lambda c: c[0] * c[1] * c[2] * c[3] * c[4])
     dpg = dt // g
+    total_rows = sum(c * bb * dd for c, bb, dd, _, _, _ in calls)
+    fwd_all, bwd_all = alg_bytes(calls)
 
     def make(rows):
         gen = torch.Generator().manual_seed(0)
@@ -391,29 +475,33 @@ def run_reference(args):
         out = selective_scan_ref(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], None, t["delta_bias"], True)
         out.backward(t["dout"])
 
-    # calibrate on 2 rows, then size the sample so that (steps + warmup) steps take about two minutes
-    probe = make(2)
-    t0 = time.perf_counter(); one(probe); per_row = (time.perf_counter() - t0) / 2
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    rows = int(max(1, min(dpg, budget / max(per_row, 1e-6))))
+    # slab = a quarter of a group's rows (48 of 192 for vm_d192); shrink only if (steps + warmup) slabs would not fit ~4 min
+    rows = max(1, min(dpg, max(dpg // 4, 1)))
     t = make(rows)
-    for _ in range(args.warmup):
+    t0 = time.perf_counter(); one(t); first = time.perf_counter() - t0
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    while rows > 4 and first > budget:
+        rows = max(4, rows // 2)
+        t = make(rows)
+        t0 = time.perf_counter(); one(t); first = time.perf_counter() - t0
+    for _ in range(max(args.warmup - 1, 0)):
         one(t)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         one(t)
     sec = (time.perf_counter() - t0) / args.steps
-    fwd_b, bwd_b = alg_bytes([(1, 1, rows, L, n, 1)])
-    val = (fwd_b + bwd_b) / sec / 1e9
-    sample = (f"selective_scan_ref fwd + autograd bwd on {rows} of the {b * dt} (batch x channel) rows of '{args.workload}' "
-              f"(1 batch, 1 group, L={L}, N={n}) per step")
+    val = (fwd_all + bwd_all) * (rows / total_rows) / sec / 1e9
+    sample = (f"selective_scan_ref fwd + autograd bwd on a slab of {rows} whole rows (1 batch, 1 group of {dpg}, shared B/C, "
+              f"L={L}, N={n}) of the {total_rows} (batch x channel) rows of '{args.workload}' per step; bytes counted as the "
+              f"workload's algorithmic bytes x {rows}/{total_rows}")
     return {
         "impl": "reference", "metric": "selective-scan fwd+bwd algorithmic HBM GB/s", "value": round(val, 6),
         "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "calls_per_step": [list(c) for c in calls], "sample_rows": rows},
-        "cpu_baseline": {"value": round(val, 6), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": our_config(args.workload),
+        "cpu_baseline": {"value": round(val, 6), "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample,
+                         "sample_rows": rows, "seconds_per_slab": round(sec, 3),
+                         "whole_step_would_take_s": round(sec * total_rows / rows, 1)},
         "e2e": {"value": round(val, 6), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -430,6 +518,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8, help="batch chunks of the end-to-end leg (H2D / scan / D2H pipelining)")
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--no-extras", action="store_true", help="skip the other_workloads context block")
+    ap.add_argument("--no-model", action="store_true", help="skip the model-level (GM-UNet train / inference) block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

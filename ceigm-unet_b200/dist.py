@@ -76,7 +76,8 @@ class GradReducer:
     buckets of about `bucket_bytes`; every `p.grad` is a VIEW into its bucket (what DDP calls gradient_as_bucket_view), so
     no gather / scatter copy is needed. A post-accumulate hook counts the bucket's gradients in; when the last one lands
     the bucket's all-reduce (mean over ranks; NCCL's own stream, so it overlaps the rest of the backward) is launched.
-    `finish()` — called after `loss.backward()` — launches the buckets whose parameters took no part in this step (their
+    With `defer = True` the hooks only count and `finish()` launches everything (used when the backward itself is replayed
+    from a CUDA graph, where no hook runs). `finish()` — called after `loss.backward()` — launches the buckets whose parameters took no part in this step (their
     gradients are zeros) and waits for all of them. Use `zero_grad()` of this object instead of the optimizer's
     (`set_to_none=True` would detach the views).
     """
@@ -84,6 +85,7 @@ class GradReducer:
     def __init__(self, module: torch.nn.Module, bucket_bytes: int = 25 << 20):
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.avg = self.world > 1 and dist.get_backend() == "nccl"
+        self.defer = False      # True: hooks only count; every bucket is launched by finish() (CUDA-graph captured backward)
         params = [p for p in module.parameters() if p.requires_grad]
         groups, cur, cur_bytes, key = [], [], 0, None
         for p in reversed(params):
@@ -120,7 +122,7 @@ class GradReducer:
     def _ready(self, p) -> None:
         b = self.buckets[self._bucket_of[p]]
         b["pending"] -= 1
-        if b["pending"] == 0 and not b["launched"]:
+        if b["pending"] == 0 and not b["launched"] and not self.defer:
             self._launch(b)
 
     def finish(self) -> None:

@@ -1,0 +1,146 @@
+"""Whole-step CUDA graphs for the launch-bound live model.
+
+One GM-UNet training step is ~8 000 kernel launches of which most move a few MB: eager execution is bounded by the host
+(260 ms per batch-24 step on a B200, profiles/r2_model_bench.txt) while the GPU idles. Everything the step does is static in
+shape, so forward + loss + backward + optimizer are captured ONCE into a CUDA graph and replayed per batch:
+
+  * inputs live in static device buffers that each step's host batch is copied into (H2D stays inside the step);
+  * the one capture-hostile spot of the reference is `DySample.sample` (model/best_decoder.py:389-403): it builds its base
+    sampling grid with CPU tensor ops and uploads it on every call (a pageable H2D copy cannot be captured). The harness
+    rebinds that method to an arithmetically identical one that caches the uploaded grid per (H, W, dtype, device) — no
+    reference file is edited;
+  * AdamW runs with `capturable=True` (step counter on the device);
+  * with N > 1 ranks the forward/backward graph writes the gradients into the GradReducer's flat buckets, the NCCL
+    all-reduce runs between that graph and the optimizer graph.
+"""
+from __future__ import annotations
+
+import importlib
+
+import torch
+import torch.nn.functional as F
+
+from . import refmodel
+
+_GRID_CACHE = {}
+
+
+def _base_grid(H, W, dtype, device):
+    """coords / normalizer of DySample.sample (best_decoder.py:393-398), computed as there (CPU, float32) and cached."""
+    key = (H, W, dtype, str(device))
+    if key not in _GRID_CACHE:
+        ch = torch.arange(H) + torch.sin(torch.pi * torch.arange(1, H + 1, 1) / H)
+        cw = torch.arange(W) + torch.sin(torch.pi * torch.arange(1, W + 1, 1) / W)
+        coords = torch.stack(torch.meshgrid([cw, ch], indexing="ij")).transpose(1, 2).unsqueeze(1).unsqueeze(0).type(dtype).to(device)
+        normalizer = torch.tensor([W, H], dtype=dtype).view(1, 2, 1, 1, 1).to(device)
+        _GRID_CACHE[key] = (coords, normalizer)
+    return _GRID_CACHE[key]
+
+
+def _sample_cached(self, x, offset):
+    """Same computation as DySample.sample (best_decoder.py:389-403) with the base grid taken from the cache."""
+    B, _, H, W = offset.shape
+    offset = offset.view(B, 2, -1, H, W)
+    coords, normalizer = _base_grid(H, W, x.dtype, x.device)
+    coords = 2 * (coords + offset) / normalizer - 1
+    coords = F.pixel_shuffle(coords.contiguous().view(B, -1, H, W), self.scale).view(
+        B, 2, -1, self.scale * H, self.scale * W).permute(0, 2, 3, 4, 1).contiguous().flatten(0, 1)
+    return F.grid_sample(x.reshape(B * self.groups, -1, H, W), coords, mode="bilinear", align_corners=False,
+                         padding_mode="border").view(B, -1, self.scale * H, self.scale * W)
+
+
+def make_capturable() -> None:
+    """Rebind DySample.sample of the currently loaded reference package (after refmodel.load_reference)."""
+    bd = importlib.import_module("model.best_decoder")
+    bd.DySample.sample = _sample_cached
+
+
+class GraphedTrainStep:
+    """Same contract as workloads.TrainStep (`step(x_host, y_host) -> loss`), replayed from CUDA graphs."""
+
+    def __init__(self, net, batch, size, num_classes=9, lr=5e-4, weight_decay=1e-3, amp_dtype=torch.bfloat16,
+                 reducer=None, warmup_iters=3):
+        self.net = net.train()
+        self.device = next(net.parameters()).device
+        self.crit = refmodel.load_losses().DiceCELoss(ce_weight=0.4, dc_weight=0.6)
+        self.opt = torch.optim.AdamW(net.parameters(), lr=lr, weight_decay=weight_decay, eps=1e-8, betas=(0.9, 0.999),
+                                     capturable=True)
+        self.amp_dtype = amp_dtype
+        self.reducer = reducer
+        self.x = torch.zeros(batch, 3, size, size, device=self.device)
+        self.y = torch.zeros(batch, 1, size, size, device=self.device)
+        if reducer is not None:
+            reducer.defer = True          # hooks must not launch collectives while the backward is being captured
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):     # warm-up off the capture: cuDNN autotuning, lazy handles, optimizer state
+            for _ in range(warmup_iters):
+                self._fwd_bwd()
+                if reducer is not None:
+                    reducer.finish()
+                self.opt.step()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.g_fb = torch.cuda.CUDAGraph()
+        if reducer is None:
+            self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.g_fb):
+            self.loss = self._fwd_bwd()
+            if reducer is None:
+                self.opt.step()
+        self.g_opt = None
+        if reducer is not None:
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt):
+                self.opt.step()
+
+    def _fwd_bwd(self):
+        if self.reducer is not None:
+            self.reducer.zero_grad()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            pred = self.net(self.x)
+            loss = self.crit(pred.float(), self.y)
+        loss.backward()
+        return loss
+
+    def __call__(self, x_host, y_host) -> float:
+        self.x.copy_(x_host, non_blocking=True)
+        self.y.copy_(y_host, non_blocking=True)
+        self.g_fb.replay()
+        if self.reducer is not None:
+            self.reducer.finish()
+            self.g_opt.replay()
+        return float(self.loss.item())
+
+
+class GraphedInference:
+    """eval.py:72-77 per batch (forward, argmax of softmax) replayed from one CUDA graph."""
+
+    def __init__(self, net, batch, size, amp_dtype=torch.bfloat16, warmup_iters=2):
+        self.net = net.eval()
+        self.device = next(net.parameters()).device
+        self.amp_dtype = amp_dtype
+        self.x = torch.zeros(batch, 3, size, size, device=self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup_iters):
+                self._fwd()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.g = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.g):
+            self.labels = self._fwd()
+
+    def _fwd(self):
+        with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
+            logits = self.net(self.x)
+        return torch.argmax(torch.softmax(logits.float(), dim=1), dim=1).to(torch.uint8)
+
+    def __call__(self, x_host, out_host):
+        self.x.copy_(x_host, non_blocking=True)
+        self.g.replay()
+        out_host.copy_(self.labels, non_blocking=True)
+        return self.labels

@@ -77,8 +77,9 @@ def _sync_all(world, device):
 
 
 def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_classes=9, steps=5, warmup=3, level="dropin",
-                amp_dtype=torch.bfloat16, weight_decay=1e-3):
-    """-> dict with whole-job slices/s (max-over-ranks device time), loss trace, all-reduce share."""
+                amp_dtype=torch.bfloat16, weight_decay=1e-3, graphs=False):
+    """-> dict with whole-job slices/s (max-over-ranks device time), loss trace, all-reduce share.
+    graphs=True: the step is replayed from CUDA graphs (harness/graph_step.py)."""
     import ceigm_unet_b200 as pkg
     from ceigm_unet_b200 import dist as D
     net = build(num_classes, level, device)
@@ -86,7 +87,13 @@ def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_clas
     if world > 1:      # same initial weights on every rank, as DDP's constructor broadcast does
         for p in list(net.parameters()) + list(net.buffers()):
             torch.distributed.broadcast(p.data, src=0)
-    step = TrainStep(net, num_classes, amp_dtype=amp_dtype, reducer=reducer, weight_decay=weight_decay)
+    if graphs:
+        from . import graph_step
+        graph_step.make_capturable()
+        step = graph_step.GraphedTrainStep(net, per_gpu_batch, size, num_classes, amp_dtype=amp_dtype, reducer=reducer,
+                                           weight_decay=weight_decay)
+    else:
+        step = TrainStep(net, num_classes, amp_dtype=amp_dtype, reducer=reducer, weight_decay=weight_decay)
     x, y = synthetic_batch(per_gpu_batch, size, num_classes, seed=42 + rank)
     losses = []
     for _ in range(max(warmup, 3)):
@@ -117,14 +124,15 @@ def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_clas
         reducer.remove()
     out = {"slices_per_s": round(world * per_gpu_batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 2),
            "wall_ms_per_step": round(wall / steps * 1e3, 2), "per_gpu_batch": per_gpu_batch, "size": size,
-           "num_classes": num_classes, "level": level, "amp": str(amp_dtype).replace("torch.", "") if amp_dtype else "fp32",
+           "num_classes": num_classes, "level": level, "cuda_graphs": bool(graphs), "amp": str(amp_dtype).replace("torch.", "") if amp_dtype else "fp32",
            "steps": steps, "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5),
            "ss2d_launches_per_step": launches // steps,
            "h2d_bytes_per_step": x.numel() * 4 + y.numel() * 4, "d2h_bytes_per_step": 4,
            "optimizer": "AdamW lr 5e-4", "loss": "DiceCELoss(0.4, 0.6)"}
     if reducer is not None:
         out["allreduce"] = {"bytes": reducer.bytes, "buckets": len(reducer.buckets), "alone_ms": round(ar_ms, 3),
-                            "share_of_step_if_exposed": round(ar_ms / ms, 4), "backend": "nccl", "overlapped": True}
+                            "share_of_step_if_exposed": round(ar_ms / ms, 4), "backend": torch.distributed.get_backend(),
+                            "overlapped_with_backward": not graphs}
     del step, net
     torch.cuda.empty_cache()
     return out
@@ -132,13 +140,20 @@ def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_clas
 
 @torch.no_grad()
 def infer_bench(device, rank=0, world=1, *, per_gpu_batch=64, size=512, num_classes=9, steps=3, warmup=2, level="dropin",
-                amp_dtype=torch.bfloat16):
+                amp_dtype=torch.bfloat16, graphs=False):
     from ceigm_unet_b200 import dist as D
     net = build(num_classes, level, device).eval()
     x, _ = synthetic_batch(per_gpu_batch, size, num_classes, seed=7 + rank)
     out_host = torch.empty((per_gpu_batch, size, size), dtype=torch.uint8).pin_memory()
+    ginf = None
+    if graphs:
+        from . import graph_step
+        graph_step.make_capturable()
+        ginf = graph_step.GraphedInference(net, per_gpu_batch, size, amp_dtype=amp_dtype)
 
     def one():
+        if ginf is not None:
+            return ginf(x, out_host)
         xd = x.to(device, non_blocking=True)
         with torch.autocast(device.type if hasattr(device, "type") else "cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
             logits = net(xd)
@@ -156,7 +171,7 @@ def infer_bench(device, rank=0, world=1, *, per_gpu_batch=64, size=512, num_clas
     _sync_all(world, device)
     ms = D.max_over_ranks(e0.elapsed_time(e1), device) / steps
     res = {"slices_per_s": round(world * per_gpu_batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 2),
-           "per_gpu_batch": per_gpu_batch, "size": size, "level": level,
+           "per_gpu_batch": per_gpu_batch, "size": size, "level": level, "cuda_graphs": bool(graphs),
            "amp": str(amp_dtype).replace("torch.", "") if amp_dtype else "fp32", "steps": steps,
            "h2d_bytes_per_step": x.numel() * 4, "d2h_bytes_per_step": out_host.numel(),
            "peak_mem_GB": round(torch.cuda.max_memory_allocated(device) / 1e9, 2)}

@@ -183,7 +183,9 @@ def test_build_model_224_forward_backward(level):
     g = torch.Generator().manual_seed(42)
     x = torch.randn(1, 3, 224, 224, generator=g)
     label = torch.randint(0, 9, (1, 1, 224, 224), generator=g).float()
-    net_cpu.train()
+    # eval(): stochastic depth (DropPath, groupmamba.py:327) draws from the device's own RNG stream, so train() mode is not
+    # comparable across devices sample by sample; BatchNorm then uses its running statistics on both sides. Gradients still flow.
+    net_cpu.eval()
     out_cpu = net_cpu(x)
     loss_cpu = crit(out_cpu, label)
     loss_cpu.backward()
@@ -196,7 +198,7 @@ def test_build_model_224_forward_backward(level):
     net = m_gpu.build_model(in_channels=3, num_classes=9)
     missing, unexpected = net.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
-    net = net.cuda().train()
+    net = net.cuda().eval()
     import ceigm_unet_b200 as P
     P.launch_count(reset=True)
     out = net(x.cuda())
