@@ -16,6 +16,9 @@ cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_bwd_finalize(const ScanParams& p, float* dA, float* dD, float* dbias, cudaStream_t stream);
 cudaError_t scan_par_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_par_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
+bool scan_n1_fwd_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err);
+bool scan_n1_bwd_try(const ScanParams& p, float* dA, float* dD, float* dbias, int grads_zeroed, cudaStream_t stream,
+                     cudaError_t* err);
 
 // d_state == 1 (the live GM-UNet regime) runs the parallel-along-L kernels (scan_par.cu)
 static bool use_par(const ScanParams& p) { return p.N == 1 && p.A_ld == 1; }
@@ -170,8 +173,12 @@ int ss2d_scan_fwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
     p.ckpt = ckpt ? ckpt + ck_off : nullptr;
     p.last_state = last_state ? last_state + (d->last_state_interleaved ? 2 : 1) * n0 : nullptr;
     ck_off += round4(ckpt_floats_pass(d, n));
-    cudaError_t e = use_par(p) ? scan_par_fwd_dispatch(p, static_cast<cudaStream_t>(stream))
-                               : scan_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
+    cudaError_t e;
+    if (use_par(p)) {      // d_state = 1: lean fp32 kernels (scan_n1.cu) when eligible, else the generic parallel-along-L ones
+      if (!scan_n1_fwd_try(p, static_cast<cudaStream_t>(stream), &e)) e = scan_par_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
+    } else {
+      e = scan_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
+    }
     if (e != cudaSuccess) return cuda_fail(e);
     ++g_launches;
   }
@@ -225,11 +232,21 @@ int ss2d_scan_bwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
     p.dB = dB + (size_t)n0 * d->seqlen;
     p.dC = dC + (size_t)n0 * d->seqlen;
     ck_off += round4(ckpt_floats_pass(d, n));
-    cudaError_t e = use_par(p) ? scan_par_bwd_dispatch(p, st) : scan_bwd_dispatch(p, st);
+    cudaError_t e;
+    bool finalize = true;
+    if (use_par(p)) {
+      if (scan_n1_bwd_try(p, dA, dD, ddelta_bias, d->grads_prezeroed, st, &e)) finalize = !d->grads_prezeroed;
+      else e = scan_par_bwd_dispatch(p, st);
+    } else {
+      e = scan_bwd_dispatch(p, st);
+    }
     if (e != cudaSuccess) return cuda_fail(e);
-    e = scan_bwd_finalize(p, dA + n0, dD, ddelta_bias, st);
-    if (e != cudaSuccess) return cuda_fail(e);
-    g_launches += 2;
+    ++g_launches;
+    if (finalize) {
+      e = scan_bwd_finalize(p, dA + n0, dD, ddelta_bias, st);
+      if (e != cudaSuccess) return cuda_fail(e);
+      ++g_launches;
+    }
   }
   return SS2D_OK;
 }

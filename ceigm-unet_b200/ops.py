@@ -151,12 +151,23 @@ class ScanProblem:
             d.delta_batch_stride, d.delta_dim_stride = delta.stride(0), delta.stride(1)
         du = torch.empty((self.batch, self.dim, self.L), dtype=u.dtype, device=dev) if self.u_mod else torch.empty_like(u)
         ddelta = torch.empty_like(delta)
-        dA = torch.empty_like(self.A)
-        # one zero-fill launch for both accumulators (the live GM-UNet regime is launch-bound: 104 scan calls per step)
-        dBC = torch.zeros((2, self.batch, self.G, self.N, self.L), dtype=torch.float32, device=dev)
-        dB, dC = dBC[0], dBC[1]
-        dD = torch.empty_like(self.D) if self.D is not None else None
-        dbias = torch.empty_like(self.bias) if self.bias is not None else None
+        # one zero-fill launch for every accumulator (the live GM-UNet regime is launch-bound: 104 scan calls per step):
+        # dB | dC always; for d_state = 1 also dA | dD | ddelta_bias, which the lean kernel then adds into directly
+        nbc = self.batch * self.G * self.N * self.L
+        small = self.N == 1
+        extra = self.dim * (self.N + 2) if small else 0
+        zbuf = torch.zeros(2 * nbc + extra, dtype=torch.float32, device=dev)
+        dB, dC = zbuf[:nbc].view(self.batch, self.G, self.N, self.L), zbuf[nbc:2 * nbc].view(self.batch, self.G, self.N, self.L)
+        if small:
+            dA = zbuf[2 * nbc:2 * nbc + self.dim * self.N].view(self.dim, self.N)
+            dD = zbuf[2 * nbc + self.dim * self.N:2 * nbc + self.dim * (self.N + 1)] if self.D is not None else None
+            dbias = zbuf[2 * nbc + self.dim * (self.N + 1):] if self.bias is not None else None
+            d.grads_prezeroed = 1
+        else:
+            dA = torch.empty_like(self.A)
+            dD = torch.empty_like(self.D) if self.D is not None else None
+            dbias = torch.empty_like(self.bias) if self.bias is not None else None
+            d.grads_prezeroed = 0
         ckpt = self._ckpt_from_x(x)
         L = _lib.lib()
         ws_bytes = int(L.ss2d_scan_bwd_workspace_bytes(ctypes.byref(d), 1 if ckpt is not None else 0))

@@ -86,6 +86,10 @@ typedef struct ss2d_scan_desc {
   /* 1: last_state is (batch, dim, 2*dstate) with h in the ODD slots and 0 in the even ones — the layout of
    * the last chunk row of the reference's `x` output (read as x[:, :, -1, 1::2]). */
   int32_t last_state_interleaved;
+  /* Backward only. 1: dA, dD and ddelta_bias were ZEROED by the caller (together with dB / dC, e.g. one memset over one
+   * buffer) and may be accumulated into; the d_state = 1 path then adds its per-batch sums straight into them and the call is
+   * a single kernel. 0: they are fully overwritten (per-batch partials in `workspace` + a fixed-order finalize pass). */
+  int32_t grads_prezeroed;
 } ss2d_scan_desc;
 
 /* ---- forward -------------------------------------------------------------------------------
@@ -103,7 +107,7 @@ size_t ss2d_scan_ckpt_floats(const ss2d_scan_desc* desc);
 
 /* ---- backward ------------------------------------------------------------------------------
  * dout has out's dtype/strides; du, ddelta have u's / delta's dtype and strides.
- * dA (dim, dstate), dD (dim) or NULL, ddelta_bias (dim) or NULL: fp32, fully overwritten.
+ * dA (dim, dstate), dD (dim) or NULL, ddelta_bias (dim) or NULL: fp32, fully overwritten (see desc->grads_prezeroed).
  * dB, dC: fp32 (batch, group, dstate, L | H, W) contiguous accumulators that the caller has ZEROED
  *         (the reference does the same: torch::zeros_like(B, fp32), selective_scan.cpp:322-323); 16-byte aligned
  *         when L % 4 == 0 (they are then updated with 128-bit accesses), else SS2D_ERR_ALIGNMENT.

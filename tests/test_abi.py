@@ -59,7 +59,8 @@ def test_struct_layout_matches_header():
     # 11 int32 + 8 dirs + 12 int64 + 2 int32, 8-byte aligned: offsets must match the C struct
     assert _lib.ScanDesc.dirs.offset == 44
     assert _lib.ScanDesc.u_batch_stride.offset == 80
-    assert ctypes.sizeof(_lib.ScanDesc) == 80 + 12 * 8 + 8
+    assert _lib.ScanDesc.grads_prezeroed.offset == 80 + 12 * 8 + 8
+    assert ctypes.sizeof(_lib.ScanDesc) == 80 + 12 * 8 + 16      # 3 trailing int32 padded to the struct's 8-byte alignment
 
 
 def test_no_fallback_without_library(monkeypatch):
