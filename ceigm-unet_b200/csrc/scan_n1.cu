@@ -6,15 +6,21 @@
 //
 // Same algorithm as scan_par.cu — the scan is parallel ALONG L: a row is owned by seg x wpr threads, each scanning
 // P = 8 consecutive positions in registers; the (decay, state) aggregates are combined by a Kogge-Stone shuffle scan inside
-// the warp and one shared-memory hop between the warps of a row — but built for calls that move 2 ... 60 MB:
-//   * ONE code path. ncu on scan_par (profiles/r2_ncu_scan_par_small_shapes.txt) showed its 7 700-instruction bodies (generic
-//     dtype / direction / tail handling inlined next to the fast path) stalled on instruction fetch (`no_instruction` 19.7
-//     cycles per issue at the stage-3 shape): every warp runs the code exactly once. Here eligibility is decided on the
-//     host, the geometry (lanes per row, warps per row, rows per CTA) is a kernel ARGUMENT, and a body is ~10x smaller.
+// the warp, one shared-memory hop and a second shuffle scan over the warps of the row — but built for calls that move
+// 2 ... 60 MB, where scan_par lost to the reference kernel (profiles/r2_time_stages.txt):
+//   * ONE code path per launch. ncu on scan_par (profiles/r2_ncu_scan_par_small_shapes.txt) showed its 7 700-instruction
+//     bodies (generic dtype / direction / tail handling inlined next to the fast path) stalled on instruction fetch
+//     (`no_instruction` 19.7 cycles per issue at the stage-3 shape): every warp runs the code exactly once. Here eligibility
+//     is decided on the host and the geometry (lanes per row, warps per row, rows per CTA) is a kernel ARGUMENT.
 //   * the whole row in flight at once: up to 16 warps per row, so a 56^2 row is one pass (scan_par: two sequential chunks).
-//   * all loads of a thread (delta, u, B, C [, dout]) are issued before any arithmetic.
-//   * backward: dA / dD / d(delta_bias) are added straight into caller-zeroed accumulators (`grads_prezeroed`), so the
-//     call is memset + ONE kernel (scan_par: memset + kernel + finalize).
+//   * out-of-range positions are loaded as delta = -inf: softplus gives exactly 0 there, the state freezes, and no
+//     per-position bound check is left in the arithmetic.
+//   * backward (`scan_n1_bwd_rows_kernel`): a CTA walks SEVERAL rows of its group one after the other and keeps dB / dC in
+//     registers across them — the sum over the rows of a group costs nothing and is stored once (deterministic, no atomics
+//     when one CTA covers the group). The next row's delta / u / dout are in flight meanwhile: one elected thread per row
+//     lane streams them through a 2-stage shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier); row lanes
+//     synchronise on their own named barriers, so they drift apart and overlap. dA / dD / d(delta_bias) go into
+//     caller-zeroed accumulators (`grads_prezeroed`): the call is memset + ONE kernel (scan_par: memset, kernel, finalize).
 #include "common.cuh"
 #include "host_util.h"
 #include "scan_params.h"
@@ -27,46 +33,76 @@ constexpr int N1_MAX_WARPS = 16;    // warps per CTA
 struct N1Geom {
   int seg;       // lanes of one row inside a warp: 4, 8, 16 or 32
   int wpr;       // warps per row (1 when seg < 32)
-  int rt;        // rows per CTA
+  int rt;        // row lanes per CTA (rows processed concurrently)
+  int rseq;      // rows each lane walks one after the other (backward rows kernel; 1 otherwise)
   int lc;        // positions per chunk = seg * wpr * P
   int nchunks;   // ceil(L / lc)
 };
 
-template <bool VEC>
-__device__ __forceinline__ void n1_load(const float* __restrict__ row, int l0, int L, bool rev, float (&o)[N1_P]) {
+template <bool VEC, bool REV>
+__device__ __forceinline__ void n1_load(const float* __restrict__ row, int l0, int L, float fill, float (&o)[N1_P]) {
   if constexpr (VEC) {
 #pragma unroll
     for (int c = 0; c < N1_P; c += 4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (l0 + c < L) v = __ldg(reinterpret_cast<const float4*>(row + (rev ? L - 4 - (l0 + c) : l0 + c)));
-      o[c] = rev ? v.w : v.x; o[c + 1] = rev ? v.z : v.y; o[c + 2] = rev ? v.y : v.z; o[c + 3] = rev ? v.x : v.w;
+      float4 v = make_float4(fill, fill, fill, fill);
+      if (l0 + c < L) v = __ldg(reinterpret_cast<const float4*>(row + (REV ? L - 4 - (l0 + c) : l0 + c)));
+      o[c] = REV ? v.w : v.x; o[c + 1] = REV ? v.z : v.y; o[c + 2] = REV ? v.y : v.z; o[c + 3] = REV ? v.x : v.w;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < N1_P; ++i) o[i] = l0 + i < L ? __ldg(row + (rev ? L - 1 - (l0 + i) : l0 + i)) : 0.f;
+    for (int i = 0; i < N1_P; ++i) o[i] = l0 + i < L ? __ldg(row + (REV ? L - 1 - (l0 + i) : l0 + i)) : fill;
   }
 }
-template <bool VEC>
-__device__ __forceinline__ void n1_store(float* __restrict__ row, int l0, int L, bool rev, const float (&v)[N1_P]) {
+template <bool VEC, bool REV>
+__device__ __forceinline__ void n1_store(float* __restrict__ row, int l0, int L, const float (&v)[N1_P]) {
   if constexpr (VEC) {
 #pragma unroll
     for (int c = 0; c < N1_P; c += 4) {
       if (l0 + c < L) {
-        const float4 q = rev ? make_float4(v[c + 3], v[c + 2], v[c + 1], v[c]) : make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        *reinterpret_cast<float4*>(row + (rev ? L - 4 - (l0 + c) : l0 + c)) = q;
+        const float4 q = REV ? make_float4(v[c + 3], v[c + 2], v[c + 1], v[c]) : make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        *reinterpret_cast<float4*>(row + (REV ? L - 4 - (l0 + c) : l0 + c)) = q;
       }
     }
   } else {
 #pragma unroll
     for (int i = 0; i < N1_P; ++i)
-      if (l0 + i < L) row[rev ? L - 1 - (l0 + i) : l0 + i] = v[i];
+      if (l0 + i < L) row[REV ? L - 1 - (l0 + i) : l0 + i] = v[i];
+  }
+}
+// dB / dC of 8 positions: plain store when this CTA holds the whole sum, red.global otherwise
+template <bool VEC, bool REV>
+__device__ __forceinline__ void n1_emit(float* __restrict__ row, int l0, int L, const float (&v)[N1_P], bool plain) {
+  if constexpr (VEC) {
+#pragma unroll
+    for (int c = 0; c < N1_P; c += 4) {
+      if (l0 + c < L) {
+        float4* q4 = reinterpret_cast<float4*>(row + (REV ? L - 4 - (l0 + c) : l0 + c));
+        const float4 x = REV ? make_float4(v[c + 3], v[c + 2], v[c + 1], v[c]) : make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        if (plain) *q4 = x;
+        else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q4), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N1_P; ++i) {
+      if (l0 + i < L) {
+        float* q1 = row + (REV ? L - 1 - (l0 + i) : l0 + i);
+        if (plain) *q1 = v[i];
+        else atomicAdd(q1, v[i]);
+      }
+    }
   }
 }
 
+__device__ __forceinline__ void n1_bar(int id, int nthreads) {      // named barrier of one row lane (id 1 ... 15)
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Exclusive carry for every thread of a row + the row total, given the thread's own affine map h -> Pm h + Hm.
-// UP: composition of the EARLIER threads (prefix); !UP: of the LATER threads (suffix).
+// UP: composition of the EARLIER threads (prefix); !UP: of the LATER threads (suffix). Rows of wpr > 1 warps synchronise
+// on the named barrier `bar_id` (their own: row lanes of one CTA do not wait for each other).
 template <bool UP>
-__device__ __forceinline__ void n1_row_exclusive(float Pm, float Hm, int lane, int lis, int seg, int wir, int wpr, int slot0,
+__device__ __forceinline__ void n1_row_exclusive(float Pm, float Hm, int lane, int lis, int seg, int wir, int wpr, int bar_id,
                                                  float (*s_agg)[2], float& Pex, float& Hex, float& Ptot, float& Htot) {
   for (int off = 1; off < seg; off <<= 1) {
     const float Pp = UP ? __shfl_up_sync(0xffffffffu, Pm, off) : __shfl_down_sync(0xffffffffu, Pm, off);
@@ -83,22 +119,29 @@ __device__ __forceinline__ void n1_row_exclusive(float Pm, float Hm, int lane, i
     Htot = __shfl_sync(0xffffffffu, Hm, src);
     Pex = Pe; Hex = He;
   } else {
-    if (UP ? (lis == 31) : (lis == 0)) { s_agg[slot0 + wir][0] = Pm; s_agg[slot0 + wir][1] = Hm; }
-    __syncthreads();
-    float Pq = 1.f, Hq = 0.f;
-    Ptot = 1.f; Htot = 0.f;
-    for (int i = 0; i < wpr; ++i) {
-      const int w = UP ? i : wpr - 1 - i;
-      const float Pw = s_agg[slot0 + w][0], Hw = s_agg[slot0 + w][1];
-      if (UP ? (w < wir) : (w > wir)) { Hq = fmaf(Pw, Hq, Hw); Pq *= Pw; }
-      Htot = fmaf(Pw, Htot, Hw); Ptot *= Pw;
+    // the warp's aggregate goes to shared memory; afterwards every warp scans the row's <= 16 aggregates with shuffles
+    if (UP ? (lis == 31) : (lis == 0)) { s_agg[wir][0] = Pm; s_agg[wir][1] = Hm; }
+    n1_bar(bar_id, wpr * 32);
+    float Pw = 1.f, Hw = 0.f;
+    if (lane < wpr) { Pw = s_agg[lane][0]; Hw = s_agg[lane][1]; }
+#pragma unroll
+    for (int off = 1; off < N1_MAX_WARPS; off <<= 1) {
+      const float Pp = UP ? __shfl_up_sync(0xffffffffu, Pw, off) : __shfl_down_sync(0xffffffffu, Pw, off);
+      const float Hp = UP ? __shfl_up_sync(0xffffffffu, Hw, off) : __shfl_down_sync(0xffffffffu, Hw, off);
+      const bool take = UP ? (lane >= off) : (lane + off < 32);
+      if (take) { Hw = fmaf(Pw, Hp, Hw); Pw *= Pp; }       // lanes >= wpr hold the identity: harmless in either direction
     }
+    const int nb = UP ? wir - 1 : wir + 1;                 // neighbour warp whose inclusive value is this warp's carry-in
+    float Pq = __shfl_sync(0xffffffffu, Pw, nb & 31), Hq = __shfl_sync(0xffffffffu, Hw, nb & 31);
+    if (UP ? (wir == 0) : (wir == wpr - 1)) { Pq = 1.f; Hq = 0.f; }
+    Ptot = __shfl_sync(0xffffffffu, Pw, UP ? wpr - 1 : 0);
+    Htot = __shfl_sync(0xffffffffu, Hw, UP ? wpr - 1 : 0);
     Hex = fmaf(Pe, Hq, He); Pex = Pe * Pq;
   }
 }
 
 struct N1Thread {
-  int r, wir, lis, t;     // row inside the CTA, warp inside the row, lane inside the row segment, thread index along the row
+  int r, wir, lis, t;     // row lane inside the CTA, warp inside the row, lane inside the row segment, thread index along the row
 };
 __device__ __forceinline__ N1Thread n1_thread(const N1Geom gm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,8 +152,15 @@ __device__ __forceinline__ N1Thread n1_thread(const N1Geom gm) {
   return q;
 }
 
+// activated delta: softplus(raw + bias) with threshold 20, or raw + bias; out-of-range positions (raw = -inf) give 0
+template <bool SP>
+__device__ __forceinline__ float n1_act(float raw, float bias, bool in_range) {
+  if constexpr (SP) return softplus20(raw + bias);
+  return in_range ? raw + bias : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------- forward
-template <bool VEC>
+template <bool VEC, bool SP>
 __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_fwd_kernel(const ScanParams p, const N1Geom gm) {
   __shared__ float s_agg[2][N1_MAX_WARPS][2];
   const N1Thread q = n1_thread(gm);
@@ -120,8 +170,6 @@ __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_fwd_kernel(const Sc
   const bool valid = q.r < gm.rt && row < p.dpg;
   const int d = g * p.dpg + (valid ? row : 0);
   const int L = valid ? p.L : 0;                         // invalid rows: every load / store predicated off
-  const bool rev = p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3;
-
   const float A2 = p.A[d] * kLog2e;
   const float bias = p.bias ? p.bias[d] : 0.f;
   const float Dd = p.Dv ? p.Dv[d] : 0.f;
@@ -130,55 +178,152 @@ __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_fwd_kernel(const Sc
   const float* fB = static_cast<const float*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
   const float* fC = static_cast<const float*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
   float* fo = p.out ? static_cast<float*>(p.out) + (int64_t)b * p.out_bs + (int64_t)d * p.out_ds : nullptr;
+  const float dfill = SP ? -INFINITY : 0.f;
 
-  float h_carry = 0.f;
-  for (int c = 0; c < gm.nchunks; ++c) {
-    const int l0 = c * gm.lc + q.t * N1_P;
-    float dl[N1_P], uu[N1_P], bb[N1_P], cc[N1_P];
-    n1_load<VEC>(fd, l0, L, rev, dl);
-    n1_load<VEC>(fu, l0, L, rev, uu);
-    n1_load<VEC>(fB, l0, L, rev, bb);
-    n1_load<VEC>(fC, l0, L, rev, cc);
-    // local scan from h = 0: hl = local state, pc = cumulative decay; beyond the end of the row the state is frozen
-    float hl[N1_P], pc[N1_P];
-    float h = 0.f, pm = 1.f;
+  auto body = [&](auto REVT) {
+    constexpr bool REV = decltype(REVT)::value;
+    float h_carry = 0.f;
+    for (int c = 0; c < gm.nchunks; ++c) {
+      const int l0 = c * gm.lc + q.t * N1_P;
+      float dl[N1_P], uu[N1_P], bb[N1_P], cc[N1_P];
+      n1_load<VEC, REV>(fd, l0, L, dfill, dl);
+      n1_load<VEC, REV>(fu, l0, L, 0.f, uu);
+      n1_load<VEC, REV>(fB, l0, L, 0.f, bb);
+      n1_load<VEC, REV>(fC, l0, L, 0.f, cc);
+      // local scan from h = 0: hl = local state, pc = cumulative decay; beyond the end of the row the state is frozen
+      float hl[N1_P], pc[N1_P];
+      float h = 0.f, pm = 1.f;
 #pragma unroll
-    for (int i = 0; i < N1_P; ++i) {
-      float x = dl[i] + bias;
-      if (p.softplus) x = softplus20(x);
-      if (l0 + i >= L) x = 0.f;
-      const float a = ex2f(x * A2);
-      h = fmaf(a, h, x * uu[i] * bb[i]);
-      pm *= a;
-      hl[i] = h; pc[i] = pm;
-    }
-    float Pex, Hex, Ptot, Htot;
-    n1_row_exclusive<true>(pm, h, lane, q.lis, gm.seg, q.wir, gm.wpr, q.r * gm.wpr, s_agg[c & 1], Pex, Hex, Ptot, Htot);
-    const float h_in = fmaf(Pex, h_carry, Hex);             // state entering this thread's first position
-    if (fo) {
-      float y[N1_P];
+      for (int i = 0; i < N1_P; ++i) {
+        const float x = n1_act<SP>(dl[i], bias, l0 + i < L);
+        const float a = ex2f(x * A2);
+        h = fmaf(a, h, x * uu[i] * bb[i]);
+        pm *= a;
+        hl[i] = h; pc[i] = pm;
+      }
+      float Pex, Hex, Ptot, Htot;
+      n1_row_exclusive<true>(pm, h, lane, q.lis, gm.seg, q.wir, gm.wpr, 1 + q.r, s_agg[c & 1] + q.r * gm.wpr, Pex, Hex, Ptot, Htot);
+      const float h_in = fmaf(Pex, h_carry, Hex);             // state entering this thread's first position
+      if (fo) {
+        float y[N1_P];
 #pragma unroll
-      for (int i = 0; i < N1_P; ++i) y[i] = fmaf(cc[i], fmaf(pc[i], h_in, hl[i]), Dd * uu[i]);
-      n1_store<VEC>(fo, l0, L, rev, y);
+        for (int i = 0; i < N1_P; ++i) y[i] = fmaf(cc[i], fmaf(pc[i], h_in, hl[i]), Dd * uu[i]);
+        n1_store<VEC, REV>(fo, l0, L, y);
+      }
+      // chunk checkpoint every SS2D_CHUNK positions: the thread whose last position closes a chunk owns it
+      if (p.ckpt != nullptr && (q.t & 3) == 3 && l0 < L) {
+        const int idx = (l0 + N1_P) / SS2D_CHUNK - 1;
+        if (idx < p.nck) p.ckpt[((int64_t)b * p.dim + d) * p.nck + idx] = fmaf(pc[N1_P - 1], h_in, hl[N1_P - 1]);
+      }
+      h_carry = fmaf(Ptot, h_carry, Htot);
     }
-    // chunk checkpoint every SS2D_CHUNK positions: the thread whose last position closes a chunk owns it
-    if (p.ckpt != nullptr && valid && ((l0 + N1_P) % SS2D_CHUNK) == 0) {
-      const int idx = (l0 + N1_P) / SS2D_CHUNK - 1;
-      if (idx < p.nck) p.ckpt[((int64_t)b * p.dim + d) * p.nck + idx] = fmaf(pc[N1_P - 1], h_in, hl[N1_P - 1]);
+    if (p.last_state != nullptr && valid && q.t == 0) {
+      const int64_t slot = (int64_t)b * p.dim + d;
+      if (p.last_il) { p.last_state[2 * slot] = 0.f; p.last_state[2 * slot + 1] = h_carry; }
+      else p.last_state[slot] = h_carry;
     }
-    h_carry = fmaf(Ptot, h_carry, Htot);
+  };
+  if (p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3) body(std::true_type{}); else body(std::false_type{});
+}
+
+// ------------------------------------------------------------------------------------------------- backward, shared math
+// One row segment of 8 positions per thread: forward recompute, row-wide prefix / suffix scans, adjoint. On exit dub / ddl
+// hold du / d(delta); dBv / dCv are ADDED to (accumulate over the rows a thread walks); accA / accD / accb likewise.
+template <bool SP>
+__device__ __forceinline__ void n1_bwd_segment(float (&dl)[N1_P], const float (&uu)[N1_P], const float (&dy)[N1_P],
+                                               const float (&bb)[N1_P], const float (&cB)[N1_P], int l0, int L, float A1,
+                                               float bias, float Dd, float h_chunk, float& t_carry, int lane, const N1Thread q,
+                                               const N1Geom gm, float (*s_agg0)[2], float (*s_agg1)[2], float (&dub)[N1_P],
+                                               float (&ddl)[N1_P], float (&dBv)[N1_P], float (&dCv)[N1_P], float& accA,
+                                               float& accD, float& accb) {
+  const float A2 = A1 * kLog2e;
+  float a[N1_P], hh[N1_P], cc[N1_P];
+  float h = 0.f, pm = 1.f;
+#pragma unroll
+  for (int i = 0; i < N1_P; ++i) {
+    const float x = n1_act<SP>(dl[i], bias, l0 + i < L);
+    dl[i] = x;
+    a[i] = ex2f(x * A2);
+    h = fmaf(a[i], h, x * uu[i] * bb[i]);
+    pm *= a[i];
+    hh[i] = h;
+    cc[i] = cB[i] * dy[i];                                     // c_l = C_l dy_l
   }
-  if (p.last_state != nullptr && valid && q.t == 0) {
-    const int64_t slot = (int64_t)b * p.dim + d;
-    if (p.last_il) { p.last_state[2 * slot] = 0.f; p.last_state[2 * slot + 1] = h_carry; }
-    else p.last_state[slot] = h_carry;
+  float Pex, Hex, Ptot, Htot;
+  n1_row_exclusive<true>(pm, h, lane, q.lis, gm.seg, q.wir, gm.wpr, 1 + q.r, s_agg0, Pex, Hex, Ptot, Htot);
+  const float h_in = fmaf(Pex, h_chunk, Hex);                  // true state before this thread's first position
+  {
+    float pc = 1.f;
+#pragma unroll
+    for (int i = 0; i < N1_P; ++i) { pc *= a[i]; hh[i] = fmaf(pc, h_in, hh[i]); }
+  }
+  // reverse aggregate: t_l = a_l (c_l + t_(l+1)) as an affine map of the t entering from the right
+  float tq = 0.f, qm = 1.f;
+#pragma unroll
+  for (int i = N1_P - 1; i >= 0; --i) { tq = a[i] * (cc[i] + tq); qm *= a[i]; }
+  float Qex, Tex, Qtot, Ttot;
+  n1_row_exclusive<false>(qm, tq, lane, q.lis, gm.seg, q.wir, gm.wpr, 1 + q.r, s_agg1, Qex, Tex, Qtot, Ttot);
+  float t_next = fmaf(Qex, t_carry, Tex);                      // t of the position right after this thread's last one
+#pragma unroll
+  for (int i = N1_P - 1; i >= 0; --i) {
+    const float gi = cc[i] + t_next;                           // g_i = C_i dy_i + a_(i+1) g_(i+1)
+    const float ti = a[i] * gi;
+    t_next = ti;
+    const float hprev = i > 0 ? hh[i - 1] : h_in;
+    const float sB = gi * bb[i];
+    const float w = ti * hprev;
+    float dd = fmaf(uu[i], sB, w * A1);
+    if constexpr (SP) {      // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
+      const float de = dl[i];
+      dd *= de < 0.015625f ? de * (1.f - de * (0.5f - de * 0.16666667f)) : 1.f - ex2f(-de * kLog2e);
+    }
+    dub[i] = fmaf(Dd, dy[i], dl[i] * sB);
+    ddl[i] = dd;                                               // 0 beyond the row: u = dout = 0 there and t has not started
+    dBv[i] = fmaf(gi * dl[i], uu[i], dBv[i]);
+    dCv[i] = fmaf(dy[i], hh[i], dCv[i]);
+    accA = fmaf(w, dl[i], accA);
+    accD = fmaf(dy[i], uu[i], accD);
+    accb += dd;
+  }
+  t_carry = fmaf(Qtot, t_carry, Ttot);
+}
+
+// sum over the seg x wpr threads of a row; result valid in the thread with q.t == 0
+__device__ __forceinline__ void n1_row_sum3(float& x, float& y, float& z, int lane, const N1Thread q, const N1Geom gm,
+                                            float (*s_red)[3], int bar_id) {
+  for (int off = gm.seg >> 1; off >= 1; off >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, off);
+    y += __shfl_xor_sync(0xffffffffu, y, off);
+    z += __shfl_xor_sync(0xffffffffu, z, off);
+  }
+  if (gm.wpr > 1) {
+    if (lane == 0) { s_red[q.wir][0] = x; s_red[q.wir][1] = y; s_red[q.wir][2] = z; }
+    n1_bar(bar_id, gm.wpr * 32);
+    if (q.t == 0) {
+      x = y = z = 0.f;
+      for (int w = 0; w < gm.wpr; ++w) { x += s_red[w][0]; y += s_red[w][1]; z += s_red[w][2]; }
+    }
+    n1_bar(bar_id, gm.wpr * 32);        // s_red is reused by the next row
   }
 }
 
-// ------------------------------------------------------------------------------------------------- backward
-// grads_zeroed != 0: dA / dD / d(delta_bias) are caller-zeroed accumulators (p.part unused); else per-(batch, channel)
-// partials go to p.part and scan_bwd_finalize sums them.
-template <bool VEC>
+__device__ __forceinline__ void n1_emit_row_grads(const ScanParams& p, int b, int d, float accA, float accD, float accb,
+                                                  float* dA, float* dD, float* dbias, int grads_zeroed) {
+  if (grads_zeroed) {
+    atomicAdd(dA + d, accA);
+    if (dD) atomicAdd(dD + d, accD);
+    if (dbias) atomicAdd(dbias + d, accb);
+  } else {
+    float* dst = p.part + ((int64_t)b * p.dim + d) * 3;
+    dst[0] = accA; dst[1] = accD; dst[2] = accb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- backward, one row per lane
+// Any L (rows longer than 16 warps x 256 positions are walked in chunks, last to first, from the forward's checkpoints), any
+// alignment. grads_zeroed != 0: dA / dD / d(delta_bias) are caller-zeroed accumulators; else per-(batch, channel) partials
+// go to p.part and scan_bwd_finalize sums them.
+template <bool VEC, bool SP>
 __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_bwd_kernel(const ScanParams p, const N1Geom gm, float* __restrict__ dA,
                                                                       float* __restrict__ dD, float* __restrict__ dbias,
                                                                       int grads_zeroed) {
@@ -192,11 +337,8 @@ __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_bwd_kernel(const Sc
   const bool valid = q.r < gm.rt && row < p.dpg;
   const int d = g * p.dpg + (valid ? row : 0);
   const int L = valid ? p.L : 0;
-  const bool rev = p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3;
-  const bool single_cta_group = gridDim.x == 1;
-
+  const bool plain = gridDim.x == 1;
   const float A1 = p.A[d];
-  const float A2 = A1 * kLog2e;
   const float bias = p.bias ? p.bias[d] : 0.f;
   const float Dd = p.Dv ? p.Dv[d] : 0.f;
   const int u_ch = p.u_mod > 0 ? d % p.u_mod : d;
@@ -209,175 +351,199 @@ __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_bwd_kernel(const Sc
   float* fdd = static_cast<float*>(p.ddelta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
   float* dBrow = p.dB + (int64_t)(b * p.G + g) * p.L;
   float* dCrow = p.dC + (int64_t)(b * p.G + g) * p.L;
+  const float dfill = SP ? -INFINITY : 0.f;
 
-  float t_carry = 0.f;          // a_l g_l of the first position of the chunk after this one
-  float accA = 0.f, accD = 0.f, accb = 0.f;
-  for (int c = gm.nchunks - 1; c >= 0; --c) {
-    const int l0 = c * gm.lc + q.t * N1_P;
-    float dl[N1_P], uu[N1_P], bb[N1_P], cc[N1_P], dy[N1_P];
-    n1_load<VEC>(fd, l0, L, rev, dl);
-    n1_load<VEC>(fu, l0, L, rev, uu);
-    n1_load<VEC>(fy, l0, L, rev, dy);
-    n1_load<VEC>(fB, l0, L, rev, bb);
-    n1_load<VEC>(fC, l0, L, rev, cc);
-    // state entering the chunk: checkpoint written by the forward at the end of the previous SS2D_CHUNK block
-    const float h_chunk = (c > 0 && valid) ? __ldg(p.ckpt_in + ((int64_t)b * p.dim + d) * p.nck + (c * gm.lc) / SS2D_CHUNK - 1) : 0.f;
-    // ---- forward recompute: a, local h, decay products ----
-    float a[N1_P], hh[N1_P];
-    float h = 0.f, pm = 1.f;
+  auto body = [&](auto REVT) {
+    constexpr bool REV = decltype(REVT)::value;
+    float t_carry = 0.f;          // a_l g_l of the first position of the chunk after this one
+    float accA = 0.f, accD = 0.f, accb = 0.f;
+    for (int c = gm.nchunks - 1; c >= 0; --c) {
+      const int l0 = c * gm.lc + q.t * N1_P;
+      float dl[N1_P], uu[N1_P], bb[N1_P], cc[N1_P], dy[N1_P];
+      n1_load<VEC, REV>(fd, l0, L, dfill, dl);
+      n1_load<VEC, REV>(fu, l0, L, 0.f, uu);
+      n1_load<VEC, REV>(fy, l0, L, 0.f, dy);
+      n1_load<VEC, REV>(fB, l0, L, 0.f, bb);
+      n1_load<VEC, REV>(fC, l0, L, 0.f, cc);
+      // state entering the chunk: checkpoint written by the forward at the end of the previous SS2D_CHUNK block
+      const float h_chunk = (c > 0 && valid) ? __ldg(p.ckpt_in + ((int64_t)b * p.dim + d) * p.nck + (c * gm.lc) / SS2D_CHUNK - 1) : 0.f;
+      float dub[N1_P], ddl[N1_P], dBv[N1_P], dCv[N1_P];
 #pragma unroll
-    for (int i = 0; i < N1_P; ++i) {
-      float x = dl[i] + bias;
-      if (p.softplus) x = softplus20(x);
-      if (l0 + i >= L) x = 0.f;
-      dl[i] = x;
-      a[i] = ex2f(x * A2);
-      h = fmaf(a[i], h, x * uu[i] * bb[i]);
-      pm *= a[i];
-      hh[i] = h;
-      cc[i] *= dy[i];                                        // c_l = C_l dy_l
-    }
-    float Pex, Hex, Ptot, Htot;
-    n1_row_exclusive<true>(pm, h, lane, q.lis, gm.seg, q.wir, gm.wpr, q.r * gm.wpr, s_agg[0], Pex, Hex, Ptot, Htot);
-    const float h_in = fmaf(Pex, h_chunk, Hex);              // true state before this thread's first position
-    {
-      float pc = 1.f;
-#pragma unroll
-      for (int i = 0; i < N1_P; ++i) { pc *= a[i]; hh[i] = fmaf(pc, h_in, hh[i]); }
-    }
-    // ---- reverse: t_l = a_l (c_l + t_(l+1)); g_l = c_l + t_(l+1) ----
-    float tl[N1_P];
-    float tq = 0.f, qm = 1.f;
-#pragma unroll
-    for (int i = N1_P - 1; i >= 0; --i) { tq = a[i] * (cc[i] + tq); qm *= a[i]; tl[i] = tq; }
-    float Qex, Tex, Qtot, Ttot;
-    n1_row_exclusive<false>(qm, tq, lane, q.lis, gm.seg, q.wir, gm.wpr, q.r * gm.wpr, s_agg[1], Qex, Tex, Qtot, Ttot);
-    const float t_in = fmaf(Qex, t_carry, Tex);              // t of the position right after this thread's last one
-    float dub[N1_P], ddl[N1_P], dBv[N1_P], dCv[N1_P];
-    {
-      float qc = 1.f, t_next = t_in;
-#pragma unroll
-      for (int i = N1_P - 1; i >= 0; --i) {
-        qc *= a[i];
-        const float ti = fmaf(qc, t_in, tl[i]);              // true t_i
-        const float gi = cc[i] + t_next;                     // true g_i
-        t_next = ti;
-        const float hprev = i > 0 ? hh[i - 1] : h_in;
-        const float sB = gi * bb[i];
-        const float w = ti * hprev;
-        float dd = fmaf(uu[i], sB, w * A1);
-        if (p.softplus) {      // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
-          const float de = dl[i];
-          dd *= de < 0.015625f ? de * (1.f - de * (0.5f - de * 0.16666667f)) : 1.f - ex2f(-de * kLog2e);
+      for (int i = 0; i < N1_P; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+      n1_bwd_segment<SP>(dl, uu, dy, bb, cc, l0, L, A1, bias, Dd, h_chunk, t_carry, lane, q, gm, s_agg[0] + q.r * gm.wpr,
+                         s_agg[1] + q.r * gm.wpr, dub, ddl, dBv, dCv, accA, accD, accb);
+      n1_store<VEC, REV>(fdu, l0, L, dub);
+      n1_store<VEC, REV>(fdd, l0, L, ddl);
+      // ---- dB / dC: summed over the rows of this CTA, then one store (CTA = whole group) or reduction per 4 positions ----
+      if (gm.rt == 1) {
+        n1_emit<VEC, REV>(dBrow, l0, L, dBv, plain);
+        n1_emit<VEC, REV>(dCrow, l0, L, dCv, plain);
+      } else {
+        float* slabB = s_slab + (size_t)q.r * gm.lc + q.t * N1_P;
+        float* slabC = slabB + (size_t)gm.rt * gm.lc;
+        if (q.r < gm.rt) {
+          *reinterpret_cast<float4*>(slabB) = make_float4(dBv[0], dBv[1], dBv[2], dBv[3]);
+          *reinterpret_cast<float4*>(slabB + 4) = make_float4(dBv[4], dBv[5], dBv[6], dBv[7]);
+          *reinterpret_cast<float4*>(slabC) = make_float4(dCv[0], dCv[1], dCv[2], dCv[3]);
+          *reinterpret_cast<float4*>(slabC + 4) = make_float4(dCv[4], dCv[5], dCv[6], dCv[7]);
         }
-        if (l0 + i >= L) dd = 0.f;
-        dub[i] = fmaf(Dd, dy[i], dl[i] * sB);
-        ddl[i] = dd;
-        dBv[i] = gi * dl[i] * uu[i];
-        dCv[i] = dy[i] * hh[i];
-        accA = fmaf(w, dl[i], accA);
-        accD = fmaf(dy[i], uu[i], accD);
-        accb += dd;
+        __syncthreads();
+        const int L0 = p.L, c8 = gm.lc / N1_P;
+        for (int i = threadIdx.x; i < 2 * c8; i += blockDim.x) {
+          const int which = i / c8, pos = (i - which * c8) * N1_P;
+          const int l = c * gm.lc + pos;
+          if (l >= L0) continue;
+          float acc[N1_P];
+#pragma unroll
+          for (int e = 0; e < N1_P; ++e) acc[e] = 0.f;
+          const float* col = s_slab + (size_t)which * gm.rt * gm.lc + pos;
+          for (int rr = 0; rr < gm.rt; ++rr) {
+            const float4 v0 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc);
+            const float4 v1 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc + 4);
+            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+            acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+          }
+          n1_emit<VEC, REV>(which == 0 ? dBrow : dCrow, l, L0, acc, plain);
+        }
+        __syncthreads();
       }
     }
-    n1_store<VEC>(fdu, l0, L, rev, dub);
-    n1_store<VEC>(fdd, l0, L, rev, ddl);
-    t_carry = fmaf(Qtot, t_carry, Ttot);
-    // ---- dB / dC: summed over the rows of this CTA, then one store (CTA = whole group) or reduction per 4 positions ----
-    if (gm.rt == 1) {
-      if (valid) {
+    n1_row_sum3(accA, accD, accb, lane, q, gm, s_red + q.r * gm.wpr, 1 + q.r);
+    if (q.t == 0 && valid) n1_emit_row_grads(p, b, d, accA, accD, accb, dA, dD, dbias, grads_zeroed);
+  };
+  if (p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3) body(std::true_type{}); else body(std::false_type{});
+}
+
+// ------------------------------------------------------------------------------------------------- backward, rows walked per lane
+// Single-pass rows (L <= 16 warps x 256), 16-byte aligned: see the header comment. Shared memory: per row lane a 2-stage
+// ring of [delta | u | dout] rows (TMA bulk copies), reused at the end as the slab that sums dB / dC over the row lanes.
+template <bool SP>
+__global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_bwd_rows_kernel(const ScanParams p, const N1Geom gm, float* __restrict__ dA,
+                                                                           float* __restrict__ dD, float* __restrict__ dbias,
+                                                                           int grads_zeroed) {
+  extern __shared__ __align__(128) float s_ring[];         // [rt][2 stages][3][Lp]
+  __shared__ float s_agg[2][N1_MAX_WARPS][2];
+  __shared__ float s_red[N1_MAX_WARPS][3];
+  __shared__ __align__(8) uint64_t s_full[N1_MAX_WARPS][2];
+  const N1Thread q = n1_thread(gm);
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.z, g = blockIdx.y;
+  const int L = p.L, Lp = (L + 31) & ~31;                  // ring rows padded to 128 bytes
+  const int rows_cta = gm.rt * gm.rseq;
+  const int row_base = blockIdx.x * rows_cta;
+  const bool lane_ok = q.r < gm.rt;
+  const bool plain = gridDim.x == 1;
+  const int l0 = q.t * N1_P;
+  const float* fB = static_cast<const float*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
+  const float* fC = static_cast<const float*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
+  float* dBrow = p.dB + (int64_t)(b * p.G + g) * L;
+  float* dCrow = p.dC + (int64_t)(b * p.G + g) * L;
+  float* ring = s_ring + (size_t)(lane_ok ? q.r : 0) * 6 * Lp;
+  const bool leader = lane_ok && q.t == 0;                 // issues this row lane's TMA copies
+  const uint32_t row_bytes = (uint32_t)L * 4u;
+
+  auto row_of = [&](int j) { return row_base + j * gm.rt + q.r; };
+  auto issue = [&](int j) {                                // leader only: rows past the group are skipped (never waited for)
+    const int row = row_of(j);
+    if (j >= gm.rseq || row >= p.dpg) return;
+    const int d = g * p.dpg + row, s = j & 1;
+    const int u_ch = p.u_mod > 0 ? d % p.u_mod : d;
+    float* st = ring + (size_t)s * 3 * Lp;
+    mbar_arrive_expect_tx(&s_full[q.r][s], 3u * row_bytes);
+    tma_load_1d(st, static_cast<const float*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds, row_bytes, &s_full[q.r][s]);
+    tma_load_1d(st + Lp, static_cast<const float*>(p.u) + (int64_t)b * p.u_bs + (int64_t)u_ch * p.u_ds, row_bytes, &s_full[q.r][s]);
+    tma_load_1d(st + 2 * Lp, static_cast<const float*>(p.dout) + (int64_t)b * p.out_bs + (int64_t)u_ch * p.out_ds, row_bytes, &s_full[q.r][s]);
+  };
+  if (leader) { mbar_init(&s_full[q.r][0], 1); mbar_init(&s_full[q.r][1], 1); fence_mbar_init(); }
+  __syncthreads();
+  if (leader) { issue(0); issue(1); }
+
+  auto body = [&](auto REVT) {
+    constexpr bool REV = decltype(REVT)::value;
+    float bb[N1_P], cB[N1_P];
+    n1_load<true, REV>(fB, l0, lane_ok ? L : 0, 0.f, bb);
+    n1_load<true, REV>(fC, l0, lane_ok ? L : 0, 0.f, cB);
+    float dBv[N1_P], dCv[N1_P];
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          float* dst = which == 0 ? dBrow : dCrow;
-          const float* v = which == 0 ? dBv : dCv;
-          if constexpr (VEC) {
+    for (int i = 0; i < N1_P; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+    for (int j = 0; j < gm.rseq; ++j) {
+      const int row = row_of(j);
+      if (!lane_ok || row >= p.dpg) break;                 // uniform over the row lane: its barriers stay consistent
+      const int d = g * p.dpg + row, s = j & 1;
+      const float A1 = p.A[d];
+      const float bias = p.bias ? p.bias[d] : 0.f;
+      const float Dd = p.Dv ? p.Dv[d] : 0.f;
+      mbar_wait(&s_full[q.r][s], (uint32_t)(j >> 1) & 1u);
+      const float* st = ring + (size_t)s * 3 * Lp;
+      float dl[N1_P], uu[N1_P], dy[N1_P];
+      // generic-proxy reads of what the async proxy wrote: ordered by the mbarrier wait above
 #pragma unroll
-            for (int k = 0; k < N1_P; k += 4) {
-              if (l0 + k < L) {
-                float4* q4 = reinterpret_cast<float4*>(dst + (rev ? L - 4 - (l0 + k) : l0 + k));
-                const float4 x = rev ? make_float4(v[k + 3], v[k + 2], v[k + 1], v[k]) : make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                if (single_cta_group) *q4 = x;
-                else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q4), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
-              }
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < N1_P; ++k) {
-              if (l0 + k < L) {
-                float* q1 = dst + (rev ? L - 1 - (l0 + k) : l0 + k);
-                if (single_cta_group) *q1 = v[k];
-                else atomicAdd(q1, v[k]);
-              }
-            }
-          }
+      for (int cch = 0; cch < N1_P; cch += 4) {
+        const bool in = l0 + cch < L;
+        const int off = REV ? L - 4 - (l0 + cch) : l0 + cch;
+        float4 v0 = make_float4(SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f);
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
+        if (in) {
+          v0 = *reinterpret_cast<const float4*>(st + off);
+          v1 = *reinterpret_cast<const float4*>(st + Lp + off);
+          v2 = *reinterpret_cast<const float4*>(st + 2 * Lp + off);
         }
+        dl[cch] = REV ? v0.w : v0.x; dl[cch + 1] = REV ? v0.z : v0.y; dl[cch + 2] = REV ? v0.y : v0.z; dl[cch + 3] = REV ? v0.x : v0.w;
+        uu[cch] = REV ? v1.w : v1.x; uu[cch + 1] = REV ? v1.z : v1.y; uu[cch + 2] = REV ? v1.y : v1.z; uu[cch + 3] = REV ? v1.x : v1.w;
+        dy[cch] = REV ? v2.w : v2.x; dy[cch + 1] = REV ? v2.z : v2.y; dy[cch + 2] = REV ? v2.y : v2.z; dy[cch + 3] = REV ? v2.x : v2.w;
+      }
+      float dub[N1_P], ddl[N1_P];
+      float t_carry = 0.f, accA = 0.f, accD = 0.f, accb = 0.f;
+      n1_bwd_segment<SP>(dl, uu, dy, bb, cB, l0, L, A1, bias, Dd, 0.f, t_carry, lane, q, gm, s_agg[0] + q.r * gm.wpr,
+                         s_agg[1] + q.r * gm.wpr, dub, ddl, dBv, dCv, accA, accD, accb);
+      // every thread of the row lane passed the barriers inside the segment after its reads of stage s: refill it
+      if (gm.wpr == 1) __syncwarp();
+      if (leader) { fence_proxy_async(); issue(j + 2); }
+      const int u_ch = p.u_mod > 0 ? d % p.u_mod : d;
+      (void)u_ch;
+      float* fdu = static_cast<float*>(p.du) + (p.u_mod > 0 ? ((int64_t)b * p.dim + d) * (int64_t)L : (int64_t)b * p.u_bs + (int64_t)d * p.u_ds);
+      float* fdd = static_cast<float*>(p.ddelta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
+      n1_store<true, REV>(fdu, l0, L, dub);
+      n1_store<true, REV>(fdd, l0, L, ddl);
+      n1_row_sum3(accA, accD, accb, lane, q, gm, s_red + q.r * gm.wpr, 1 + q.r);
+      if (q.t == 0) n1_emit_row_grads(p, b, d, accA, accD, accb, dA, dD, dbias, grads_zeroed);
+    }
+    // ---- dB / dC of the rows this CTA walked: sum over the row lanes through shared memory (the ring is idle now) ----
+    if (gm.rt == 1) {
+      if (lane_ok) {
+        n1_emit<true, REV>(dBrow, l0, L, dBv, plain);
+        n1_emit<true, REV>(dCrow, l0, L, dCv, plain);
       }
     } else {
-      float* slabB = s_slab + (size_t)q.r * gm.lc + q.t * N1_P;
+      __syncthreads();                                     // every lane is past its last ring read (no copy is in flight: issue() stops at rseq)
+      float* slabB = s_ring + (size_t)q.r * gm.lc + l0;
       float* slabC = slabB + (size_t)gm.rt * gm.lc;
-      if (q.r < gm.rt) {
+      if (lane_ok) {
         *reinterpret_cast<float4*>(slabB) = make_float4(dBv[0], dBv[1], dBv[2], dBv[3]);
         *reinterpret_cast<float4*>(slabB + 4) = make_float4(dBv[4], dBv[5], dBv[6], dBv[7]);
         *reinterpret_cast<float4*>(slabC) = make_float4(dCv[0], dCv[1], dCv[2], dCv[3]);
         *reinterpret_cast<float4*>(slabC + 4) = make_float4(dCv[4], dCv[5], dCv[6], dCv[7]);
       }
       __syncthreads();
-      const int L0 = p.L, c4 = gm.lc / 4;
-      for (int i = threadIdx.x; i < 2 * c4; i += blockDim.x) {
-        const int which = i / c4, pos = (i - which * c4) * 4;
-        const int l = c * gm.lc + pos;
-        if (l >= L0) continue;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* col = s_slab + (size_t)which * gm.rt * gm.lc + pos;
-        for (int rr = 0; rr < gm.rt; ++rr) {
-          const float4 v = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc);
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        float* dst = which == 0 ? dBrow : dCrow;
-        if (VEC) {
-          float4* q4 = reinterpret_cast<float4*>(dst + (rev ? L0 - 4 - l : l));
-          const float4 x = rev ? make_float4(acc.w, acc.z, acc.y, acc.x) : acc;
-          if (single_cta_group) *q4 = x;
-          else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q4), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
-        } else {
+      const int c8 = gm.lc / N1_P;
+      for (int i = threadIdx.x; i < 2 * c8; i += blockDim.x) {
+        const int which = i / c8, pos = (i - which * c8) * N1_P;
+        if (pos >= L) continue;
+        float acc[N1_P];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (l + e < L0) {
-              float* q1 = dst + (rev ? L0 - 1 - (l + e) : l + e);
-              if (single_cta_group) *q1 = f4_at(acc, e);
-              else atomicAdd(q1, f4_at(acc, e));
-            }
-          }
+        for (int e = 0; e < N1_P; ++e) acc[e] = 0.f;
+        const float* col = s_ring + (size_t)which * gm.rt * gm.lc + pos;
+        for (int rr = 0; rr < gm.rt; ++rr) {
+          const float4 v0 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc);
+          const float4 v1 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc + 4);
+          acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+          acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
         }
+        n1_emit<true, REV>(which == 0 ? dBrow : dCrow, pos, L, acc, plain);
       }
-      __syncthreads();
     }
-  }
-  // ---- dA, dD, d(delta_bias): sum over the threads of the row ----
-  for (int off = gm.seg >> 1; off >= 1; off >>= 1) {
-    accA += __shfl_xor_sync(0xffffffffu, accA, off);
-    accD += __shfl_xor_sync(0xffffffffu, accD, off);
-    accb += __shfl_xor_sync(0xffffffffu, accb, off);
-  }
-  if (gm.wpr > 1) {
-    const int warp = threadIdx.x >> 5;
-    if (lane == 0) { s_red[warp][0] = accA; s_red[warp][1] = accD; s_red[warp][2] = accb; }
-    __syncthreads();
-    if (q.t == 0) {
-      accA = accD = accb = 0.f;
-      for (int w = 0; w < gm.wpr; ++w) { accA += s_red[q.r * gm.wpr + w][0]; accD += s_red[q.r * gm.wpr + w][1]; accb += s_red[q.r * gm.wpr + w][2]; }
-    }
-  }
-  if (q.t == 0 && valid) {
-    if (grads_zeroed) {
-      atomicAdd(dA + d, accA);
-      if (dD) atomicAdd(dD + d, accD);
-      if (dbias) atomicAdd(dbias + d, accb);
-    } else {
-      float* dst = p.part + ((int64_t)b * p.dim + d) * 3;
-      dst[0] = accA; dst[1] = accD; dst[2] = accb;
-    }
-  }
+  };
+  if (p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3) body(std::true_type{}); else body(std::false_type{});
 }
 
 // ------------------------------------------------------------------------------------------------- host side
@@ -405,7 +571,7 @@ static bool n1_vec(const ScanParams& p, bool backward) {
          n1_aligned16(p.dB) && n1_aligned16(p.dC);
 }
 
-static N1Geom n1_geometry(const ScanParams& p, bool backward) {
+static N1Geom n1_geometry(const ScanParams& p) {
   N1Geom gm;
   const int L = p.L;
   if (L <= 32 * N1_P) {                       // one warp (or a fraction of it) per row
@@ -419,16 +585,16 @@ static N1Geom n1_geometry(const ScanParams& p, bool backward) {
   }
   gm.lc = gm.seg * gm.wpr * N1_P;
   gm.nchunks = (L + gm.lc - 1) / gm.lc;
-  // rows per CTA: fill about 8 warps, but keep at least ~2 CTAs per SM in the grid when the problem is that small
+  gm.rseq = 1;
+  // row lanes per CTA: fill about 8 warps, but keep at least ~2 CTAs per SM in the grid when the problem is that small
   const int rows_per_warp = gm.seg == 32 ? 1 : 32 / gm.seg;
-  int warps = gm.wpr > 8 ? gm.wpr : 8;
+  const int warps = gm.wpr > 8 ? gm.wpr : 8;
   int rt = gm.seg == 32 ? warps / gm.wpr : warps * rows_per_warp;
   const int sms = sm_count_current_device();
   while (rt > rows_per_warp && rt > 1 && (long)((p.dpg + rt - 1) / rt) * p.G * p.batch < 2L * sms) rt = (rt + 1) / 2;
   if (gm.seg < 32) rt = (rt + rows_per_warp - 1) / rows_per_warp * rows_per_warp;     // whole warps
   if (rt > p.dpg) rt = gm.seg == 32 ? p.dpg : (p.dpg + rows_per_warp - 1) / rows_per_warp * rows_per_warp;
   gm.rt = rt < 1 ? 1 : rt;
-  (void)backward;
   return gm;
 }
 
@@ -439,23 +605,77 @@ static int n1_threads(const N1Geom& gm) {
 // Returns true when the lean path took the call (*err holds the launch status).
 bool scan_n1_fwd_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   if (!n1_eligible(p, false)) return false;
-  const N1Geom gm = n1_geometry(p, false);
+  const N1Geom gm = n1_geometry(p);
   dim3 grid((p.dpg + gm.rt - 1) / gm.rt, p.G, p.batch);
-  if (n1_vec(p, false)) scan_n1_fwd_kernel<true><<<grid, n1_threads(gm), 0, stream>>>(p, gm);
-  else scan_n1_fwd_kernel<false><<<grid, n1_threads(gm), 0, stream>>>(p, gm);
+  const int nt = n1_threads(gm);
+  const bool vec = n1_vec(p, false), sp = p.softplus != 0;
+  if (vec && sp) scan_n1_fwd_kernel<true, true><<<grid, nt, 0, stream>>>(p, gm);
+  else if (vec) scan_n1_fwd_kernel<true, false><<<grid, nt, 0, stream>>>(p, gm);
+  else if (sp) scan_n1_fwd_kernel<false, true><<<grid, nt, 0, stream>>>(p, gm);
+  else scan_n1_fwd_kernel<false, false><<<grid, nt, 0, stream>>>(p, gm);
   *err = cudaGetLastError();
+  return true;
+}
+
+// Geometry of the rows kernel: seg = 32 only (rows of at least one warp), single-pass rows; the row lanes of a CTA share
+// up to 16 warps and at most 15 named barriers; rseq rows per lane such that the grid still has ~1.5 CTAs per SM when the
+// group is big enough, one CTA per group otherwise (then dB / dC are plain stores).
+static bool n1_rows_geometry(const ScanParams& p, N1Geom* out, size_t* smem) {
+  if (p.L <= 32 * N1_P / 2 || p.L > N1_MAX_WARPS * 32 * N1_P) return false;
+  N1Geom gm;
+  gm.seg = 32;
+  gm.wpr = (p.L + 32 * N1_P - 1) / (32 * N1_P);
+  gm.lc = gm.wpr * 32 * N1_P;
+  gm.nchunks = 1;
+  int rt = N1_MAX_WARPS / gm.wpr;
+  if (rt > 8) rt = 8;
+  if (rt > p.dpg) rt = p.dpg;
+  const int Lp = (p.L + 31) & ~31;
+  while (rt > 1 && (size_t)rt * 6 * Lp * sizeof(float) > 96 * 1024) --rt;
+  const int sms = sm_count_current_device();
+  const long groups = (long)p.G * p.batch;
+  long blocks = (3L * sms / 2 + groups - 1) / groups;                   // row blocks per group we would like
+  const long max_blocks = (p.dpg + rt - 1) / rt;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  gm.rt = rt;
+  gm.rseq = (int)((p.dpg + rt * blocks - 1) / (rt * blocks));
+  *smem = (size_t)rt * 6 * Lp * sizeof(float);
+  if (*smem < (size_t)2 * rt * gm.lc * sizeof(float)) *smem = (size_t)2 * rt * gm.lc * sizeof(float);
+  *out = gm;
   return true;
 }
 
 bool scan_n1_bwd_try(const ScanParams& p, float* dA, float* dD, float* dbias, int grads_zeroed, cudaStream_t stream,
                      cudaError_t* err) {
   if (!n1_eligible(p, true)) return false;
-  const N1Geom gm = n1_geometry(p, true);
+  const bool vec = n1_vec(p, true), sp = p.softplus != 0;
+  N1Geom gr;
+  size_t smem_rows = 0;
+  if (vec && n1_rows_geometry(p, &gr, &smem_rows)) {
+    static PerDeviceOnce once_sp, once_nosp;
+    cudaError_t e = sp ? func_attr_once(once_sp, reinterpret_cast<const void*>(scan_n1_bwd_rows_kernel<true>),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
+                       : func_attr_once(once_nosp, reinterpret_cast<const void*>(scan_n1_bwd_rows_kernel<false>),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) { *err = e; return true; }
+    const int rows_cta = gr.rt * gr.rseq;
+    dim3 grid((p.dpg + rows_cta - 1) / rows_cta, p.G, p.batch);
+    const int nt = gr.rt * gr.wpr * 32;
+    if (sp) scan_n1_bwd_rows_kernel<true><<<grid, nt, smem_rows, stream>>>(p, gr, dA, dD, dbias, grads_zeroed);
+    else scan_n1_bwd_rows_kernel<false><<<grid, nt, smem_rows, stream>>>(p, gr, dA, dD, dbias, grads_zeroed);
+    *err = cudaGetLastError();
+    return true;
+  }
+  const N1Geom gm = n1_geometry(p);
   dim3 grid((p.dpg + gm.rt - 1) / gm.rt, p.G, p.batch);
   const size_t smem = gm.rt > 1 ? (size_t)2 * gm.rt * gm.lc * sizeof(float) : 0;
   if (smem > 40 * 1024) return false;
-  if (n1_vec(p, true)) scan_n1_bwd_kernel<true><<<grid, n1_threads(gm), smem, stream>>>(p, gm, dA, dD, dbias, grads_zeroed);
-  else scan_n1_bwd_kernel<false><<<grid, n1_threads(gm), smem, stream>>>(p, gm, dA, dD, dbias, grads_zeroed);
+  const int nt = n1_threads(gm);
+  if (vec && sp) scan_n1_bwd_kernel<true, true><<<grid, nt, smem, stream>>>(p, gm, dA, dD, dbias, grads_zeroed);
+  else if (vec) scan_n1_bwd_kernel<true, false><<<grid, nt, smem, stream>>>(p, gm, dA, dD, dbias, grads_zeroed);
+  else if (sp) scan_n1_bwd_kernel<false, true><<<grid, nt, smem, stream>>>(p, gm, dA, dD, dbias, grads_zeroed);
+  else scan_n1_bwd_kernel<false, false><<<grid, nt, smem, stream>>>(p, gm, dA, dD, dbias, grads_zeroed);
   *err = cudaGetLastError();
   return true;
 }
