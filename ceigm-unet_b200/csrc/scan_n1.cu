@@ -415,131 +415,176 @@ __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_bwd_kernel(const Sc
 }
 
 // ------------------------------------------------------------------------------------------------- backward, rows walked per lane
-// Single-pass rows (L <= 16 warps x 256), 16-byte aligned: see the header comment. Shared memory: per row lane a 2-stage
-// ring of [delta | u | dout] rows (TMA bulk copies), reused at the end as the slab that sums dB / dC over the row lanes.
+// 16-byte aligned fp32 rows of at least one warp: see the header comment. Rows longer than 16 warps x 256 positions are
+// walked in chunks of 8 warps x 256, last to first (chunk-outer, rows-inner, so dB / dC of a chunk stay in registers across the
+// rows; the per-row reverse carry lives in shared memory, the forward state entering a chunk comes from the forward's
+// checkpoints). Shared memory: per row lane a 2-stage ring of [delta | u | dout] row pieces (TMA bulk copies), reused after
+// each chunk as the slab that sums dB / dC over the row lanes.
+constexpr int N1_MAX_RSEQ = 64;
+
 template <bool SP>
 __global__ void __launch_bounds__(N1_MAX_WARPS * 32) scan_n1_bwd_rows_kernel(const ScanParams p, const N1Geom gm, float* __restrict__ dA,
                                                                            float* __restrict__ dD, float* __restrict__ dbias,
                                                                            int grads_zeroed) {
-  extern __shared__ __align__(128) float s_ring[];         // [rt][2 stages][3][Lp]
+  extern __shared__ __align__(128) float s_ring[];         // [rt][2 stages][3][lr]
   __shared__ float s_agg[2][N1_MAX_WARPS][2];
-  __shared__ float s_red[N1_MAX_WARPS][3];
+  __shared__ float s_red[2][N1_MAX_WARPS][3];
+  __shared__ float s_tc[N1_MAX_WARPS][N1_MAX_RSEQ];        // reverse carry of each row between chunks (multi-chunk rows)
   __shared__ __align__(8) uint64_t s_full[N1_MAX_WARPS][2];
-  const N1Thread q = n1_thread(gm);
+  N1Geom gq = gm;
+  gq.seg = 32;                                             // compile-time constant for the shuffle scans below
+  const N1Thread q = n1_thread(gq);
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, g = blockIdx.y;
-  const int L = p.L, Lp = (L + 31) & ~31;                  // ring rows padded to 128 bytes
+  const int L = p.L;
+  const int lr = gm.nchunks == 1 ? ((L + 31) & ~31) : gm.lc;          // ring row length (floats), a multiple of 128 bytes
   const int rows_cta = gm.rt * gm.rseq;
-  const int row_base = blockIdx.x * rows_cta;
-  const bool lane_ok = q.r < gm.rt;
+  const int row_base = blockIdx.x * rows_cta + q.r;
+  // rows this lane walks: row_base + j rt for j < nj
+  const int nj = row_base < p.dpg ? min(gm.rseq, (p.dpg - row_base + gm.rt - 1) / gm.rt) : 0;
   const bool plain = gridDim.x == 1;
-  const int l0 = q.t * N1_P;
   const float* fB = static_cast<const float*>(p.Bm) + (int64_t)b * p.B_bs + (int64_t)g * p.B_gs;
   const float* fC = static_cast<const float*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
   float* dBrow = p.dB + (int64_t)(b * p.G + g) * L;
   float* dCrow = p.dC + (int64_t)(b * p.G + g) * L;
-  float* ring = s_ring + (size_t)(lane_ok ? q.r : 0) * 6 * Lp;
-  const bool leader = lane_ok && q.t == 0;                 // issues this row lane's TMA copies
-  const uint32_t row_bytes = (uint32_t)L * 4u;
-
-  auto row_of = [&](int j) { return row_base + j * gm.rt + q.r; };
-  auto issue = [&](int j) {                                // leader only: rows past the group are skipped (never waited for)
-    const int row = row_of(j);
-    if (j >= gm.rseq || row >= p.dpg) return;
-    const int d = g * p.dpg + row, s = j & 1;
-    const int u_ch = p.u_mod > 0 ? d % p.u_mod : d;
-    float* st = ring + (size_t)s * 3 * Lp;
-    mbar_arrive_expect_tx(&s_full[q.r][s], 3u * row_bytes);
-    tma_load_1d(st, static_cast<const float*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds, row_bytes, &s_full[q.r][s]);
-    tma_load_1d(st + Lp, static_cast<const float*>(p.u) + (int64_t)b * p.u_bs + (int64_t)u_ch * p.u_ds, row_bytes, &s_full[q.r][s]);
-    tma_load_1d(st + 2 * Lp, static_cast<const float*>(p.dout) + (int64_t)b * p.out_bs + (int64_t)u_ch * p.out_ds, row_bytes, &s_full[q.r][s]);
-  };
-  if (leader) { mbar_init(&s_full[q.r][0], 1); mbar_init(&s_full[q.r][1], 1); fence_mbar_init(); }
-  __syncthreads();
-  if (leader) { issue(0); issue(1); }
+  float* ring = s_ring + (size_t)q.r * 6 * lr;
+  const bool leader = q.t == 0;                            // issues this row lane's TMA copies
+  const int total_it = nj * gm.nchunks;
 
   auto body = [&](auto REVT) {
     constexpr bool REV = decltype(REVT)::value;
-    float bb[N1_P], cB[N1_P];
-    n1_load<true, REV>(fB, l0, lane_ok ? L : 0, 0.f, bb);
-    n1_load<true, REV>(fC, l0, lane_ok ? L : 0, 0.f, cB);
-    float dBv[N1_P], dCv[N1_P];
-#pragma unroll
-    for (int i = 0; i < N1_P; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
-    for (int j = 0; j < gm.rseq; ++j) {
-      const int row = row_of(j);
-      if (!lane_ok || row >= p.dpg) break;                 // uniform over the row lane: its barriers stay consistent
-      const int d = g * p.dpg + row, s = j & 1;
-      const float A1 = p.A[d];
-      const float bias = p.bias ? p.bias[d] : 0.f;
-      const float Dd = p.Dv ? p.Dv[d] : 0.f;
-      mbar_wait(&s_full[q.r][s], (uint32_t)(j >> 1) & 1u);
-      const float* st = ring + (size_t)s * 3 * Lp;
-      float dl[N1_P], uu[N1_P], dy[N1_P];
-      // generic-proxy reads of what the async proxy wrote: ordered by the mbarrier wait above
-#pragma unroll
-      for (int cch = 0; cch < N1_P; cch += 4) {
-        const bool in = l0 + cch < L;
-        const int off = REV ? L - 4 - (l0 + cch) : l0 + cch;
-        float4 v0 = make_float4(SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f);
-        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
-        if (in) {
-          v0 = *reinterpret_cast<const float4*>(st + off);
-          v1 = *reinterpret_cast<const float4*>(st + Lp + off);
-          v2 = *reinterpret_cast<const float4*>(st + 2 * Lp + off);
-        }
-        dl[cch] = REV ? v0.w : v0.x; dl[cch + 1] = REV ? v0.z : v0.y; dl[cch + 2] = REV ? v0.y : v0.z; dl[cch + 3] = REV ? v0.x : v0.w;
-        uu[cch] = REV ? v1.w : v1.x; uu[cch + 1] = REV ? v1.z : v1.y; uu[cch + 2] = REV ? v1.y : v1.z; uu[cch + 3] = REV ? v1.x : v1.w;
-        dy[cch] = REV ? v2.w : v2.x; dy[cch + 1] = REV ? v2.z : v2.y; dy[cch + 2] = REV ? v2.y : v2.z; dy[cch + 3] = REV ? v2.x : v2.w;
-      }
-      float dub[N1_P], ddl[N1_P];
-      float t_carry = 0.f, accA = 0.f, accD = 0.f, accb = 0.f;
-      n1_bwd_segment<SP>(dl, uu, dy, bb, cB, l0, L, A1, bias, Dd, 0.f, t_carry, lane, q, gm, s_agg[0] + q.r * gm.wpr,
-                         s_agg[1] + q.r * gm.wpr, dub, ddl, dBv, dCv, accA, accD, accb);
-      // every thread of the row lane passed the barriers inside the segment after its reads of stage s: refill it
-      if (gm.wpr == 1) __syncwarp();
-      if (leader) { fence_proxy_async(); issue(j + 2); }
+    auto issue = [&](int it) {                             // leader only; it = (chunk counted from the end) * nj + j
+      if (it >= total_it) return;
+      const int ci = it / nj, j = it - ci * nj, c = gm.nchunks - 1 - ci, s = it & 1;
+      const int d = g * p.dpg + row_base + j * gm.rt;
       const int u_ch = p.u_mod > 0 ? d % p.u_mod : d;
-      (void)u_ch;
-      float* fdu = static_cast<float*>(p.du) + (p.u_mod > 0 ? ((int64_t)b * p.dim + d) * (int64_t)L : (int64_t)b * p.u_bs + (int64_t)d * p.u_ds);
-      float* fdd = static_cast<float*>(p.ddelta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
-      n1_store<true, REV>(fdu, l0, L, dub);
-      n1_store<true, REV>(fdd, l0, L, ddl);
-      n1_row_sum3(accA, accD, accb, lane, q, gm, s_red + q.r * gm.wpr, 1 + q.r);
-      if (q.t == 0) n1_emit_row_grads(p, b, d, accA, accD, accb, dA, dD, dbias, grads_zeroed);
-    }
-    // ---- dB / dC of the rows this CTA walked: sum over the row lanes through shared memory (the ring is idle now) ----
-    if (gm.rt == 1) {
-      if (lane_ok) {
-        n1_emit<true, REV>(dBrow, l0, L, dBv, plain);
-        n1_emit<true, REV>(dCrow, l0, L, dCv, plain);
+      const int len = min(gm.lc, L - c * gm.lc);
+      const int64_t m0 = REV ? L - c * gm.lc - len : c * gm.lc;       // first memory position of the piece
+      const uint32_t bytes = (uint32_t)len * 4u;
+      float* st = ring + (size_t)s * 3 * lr;
+      mbar_arrive_expect_tx(&s_full[q.r][s], 3u * bytes);
+      tma_load_1d(st, static_cast<const float*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds + m0, bytes, &s_full[q.r][s]);
+      tma_load_1d(st + lr, static_cast<const float*>(p.u) + (int64_t)b * p.u_bs + (int64_t)u_ch * p.u_ds + m0, bytes, &s_full[q.r][s]);
+      tma_load_1d(st + 2 * lr, static_cast<const float*>(p.dout) + (int64_t)b * p.out_bs + (int64_t)u_ch * p.out_ds + m0, bytes, &s_full[q.r][s]);
+    };
+    if (leader) { mbar_init(&s_full[q.r][0], 1); mbar_init(&s_full[q.r][1], 1); fence_mbar_init(); }
+    __syncthreads();
+    if (leader) { issue(0); issue(1); }
+
+    for (int ci = 0; ci < gm.nchunks; ++ci) {
+      const int c = gm.nchunks - 1 - ci;
+      const int len = min(gm.lc, L - c * gm.lc);           // positions of this chunk
+      const int lq = q.t * N1_P;                           // this thread's first position inside the chunk
+      const int l0 = c * gm.lc + lq;
+      float bb[N1_P], cB[N1_P];
+      n1_load<true, REV>(fB, l0, nj > 0 ? L : 0, 0.f, bb);
+      n1_load<true, REV>(fC, l0, nj > 0 ? L : 0, 0.f, cB);
+      float dBv[N1_P], dCv[N1_P];
+#pragma unroll
+      for (int i = 0; i < N1_P; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+      for (int j = 0; j < nj; ++j) {
+        const int it = ci * nj + j, s = it & 1;
+        const int d = g * p.dpg + row_base + j * gm.rt;
+        const float A1 = p.A[d];
+        const float bias = p.bias ? p.bias[d] : 0.f;
+        const float Dd = p.Dv ? p.Dv[d] : 0.f;
+        const float h_chunk = c > 0 ? __ldg(p.ckpt_in + ((int64_t)b * p.dim + d) * p.nck + (c * gm.lc) / SS2D_CHUNK - 1) : 0.f;
+        float t_carry = ci > 0 ? s_tc[q.r][j] : 0.f;       // written one chunk ago, several row-lane barriers back
+        mbar_wait(&s_full[q.r][s], (uint32_t)(it >> 1) & 1u);
+        const float* st = ring + (size_t)s * 3 * lr;
+        float dl[N1_P], uu[N1_P], dy[N1_P];
+#pragma unroll
+        for (int cch = 0; cch < N1_P; cch += 4) {
+          const bool in = lq + cch < len;
+          const int off = REV ? len - 4 - (lq + cch) : lq + cch;
+          float4 v0 = make_float4(SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f, SP ? -INFINITY : 0.f);
+          float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1;
+          if (in) {
+            v0 = *reinterpret_cast<const float4*>(st + off);
+            v1 = *reinterpret_cast<const float4*>(st + lr + off);
+            v2 = *reinterpret_cast<const float4*>(st + 2 * lr + off);
+          }
+          dl[cch] = REV ? v0.w : v0.x; dl[cch + 1] = REV ? v0.z : v0.y; dl[cch + 2] = REV ? v0.y : v0.z; dl[cch + 3] = REV ? v0.x : v0.w;
+          uu[cch] = REV ? v1.w : v1.x; uu[cch + 1] = REV ? v1.z : v1.y; uu[cch + 2] = REV ? v1.y : v1.z; uu[cch + 3] = REV ? v1.x : v1.w;
+          dy[cch] = REV ? v2.w : v2.x; dy[cch + 1] = REV ? v2.z : v2.y; dy[cch + 2] = REV ? v2.y : v2.z; dy[cch + 3] = REV ? v2.x : v2.w;
+        }
+        float dub[N1_P], ddl[N1_P];
+        float accA = 0.f, accD = 0.f, accb = 0.f;
+        n1_bwd_segment<SP>(dl, uu, dy, bb, cB, l0, L, A1, bias, Dd, h_chunk, t_carry, lane, q, gq, s_agg[0] + q.r * gm.wpr,
+                           s_agg[1] + q.r * gm.wpr, dub, ddl, dBv, dCv, accA, accD, accb);
+        // every thread of the row lane passed the barriers inside the segment after its reads of stage s: refill it
+        if (gm.wpr == 1) __syncwarp();
+        if (leader) { fence_proxy_async(); issue(it + 2); if (gm.nchunks > 1) s_tc[q.r][j] = t_carry; }
+        float* fdu = static_cast<float*>(p.du) + (p.u_mod > 0 ? ((int64_t)b * p.dim + d) * (int64_t)L : (int64_t)b * p.u_bs + (int64_t)d * p.u_ds);
+        float* fdd = static_cast<float*>(p.ddelta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
+        n1_store<true, REV>(fdu, l0, L, dub);
+        n1_store<true, REV>(fdd, l0, L, ddl);
+        // per-row sums of dA / dD / d(delta_bias): shuffle tree, one shared-memory hop, warp 0 of the row finishes
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          accA += __shfl_xor_sync(0xffffffffu, accA, off);
+          accD += __shfl_xor_sync(0xffffffffu, accD, off);
+          accb += __shfl_xor_sync(0xffffffffu, accb, off);
+        }
+        if (gm.wpr > 1) {
+          float (*red)[3] = s_red[it & 1] + q.r * gm.wpr;
+          if (lane == 0) { red[q.wir][0] = accA; red[q.wir][1] = accD; red[q.wir][2] = accb; }
+          n1_bar(1 + q.r, gm.wpr * 32);
+          if (q.wir == 0) {
+            accA = lane < gm.wpr ? red[lane][0] : 0.f;
+            accD = lane < gm.wpr ? red[lane][1] : 0.f;
+            accb = lane < gm.wpr ? red[lane][2] : 0.f;
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) {
+              accA += __shfl_xor_sync(0xffffffffu, accA, off);
+              accD += __shfl_xor_sync(0xffffffffu, accD, off);
+              accb += __shfl_xor_sync(0xffffffffu, accb, off);
+            }
+          }
+        }
+        if (q.t == 0) {
+          if (grads_zeroed) {
+            atomicAdd(dA + d, accA);
+            if (dD) atomicAdd(dD + d, accD);
+            if (dbias) atomicAdd(dbias + d, accb);
+          } else {                                         // single-chunk rows only (host side): partials for the finalize pass
+            float* dst = p.part + ((int64_t)b * p.dim + d) * 3;
+            dst[0] = accA; dst[1] = accD; dst[2] = accb;
+          }
+        }
       }
-    } else {
-      __syncthreads();                                     // every lane is past its last ring read (no copy is in flight: issue() stops at rseq)
-      float* slabB = s_ring + (size_t)q.r * gm.lc + l0;
-      float* slabC = slabB + (size_t)gm.rt * gm.lc;
-      if (lane_ok) {
+      // ---- dB / dC of this chunk over the rows the CTA walked: sum over the row lanes through shared memory ----
+      if (gm.rt == 1) {
+        if (nj > 0) {
+          n1_emit<true, REV>(dBrow, l0, L, dBv, plain);
+          n1_emit<true, REV>(dCrow, l0, L, dCv, plain);
+        }
+      } else {      // single-chunk rows: the ring is idle by now and doubles as the slab; chunked rows have their own slab
+        __syncthreads();                                   // also orders this chunk's slab writes after the previous chunk's reads
+        float* slab0 = s_ring + (gm.nchunks > 1 ? (size_t)gm.rt * 6 * lr : 0);
+        float* slabB = slab0 + (size_t)q.r * gm.lc + lq;
+        float* slabC = slabB + (size_t)gm.rt * gm.lc;
         *reinterpret_cast<float4*>(slabB) = make_float4(dBv[0], dBv[1], dBv[2], dBv[3]);
         *reinterpret_cast<float4*>(slabB + 4) = make_float4(dBv[4], dBv[5], dBv[6], dBv[7]);
         *reinterpret_cast<float4*>(slabC) = make_float4(dCv[0], dCv[1], dCv[2], dCv[3]);
         *reinterpret_cast<float4*>(slabC + 4) = make_float4(dCv[4], dCv[5], dCv[6], dCv[7]);
-      }
-      __syncthreads();
-      const int c8 = gm.lc / N1_P;
-      for (int i = threadIdx.x; i < 2 * c8; i += blockDim.x) {
-        const int which = i / c8, pos = (i - which * c8) * N1_P;
-        if (pos >= L) continue;
-        float acc[N1_P];
+        __syncthreads();
+        const int c8 = gm.lc / N1_P;
+        for (int i = threadIdx.x; i < 2 * c8; i += blockDim.x) {
+          const int which = i / c8, pos = (i - which * c8) * N1_P;
+          if (c * gm.lc + pos >= L) continue;
+          float acc[N1_P];
 #pragma unroll
-        for (int e = 0; e < N1_P; ++e) acc[e] = 0.f;
-        const float* col = s_ring + (size_t)which * gm.rt * gm.lc + pos;
-        for (int rr = 0; rr < gm.rt; ++rr) {
-          const float4 v0 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc);
-          const float4 v1 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc + 4);
-          acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
-          acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+          for (int e = 0; e < N1_P; ++e) acc[e] = 0.f;
+          const float* col = slab0 + (size_t)which * gm.rt * gm.lc + pos;
+          for (int rr = 0; rr < gm.rt; ++rr) {
+            const float4 v0 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc);
+            const float4 v1 = *reinterpret_cast<const float4*>(col + (size_t)rr * gm.lc + 4);
+            acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+            acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+          }
+          n1_emit<true, REV>(which == 0 ? dBrow : dCrow, c * gm.lc + pos, L, acc, plain);
         }
-        n1_emit<true, REV>(which == 0 ? dBrow : dCrow, pos, L, acc, plain);
       }
     }
   };
@@ -617,21 +662,35 @@ bool scan_n1_fwd_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err)
   return true;
 }
 
-// Geometry of the rows kernel: seg = 32 only (rows of at least one warp), single-pass rows; the row lanes of a CTA share
-// up to 16 warps and at most 15 named barriers; rseq rows per lane such that the grid still has ~1.5 CTAs per SM when the
-// group is big enough, one CTA per group otherwise (then dB / dC are plain stores).
-static bool n1_rows_geometry(const ScanParams& p, N1Geom* out, size_t* smem) {
-  if (p.L <= 32 * N1_P / 2 || p.L > N1_MAX_WARPS * 32 * N1_P) return false;
+// Geometry of the rows kernel: whole warps per row; single-pass rows up to 16 warps x 256 positions share the CTA between up to
+// 8 row lanes (<= 16 warps, <= 15 named barriers, <= 96 KB of ring), longer rows take one lane of 8 warps and are chunked.
+// rseq rows per lane such that the grid still has ~1.5 CTAs per SM when the groups are big enough to be split, one CTA per
+// group otherwise (then dB / dC are plain stores and the result is deterministic).
+static bool n1_rows_geometry(const ScanParams& p, int grads_zeroed, N1Geom* out, size_t* smem) {
+  if (p.L <= 32 * N1_P / 2) return false;
   N1Geom gm;
   gm.seg = 32;
-  gm.wpr = (p.L + 32 * N1_P - 1) / (32 * N1_P);
+  const int need = (p.L + 32 * N1_P - 1) / (32 * N1_P);
+  int rt;
+  size_t lr;
+  if (need <= N1_MAX_WARPS) {
+    gm.wpr = need; gm.nchunks = 1;
+    lr = (size_t)((p.L + 31) & ~31);
+    rt = N1_MAX_WARPS / gm.wpr;
+    if (rt > 8) rt = 8;
+    if (rt > p.dpg) rt = p.dpg;
+    while (rt > 1 && (size_t)rt * 6 * lr * sizeof(float) > 96 * 1024) --rt;
+  } else {
+    // long rows: one lane of 8 warps x 256 positions per chunk, 2 CTAs per SM. (Measured on the 512^2 batch-64 stage-1 shape:
+    // backward 409 us this way, 475 us with 8 row lanes of 2 warps x 256 — the lanes then meet at a CTA-wide barrier for the
+    // dB / dC slab after every chunk and B / C are fetched 4x as often.)
+    if (!grads_zeroed) return false;                         // per-chunk row sums are accumulated with atomics
+    gm.wpr = 8;
+    rt = 1;
+    lr = (size_t)gm.wpr * 32 * N1_P;
+    gm.nchunks = (int)((p.L + lr - 1) / lr);
+  }
   gm.lc = gm.wpr * 32 * N1_P;
-  gm.nchunks = 1;
-  int rt = N1_MAX_WARPS / gm.wpr;
-  if (rt > 8) rt = 8;
-  if (rt > p.dpg) rt = p.dpg;
-  const int Lp = (p.L + 31) & ~31;
-  while (rt > 1 && (size_t)rt * 6 * Lp * sizeof(float) > 96 * 1024) --rt;
   const int sms = sm_count_current_device();
   const long groups = (long)p.G * p.batch;
   long blocks = (3L * sms / 2 + groups - 1) / groups;                   // row blocks per group we would like
@@ -640,8 +699,9 @@ static bool n1_rows_geometry(const ScanParams& p, N1Geom* out, size_t* smem) {
   if (blocks < 1) blocks = 1;
   gm.rt = rt;
   gm.rseq = (int)((p.dpg + rt * blocks - 1) / (rt * blocks));
-  *smem = (size_t)rt * 6 * Lp * sizeof(float);
-  if (*smem < (size_t)2 * rt * gm.lc * sizeof(float)) *smem = (size_t)2 * rt * gm.lc * sizeof(float);
+  if (gm.rseq > N1_MAX_RSEQ) return false;
+  const size_t ring = (size_t)rt * 6 * lr * sizeof(float), slab = (size_t)2 * rt * gm.lc * sizeof(float);
+  *smem = gm.nchunks > 1 ? ring + (rt > 1 ? slab : 0) : (ring > slab ? ring : slab);      // single-chunk rows reuse the idle ring
   *out = gm;
   return true;
 }
@@ -652,12 +712,12 @@ bool scan_n1_bwd_try(const ScanParams& p, float* dA, float* dD, float* dbias, in
   const bool vec = n1_vec(p, true), sp = p.softplus != 0;
   N1Geom gr;
   size_t smem_rows = 0;
-  if (vec && n1_rows_geometry(p, &gr, &smem_rows)) {
+  if (vec && n1_rows_geometry(p, grads_zeroed, &gr, &smem_rows)) {
     static PerDeviceOnce once_sp, once_nosp;
     cudaError_t e = sp ? func_attr_once(once_sp, reinterpret_cast<const void*>(scan_n1_bwd_rows_kernel<true>),
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024)
                        : func_attr_once(once_nosp, reinterpret_cast<const void*>(scan_n1_bwd_rows_kernel<false>),
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
     if (e != cudaSuccess) { *err = e; return true; }
     const int rows_cta = gr.rt * gr.rseq;
     dim3 grid((p.dpg + rows_cta - 1) / rows_cta, p.G, p.batch);
