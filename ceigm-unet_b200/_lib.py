@@ -22,7 +22,7 @@ MAX_DSTATE = 256
 EXPORTS = [
     "ss2d_scan_fwd", "ss2d_scan_ckpt_floats", "ss2d_scan_bwd", "ss2d_scan_bwd_workspace_bytes",
     "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_out_gate_fwd", "ss2d_out_gate_bwd",
-    "ss2d_out_gate_bwd_partials", "ss2d_out_gate_max_width", "ss2d_wgrad_ts", "ss2d_wgrad_ts_workspace_bytes",
+    "ss2d_out_gate_bwd_partials", "ss2d_group_gate_fwd", "ss2d_group_gate_bwd", "ss2d_out_gate_max_width", "ss2d_wgrad_ts", "ss2d_wgrad_ts_workspace_bytes",
     "ss2d_layernorm_fwd", "ss2d_layernorm_bwd", "ss2d_layernorm_bwd_partials",
     "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count",
 ]
@@ -93,6 +93,13 @@ def lib() -> ctypes.CDLL:
     L.ss2d_out_gate_bwd.restype = ctypes.c_int
     L.ss2d_out_gate_max_width.argtypes = [i32]
     L.ss2d_out_gate_max_width.restype = i32
+    u32 = ctypes.c_uint32
+    L.ss2d_group_gate_fwd.argtypes = [fp, i32, ip, u32, fp, fp, vp, i64, i64, i64, vp, i64, fp, i32, i32, i32, ctypes.c_float,
+                                      i32, i32, i32, i32, vp]
+    L.ss2d_group_gate_fwd.restype = ctypes.c_int
+    L.ss2d_group_gate_bwd.argtypes = [fp, i32, ip, u32, fp, fp, vp, i64, i64, i64, vp, i64, fp, fp, vp, i64, fp, fp, i32, i32,
+                                      i32, i32, i32, i32, i32, i32, vp]
+    L.ss2d_group_gate_bwd.restype = ctypes.c_int
     L.ss2d_out_gate_bwd_partials.argtypes = [i32, i32]
     L.ss2d_out_gate_bwd_partials.restype = i32
     L.ss2d_wgrad_ts.argtypes = [vp, vp, fp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, i32, vp, sz, vp]

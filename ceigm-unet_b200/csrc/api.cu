@@ -51,6 +51,15 @@ cudaError_t wgrad_ts_launch(const void* dY, const void* X, float* dW, int batch,
                             int64_t y_rs, int64_t y_cs, int64_t x_bs, int64_t x_rs, int64_t x_cs, int y_dt, int x_dt,
                             float* workspace, cudaStream_t stream);
 int epi_max_D(bool backward);
+cudaError_t group_gate_fwd_launch(const float* ys, int G, const int* plane_of, unsigned tmask_bits, const float* lnw,
+                                  const float* lnb, const void* z, int64_t z_rs, int64_t z_col0, int64_t z_gs, void* out,
+                                  int64_t out_rs, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
+                                  int out_dtype, int H, int W, cudaStream_t stream);
+cudaError_t group_gate_bwd_launch(const float* ys, int G, const int* plane_of, unsigned tmask_bits, const float* lnw,
+                                  const float* lnb, const void* z, int64_t z_rs, int64_t z_col0, int64_t z_gs, const void* dout,
+                                  int64_t dout_rs, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs, float* dw_part,
+                                  float* db_part, int n_partials, int batch, int D, int L, int z_dtype, int out_dtype, int H,
+                                  int W, cudaStream_t stream);
 
 thread_local char g_cuda_err[256] = "";
 // process-wide: the autograd engine launches the backward kernels from its own per-device threads
@@ -312,6 +321,53 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
   cudaError_t e = out_gate_bwd_launch(ys, K, ln_weight, ln_bias, z, z_row_stride, z_act, dout, mean_rstd, dy, dz,
                                       dz_row_stride, dln_weight_partial, dln_bias_partial, n_partials, batch, D, L,
                                       z_dtype, out_dtype, H, W, transposed_mask, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+static int group_gate_check(int32_t G, const int32_t* plane_of, int32_t batch, int32_t D, int32_t L, int32_t H, int32_t W,
+                            int32_t z_dtype, int32_t out_dtype, bool backward) {
+  if (!plane_of) return SS2D_ERR_NULL_POINTER;
+  if (G <= 0 || G > SS2D_MAX_EPI_GROUPS || batch <= 0 || D <= 0 || L <= 0 || H <= 0 || W <= 0 || (int64_t)H * W != L)
+    return SS2D_ERR_BAD_SHAPE;
+  for (int g = 0; g < G; ++g) if (plane_of[g] < 0 || plane_of[g] >= G) return SS2D_ERR_BAD_LAYOUT;
+  if (!dtype_ok(z_dtype) || !dtype_ok(out_dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (D > epi_max_D(backward)) return SS2D_ERR_UNSUPPORTED;
+  return SS2D_OK;
+}
+
+int ss2d_group_gate_fwd(const float* ys, int32_t G, const int32_t* plane_of, uint32_t transposed_planes,
+                        const float* ln_weight, const float* ln_bias, const void* z, int64_t z_row_stride,
+                        int64_t z_col0, int64_t z_group_stride, void* out, int64_t out_row_stride, float* mean_rstd,
+                        int32_t batch, int32_t D, int32_t L, float eps, int32_t z_dtype, int32_t out_dtype, int32_t H,
+                        int32_t W, ss2d_stream_t stream) {
+  if (!ys || !z || !out) return SS2D_ERR_NULL_POINTER;
+  int rc = group_gate_check(G, plane_of, batch, D, L, H, W, z_dtype, out_dtype, false);
+  if (rc != SS2D_OK) return rc;
+  cudaError_t e = group_gate_fwd_launch(ys, G, plane_of, transposed_planes, ln_weight, ln_bias, z, z_row_stride, z_col0,
+                                        z_group_stride, out, out_row_stride, mean_rstd, batch, D, L, eps, z_dtype, out_dtype,
+                                        H, W, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int ss2d_group_gate_bwd(const float* ys, int32_t G, const int32_t* plane_of, uint32_t transposed_planes,
+                        const float* ln_weight, const float* ln_bias, const void* z, int64_t z_row_stride,
+                        int64_t z_col0, int64_t z_group_stride, const void* dout, int64_t dout_row_stride,
+                        const float* mean_rstd, float* dy, void* dz, int64_t dz_row_stride,
+                        float* dln_weight_partial, float* dln_bias_partial, int32_t n_partials, int32_t batch,
+                        int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, int32_t H, int32_t W,
+                        ss2d_stream_t stream) {
+  if (!ys || !z || !dout || !mean_rstd || !dy || !dz || !dln_weight_partial || !dln_bias_partial) return SS2D_ERR_NULL_POINTER;
+  int rc = group_gate_check(G, plane_of, batch, D, L, H, W, z_dtype, out_dtype, true);
+  if (rc != SS2D_OK) return rc;
+  if (n_partials != epi_bwd_partials(batch, L)) return SS2D_ERR_WORKSPACE;
+  cudaError_t e = group_gate_bwd_launch(ys, G, plane_of, transposed_planes, ln_weight, ln_bias, z, z_row_stride, z_col0,
+                                        z_group_stride, dout, dout_row_stride, mean_rstd, dy, dz, dz_row_stride,
+                                        dln_weight_partial, dln_bias_partial, n_partials, batch, D, L, z_dtype, out_dtype, H, W,
+                                        static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
   return SS2D_OK;

@@ -3,6 +3,8 @@
 // act(z) and `y * z` of /root/reference/gm-unet/model/gm/ss2d.py:486-498, 506-508, 515-517 (5-6 kernels and as
 // many round trips through HBM) with one pass: read ys (K planes) and z once, write out once.
 // HBM-bound; a CTA owns 32 pixels x all D channels (tile staged in shared memory for the transpose).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ss2d {
@@ -17,14 +19,26 @@ constexpr int kEpiMaxDPT = 4;     // channels per thread in the backward: D <= 1
 // A tile is 32 pixels: a 1 x 32 run of the flattened image when every plane is in natural order, a 4 x 8 (h x w) patch
 // when some planes are transposed, so that both orders are read in contiguous pieces (32 B and 16 B).
 struct PlaneIdx {
-  int L, H, W; unsigned tmask; int tiles_w;     // tiles_w: patches per image row (patch mode only)
+  int L, H, W; unsigned tmask; int tiles_w;     // tiles_w: patches per image row (patch mode only; 0 = linear tiles)
   __device__ __forceinline__ int pixel(int tile_in_batch, int px) const {   // -> flattened natural index or -1
-    if (!tmask) { const int l = tile_in_batch * kEpiTL + px; return l < L ? l : -1; }
+    if (!tiles_w) { const int l = tile_in_batch * kEpiTL + px; return l < L ? l : -1; }
     const int th = tile_in_batch / tiles_w, tw = tile_in_batch - th * tiles_w;
     const int h = th * 4 + (px >> 3), w = tw * 8 + (px & 7);
     return (h < H && w < W) ? h * W + w : -1;
   }
 };
+// Grouped calls (blockIdx.y = group): the G single-direction SS2Ds of a GroupMambaLayer (groupmamba.py:143-149) share one
+// launch. Group g reads its K planes at ys + ys_off[g] (per batch: ys_bs), its LayerNorm parameters at lnw + g D, its gate
+// at column z_off[g] of a z row, and writes / reads columns io_off[g] ... + D of the out / dout rows (row stride io_rs): the
+// concatenation of the G outputs (groupmamba.py:149) is just where the columns land. G = 1 with zero offsets is the plain call.
+struct EpiGroups {
+  int G;
+  int64_t ys_bs, dy_bs, io_rs;
+  int64_t ys_off[SS2D_MAX_EPI_GROUPS], dy_off[SS2D_MAX_EPI_GROUPS], z_off[SS2D_MAX_EPI_GROUPS];
+  int io_off[SS2D_MAX_EPI_GROUPS];
+  unsigned tmask[SS2D_MAX_EPI_GROUPS];
+};
+
 __device__ __forceinline__ float merge_k(const float* __restrict__ ys, int K, int64_t plane_stride, int64_t row_off, int l,
                                          const PlaneIdx pi) {
   int lt = l;
@@ -48,9 +62,9 @@ __device__ __forceinline__ float silu_grad_f(float x) {
 
 // loads the merged tile y[d][pix] for pixels [l0, l0+32) of batch b into s_y[d * 33 + pix]
 __device__ __forceinline__ void load_merged_tile(float* s_y, const float* __restrict__ ys, int K, int b, int D, int L,
-                                                 int tib, const PlaneIdx pi) {
+                                                 int tib, const PlaneIdx pi, int64_t ys_bs) {
   const int64_t plane = (int64_t)D * L;
-  const float* base = ys + (int64_t)b * K * plane;
+  const float* base = ys + (int64_t)b * ys_bs;
   // unrolled by 4: 4 K independent loads in flight per thread (with one element per iteration the kernel ran at 1.5 TB/s)
 #pragma unroll 4
   for (int i = threadIdx.x; i < D * kEpiTL; i += kEpiThreads) {
@@ -64,14 +78,21 @@ __global__ void __launch_bounds__(kEpiThreads)
 out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict__ lnw, const float* __restrict__ lnb,
                     const void* __restrict__ z, int64_t z_rs, int z_act, void* __restrict__ out,
                     float* __restrict__ mean_rstd, int batch, int D, int L, float eps, int z_dtype, int out_dtype,
-                    int tiles_per_batch, PlaneIdx pi) {
+                    int tiles_per_batch, PlaneIdx pi, const EpiGroups eg) {
   extern __shared__ float s_y[];                 // [D][33]
   __shared__ float s_stat[kEpiTL][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gi = blockIdx.y;
+  ys += eg.ys_off[gi];
+  if (lnw) lnw += gi * D;
+  if (lnb) lnb += gi * D;
+  if (mean_rstd) mean_rstd += (int64_t)gi * batch * L * 2;
+  pi.tmask = eg.tmask[gi];
+  const int64_t zo = eg.z_off[gi], oo = eg.io_off[gi];
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
     const int b = tile / tiles_per_batch, tib = tile - b * tiles_per_batch;
     __syncthreads();
-    load_merged_tile(s_y, ys, K, b, D, L, tib, pi);
+    load_merged_tile(s_y, ys, K, b, D, L, tib, pi, eg.ys_bs);
     __syncthreads();
     // LayerNorm statistics per pixel (two-pass, fp32): warp w handles pixels w, w+8, ...
     for (int px = warp; px < kEpiTL; px += kEpiThreads / 32) {
@@ -104,11 +125,11 @@ out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       float o = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
       o = lnw ? fmaf(o, __ldg(lnw + d), lnb ? __ldg(lnb + d) : 0.f) : o;
       if (z) {
-        float zz = load1(z, ((int64_t)b * L + l) * z_rs + d, z_dtype);
+        float zz = load1(z, ((int64_t)b * L + l) * z_rs + zo + d, z_dtype);
         if (z_act) zz = silu_f(zz);
         o *= zz;
       }
-      store1(out, ((int64_t)b * L + l) * D + d, out_dtype, o);
+      store1(out, ((int64_t)b * L + l) * eg.io_rs + oo + d, out_dtype, o);
     }
   }
 }
@@ -118,7 +139,17 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
                     const void* __restrict__ z, int64_t z_rs, int z_act, const void* __restrict__ dout,
                     const float* __restrict__ mean_rstd, float* __restrict__ dy, void* __restrict__ dz, int64_t dz_rs,
                     float* __restrict__ dw_part, float* __restrict__ db_part, int batch, int D, int L, int z_dtype,
-                    int out_dtype, int tiles_per_batch, PlaneIdx pi) {
+                    int out_dtype, int tiles_per_batch, PlaneIdx pi, const EpiGroups eg) {
+  const int gi = blockIdx.y;
+  ys += eg.ys_off[gi];
+  dy += eg.dy_off[gi];
+  if (lnw) lnw += gi * D;
+  if (lnb) lnb += gi * D;
+  mean_rstd += (int64_t)gi * batch * L * 2;
+  dw_part += (int64_t)gi * gridDim.x * D;
+  db_part += (int64_t)gi * gridDim.x * D;
+  pi.tmask = eg.tmask[gi];
+  const int64_t zo = eg.z_off[gi], oo = eg.io_off[gi];
   extern __shared__ float smem[];
   float* s_y = smem;                               // [D][33] merged y, then dy
   float* s_g = s_y + (size_t)D * (kEpiTL + 1);     // [D][33] d(yn) = dout * gate * w
@@ -133,7 +164,7 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
   for (int tile = blockIdx.x; tile < batch * tiles_per_batch; tile += gridDim.x) {
     const int b = tile / tiles_per_batch, tib = tile - b * tiles_per_batch;
     __syncthreads();
-    load_merged_tile(s_y, ys, K, b, D, L, tib, pi);
+    load_merged_tile(s_y, ys, K, b, D, L, tib, pi, eg.ys_bs);
     for (int px = threadIdx.x; px < kEpiTL; px += kEpiThreads) {
       const int l = pi.pixel(tib, px);
       s_stat[px][0] = l >= 0 ? mean_rstd[((int64_t)b * L + l) * 2 + 0] : 0.f;
@@ -152,11 +183,11 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
         const float yn = (s_y[d * (kEpiTL + 1) + px] - s_stat[px][0]) * s_stat[px][1];
         const float w = lnw ? __ldg(lnw + d) : 1.f;
         const float lin = lnw ? fmaf(yn, w, lnb ? __ldg(lnb + d) : 0.f) : yn;
-        float go = load1(dout, ((int64_t)b * L + l) * D + d, out_dtype);
+        float go = load1(dout, ((int64_t)b * L + l) * eg.io_rs + oo + d, out_dtype);
         if (z) {
-          const float zr = load1(z, ((int64_t)b * L + l) * z_rs + d, z_dtype);
+          const float zr = load1(z, ((int64_t)b * L + l) * z_rs + zo + d, z_dtype);
           const float gate = z_act ? silu_f(zr) : zr;
-          if (dz) store1(dz, ((int64_t)b * L + l) * dz_rs + d, z_dtype, go * lin * (z_act ? silu_grad_f(zr) : 1.f));
+          if (dz) store1(dz, ((int64_t)b * L + l) * dz_rs + zo + d, z_dtype, go * lin * (z_act ? silu_grad_f(zr) : 1.f));
           go *= gate;
         }
         acc_dw[m] = fmaf(go, yn, acc_dw[m]);
@@ -203,7 +234,7 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       // K == 1: the gradient belongs to the single plane and is written in ITS pixel order (transposed when tmask is set)
       int lo = l;
       if (K == 1 && pi.tmask) { const int h = l / pi.W, w = l - h * pi.W; lo = w * pi.H + h; }
-      dy[((int64_t)b * D + d) * L + lo] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
+      dy[(int64_t)b * eg.dy_bs + (int64_t)d * L + lo] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
     }
   }
   if (PP == 1) {
@@ -267,7 +298,14 @@ __global__ void __launch_bounds__(kEpiThreads)
 out_gate_fwd_small_kernel(const float* __restrict__ ys, const float* __restrict__ lnw, const float* __restrict__ lnb,
                           const void* __restrict__ z, int64_t z_rs, int z_act, void* __restrict__ out,
                           float* __restrict__ mean_rstd, int batch, int D, int L, float eps, int z_dtype, int out_dtype,
-                          int H, int W, int transposed) {
+                          int H, int W, const EpiGroups eg) {
+  const int gi = blockIdx.y;
+  ys += eg.ys_off[gi];
+  if (lnw) lnw += gi * D;
+  if (lnb) lnb += gi * D;
+  if (mean_rstd) mean_rstd += (int64_t)gi * batch * L * 2;
+  const int transposed = (int)(eg.tmask[gi] & 1u);
+  const int64_t zo = eg.z_off[gi], oo = eg.io_off[gi];
   const int64_t total = (int64_t)batch * L;
   for (int64_t idx = (int64_t)blockIdx.x * kEpiThreads + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * kEpiThreads) {
     const int b = (int)(idx / L), lp = (int)(idx - (int64_t)b * L);          // pixel in plane order
@@ -276,7 +314,7 @@ out_gate_fwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
     float y[DP];
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < DP; ++d) { y[d] = d < D ? __ldg(ys + ((int64_t)b * D + d) * L + lp) : 0.f; s += y[d]; }
+    for (int d = 0; d < DP; ++d) { y[d] = d < D ? __ldg(ys + (int64_t)b * eg.ys_bs + (int64_t)d * L + lp) : 0.f; s += y[d]; }
     const float mean = s / D;
     float v = 0.f;
 #pragma unroll
@@ -285,7 +323,7 @@ out_gate_fwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
     const int64_t row = (int64_t)b * L + l;
     if (mean_rstd) { mean_rstd[row * 2] = mean; mean_rstd[row * 2 + 1] = rstd; }
     float zz[DP];
-    if (z) row_load<DP>(z, row * z_rs, z_dtype, D, zz);
+    if (z) row_load<DP>(z, row * z_rs + zo, z_dtype, D, zz);
 #pragma unroll
     for (int d = 0; d < DP; ++d) {
       if (d < D) {
@@ -295,7 +333,7 @@ out_gate_fwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
         y[d] = o;
       }
     }
-    row_store<DP>(out, row * D, out_dtype, D, y);
+    row_store<DP>(out, row * eg.io_rs + oo, out_dtype, D, y);
   }
 }
 
@@ -305,7 +343,17 @@ out_gate_bwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
                           const void* __restrict__ z, int64_t z_rs, int z_act, const void* __restrict__ dout,
                           const float* __restrict__ mean_rstd, float* __restrict__ dy, void* __restrict__ dz, int64_t dz_rs,
                           float* __restrict__ dw_part, float* __restrict__ db_part, int batch, int D, int L, int z_dtype,
-                          int out_dtype, int H, int W, int transposed) {
+                          int out_dtype, int H, int W, const EpiGroups eg) {
+  const int gi = blockIdx.y;
+  ys += eg.ys_off[gi];
+  dy += eg.dy_off[gi];
+  if (lnw) lnw += gi * D;
+  if (lnb) lnb += gi * D;
+  mean_rstd += (int64_t)gi * batch * L * 2;
+  dw_part += (int64_t)gi * gridDim.x * D;
+  db_part += (int64_t)gi * gridDim.x * D;
+  const int transposed = (int)(eg.tmask[gi] & 1u);
+  const int64_t zo = eg.z_off[gi], oo = eg.io_off[gi];
   __shared__ float s_red[kEpiThreads / 32][2 * DP];
   float acc_dw[DP], acc_db[DP];
 #pragma unroll
@@ -318,13 +366,13 @@ out_gate_bwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
     const int64_t row = (int64_t)b * L + l;
     const float mean = mean_rstd[row * 2], rstd = mean_rstd[row * 2 + 1];
     float g[DP], yn[DP], zz[DP];
-    row_load<DP>(dout, row * D, out_dtype, D, g);
-    if (z) row_load<DP>(z, row * z_rs, z_dtype, D, zz);
+    row_load<DP>(dout, row * eg.io_rs + oo, out_dtype, D, g);
+    if (z) row_load<DP>(z, row * z_rs + zo, z_dtype, D, zz);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int d = 0; d < DP; ++d) {
       if (d < D) {
-        yn[d] = (__ldg(ys + ((int64_t)b * D + d) * L + lp) - mean) * rstd;
+        yn[d] = (__ldg(ys + (int64_t)b * eg.ys_bs + (int64_t)d * L + lp) - mean) * rstd;
         const float w = lnw ? __ldg(lnw + d) : 1.f;
         const float lin = lnw ? fmaf(yn[d], w, lnb ? __ldg(lnb + d) : 0.f) : yn[d];
         float go = g[d];
@@ -340,12 +388,12 @@ out_gate_bwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
         s2 = fmaf(g[d], yn[d], s2);
       } else { g[d] = 0.f; yn[d] = 0.f; }
     }
-    if (z && dz) row_store<DP>(dz, row * dz_rs, z_dtype, D, zz);
+    if (z && dz) row_store<DP>(dz, row * dz_rs + zo, z_dtype, D, zz);
     s1 /= D; s2 /= D;
     // gradient of the single plane, written in ITS pixel order (coalesced across the warp)
 #pragma unroll
     for (int d = 0; d < DP; ++d)
-      if (d < D) dy[((int64_t)b * D + d) * L + lp] = rstd * (g[d] - s1 - yn[d] * s2);
+      if (d < D) dy[(int64_t)b * eg.dy_bs + (int64_t)d * L + lp] = rstd * (g[d] - s1 - yn[d] * s2);
   }
   // LayerNorm weight / bias gradients: warp butterflies, then the block's warps through shared memory
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -367,8 +415,8 @@ out_gate_bwd_small_kernel(const float* __restrict__ ys, const float* __restrict_
 
 static bool epi_small(int K, int D) { return K == 1 && D <= 32; }
 
-static int epi_tiles_per_batch(int L, int H, int W, unsigned tmask) {
-  return tmask ? ((H + 3) / 4) * ((W + 7) / 8) : (L + kEpiTL - 1) / kEpiTL;
+static int epi_tiles_per_batch(int L, int H, int W, bool patch) {
+  return patch ? ((H + 3) / 4) * ((W + 7) / 8) : (L + kEpiTL - 1) / kEpiTL;
 }
 int epi_bwd_partials(int batch, int L) {     // an upper bound that does not depend on the tiling mode
   const int tiles = batch * ((L + kEpiTL - 1) / kEpiTL);
@@ -376,56 +424,122 @@ int epi_bwd_partials(int batch, int L) {     // an upper bound that does not dep
 }
 int epi_max_D(bool backward) { return backward ? 832 : 1664; }   // keeps the tile(s) within 227 KB of shared memory
 
-cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
-                                int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
-                                int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
+static bool epi_any_transposed(const EpiGroups& eg) {
+  for (int g = 0; g < eg.G; ++g) if (eg.tmask[g]) return true;
+  return false;
+}
+
+static cudaError_t epi_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                  int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
+                                  int out_dtype, int H, int W, const EpiGroups& eg, cudaStream_t stream) {
   if (epi_small(K, D)) {
     const int64_t total = (int64_t)batch * L;
-    const int grid = (int)((total + kEpiThreads - 1) / kEpiThreads < 148 * 8 ? (total + kEpiThreads - 1) / kEpiThreads : 148 * 8);
+    const int cap = 148 * 8 / eg.G > 0 ? 148 * 8 / eg.G : 1;
+    dim3 grid((unsigned)((total + kEpiThreads - 1) / kEpiThreads < cap ? (total + kEpiThreads - 1) / kEpiThreads : cap), eg.G);
     if (D <= 16)
       out_gate_fwd_small_kernel<16><<<grid, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
-                                                                       eps, z_dtype, out_dtype, H, W, (int)(tmask & 1u));
+                                                                       eps, z_dtype, out_dtype, H, W, eg);
     else
       out_gate_fwd_small_kernel<32><<<grid, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
-                                                                       eps, z_dtype, out_dtype, H, W, (int)(tmask & 1u));
+                                                                       eps, z_dtype, out_dtype, H, W, eg);
     return cudaGetLastError();
   }
   const size_t smem = (size_t)D * (kEpiTL + 1) * 4;
   cudaError_t e = cudaFuncSetAttribute(out_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const int tpb = epi_tiles_per_batch(L, H, W, tmask);
+  const bool patch = epi_any_transposed(eg);
+  const int tpb = epi_tiles_per_batch(L, H, W, patch);
   const int tiles = batch * tpb;
-  const int grid = tiles < 148 * 8 ? tiles : 148 * 8;
-  const PlaneIdx pi{L, H, W, tmask, tmask ? (W + 7) / 8 : 0};
+  const int cap = 148 * 8 / eg.G > 0 ? 148 * 8 / eg.G : 1;
+  dim3 grid((unsigned)(tiles < cap ? tiles : cap), eg.G);
+  const PlaneIdx pi{L, H, W, 0u, patch ? (W + 7) / 8 : 0};
   out_gate_fwd_kernel<<<grid, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L,
-                                                          eps, z_dtype, out_dtype, tpb, pi);
+                                                          eps, z_dtype, out_dtype, tpb, pi, eg);
   return cudaGetLastError();
+}
+
+static cudaError_t epi_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                  int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
+                                  float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
+                                  int out_dtype, int H, int W, const EpiGroups& eg, cudaStream_t stream) {
+  dim3 grid((unsigned)n_partials, eg.G);
+  if (epi_small(K, D)) {
+    if (D <= 16)
+      out_gate_bwd_small_kernel<16><<<grid, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
+                                                                       dz_rs, dw_part, db_part, batch, D, L, z_dtype,
+                                                                       out_dtype, H, W, eg);
+    else
+      out_gate_bwd_small_kernel<32><<<grid, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
+                                                                       dz_rs, dw_part, db_part, batch, D, L, z_dtype,
+                                                                       out_dtype, H, W, eg);
+    return cudaGetLastError();
+  }
+  const size_t smem = (size_t)2 * D * (kEpiTL + 1) * 4;
+  cudaError_t e = cudaFuncSetAttribute(out_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const bool patch = epi_any_transposed(eg);
+  const int tpb = epi_tiles_per_batch(L, H, W, patch);
+  const PlaneIdx pi{L, H, W, 0u, patch ? (W + 7) / 8 : 0};
+  out_gate_bwd_kernel<<<grid, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
+                                                          dz_rs, dw_part, db_part, batch, D, L, z_dtype, out_dtype,
+                                                          tpb, pi, eg);
+  return cudaGetLastError();
+}
+
+static EpiGroups epi_single(int K, int D, int L, unsigned tmask) {
+  EpiGroups eg;
+  memset(&eg, 0, sizeof(eg));
+  eg.G = 1; eg.ys_bs = (int64_t)K * D * L; eg.dy_bs = (int64_t)D * L; eg.io_rs = D; eg.tmask[0] = tmask;
+  return eg;
+}
+
+cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
+                                int z_act, void* out, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
+                                int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
+  return epi_fwd_launch(ys, K, lnw, lnb, z, z_rs, z_act, out, mean_rstd, batch, D, L, eps, z_dtype, out_dtype, H, W,
+                        epi_single(K, D, L, tmask), stream);
 }
 
 cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
                                 int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
                                 int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
-  if (epi_small(K, D)) {
-    if (D <= 16)
-      out_gate_bwd_small_kernel<16><<<n_partials, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
-                                                                             dz_rs, dw_part, db_part, batch, D, L, z_dtype,
-                                                                             out_dtype, H, W, (int)(tmask & 1u));
-    else
-      out_gate_bwd_small_kernel<32><<<n_partials, kEpiThreads, 0, stream>>>(ys, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
-                                                                             dz_rs, dw_part, db_part, batch, D, L, z_dtype,
-                                                                             out_dtype, H, W, (int)(tmask & 1u));
-    return cudaGetLastError();
+  return epi_bwd_launch(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz, dz_rs, dw_part, db_part, n_partials, batch, D,
+                        L, z_dtype, out_dtype, H, W, epi_single(K, D, L, tmask), stream);
+}
+
+// G single-plane groups in one launch: ys (batch, G, D, L) with group g in plane plane_of[g]; out / dout / z / dz rows hold the
+// G groups side by side (columns g D ... of rows of io_rs / z_rs / dz_rs elements; z and dz start at column z_col0 + g z_gs).
+static EpiGroups epi_grouped(int G, int D, int L, const int* plane_of, unsigned tmask_bits, int64_t io_rs, int64_t z_col0,
+                             int64_t z_gs) {
+  EpiGroups eg;
+  memset(&eg, 0, sizeof(eg));
+  eg.G = G; eg.ys_bs = (int64_t)G * D * L; eg.dy_bs = (int64_t)G * D * L; eg.io_rs = io_rs;
+  for (int g = 0; g < G; ++g) {
+    eg.ys_off[g] = (int64_t)plane_of[g] * D * L;
+    eg.dy_off[g] = eg.ys_off[g];
+    eg.z_off[g] = z_col0 + g * z_gs;
+    eg.io_off[g] = g * D;
+    eg.tmask[g] = (tmask_bits >> plane_of[g]) & 1u;
   }
-  const size_t smem = (size_t)2 * D * (kEpiTL + 1) * 4;
-  cudaError_t e = cudaFuncSetAttribute(out_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  const int tpb = epi_tiles_per_batch(L, H, W, tmask);
-  const PlaneIdx pi{L, H, W, tmask, tmask ? (W + 7) / 8 : 0};
-  out_gate_bwd_kernel<<<n_partials, kEpiThreads, smem, stream>>>(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz,
-                                                                dz_rs, dw_part, db_part, batch, D, L, z_dtype, out_dtype,
-                                                                tpb, pi);
-  return cudaGetLastError();
+  return eg;
+}
+
+cudaError_t group_gate_fwd_launch(const float* ys, int G, const int* plane_of, unsigned tmask_bits, const float* lnw,
+                                  const float* lnb, const void* z, int64_t z_rs, int64_t z_col0, int64_t z_gs, void* out,
+                                  int64_t out_rs, float* mean_rstd, int batch, int D, int L, float eps, int z_dtype,
+                                  int out_dtype, int H, int W, cudaStream_t stream) {
+  return epi_fwd_launch(ys, 1, lnw, lnb, z, z_rs, 1, out, mean_rstd, batch, D, L, eps, z_dtype, out_dtype, H, W,
+                        epi_grouped(G, D, L, plane_of, tmask_bits, out_rs, z_col0, z_gs), stream);
+}
+
+cudaError_t group_gate_bwd_launch(const float* ys, int G, const int* plane_of, unsigned tmask_bits, const float* lnw,
+                                  const float* lnb, const void* z, int64_t z_rs, int64_t z_col0, int64_t z_gs, const void* dout,
+                                  int64_t dout_rs, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs, float* dw_part,
+                                  float* db_part, int n_partials, int batch, int D, int L, int z_dtype, int out_dtype, int H,
+                                  int W, cudaStream_t stream) {
+  return epi_bwd_launch(ys, 1, lnw, lnb, z, z_rs, 1, dout, mean_rstd, dy, dz, dz_rs, dw_part, db_part, n_partials, batch, D, L,
+                        z_dtype, out_dtype, H, W, epi_grouped(G, D, L, plane_of, tmask_bits, dout_rs, z_col0, z_gs), stream);
 }
 
 }  // namespace ss2d

@@ -199,6 +199,80 @@ class _OutGate(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+class _GroupGate(torch.autograd.Function):
+    """The epilogues of the four single-direction SS2Ds of a GroupMambaLayer in one launch (ops.group_gate_fwd/bwd):
+    per group out_norm LayerNorm(D) + SiLU(z) gate (ss2d.py:498, 515-517), un-transposition of the column-major planes,
+    (B,D,L)->(B,L,D), and the concatenation over the groups (groupmamba.py:149) as the column placement of the stores."""
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, ys, ln_w, ln_b, z, eps, out_dtype, H, W, plane_of, tbits):
+        out, stats = ops.group_gate_fwd(ys, plane_of, tbits, ln_w, ln_b, z, eps, out_dtype, (H, W))
+        ctx.meta = (H, W, tuple(plane_of), tbits)
+        ctx.save_for_backward(ys, ln_w, ln_b, z, stats)
+        return out
+
+    @staticmethod
+    @_custom_bwd
+    def backward(ctx, dout):
+        ys, ln_w, ln_b, z, stats = ctx.saved_tensors
+        H, W, plane_of, tbits = ctx.meta
+        dy, dz, dw, db = ops.group_gate_bwd(ys, plane_of, tbits, ln_w, ln_b, z, dout, stats, (H, W))
+        return dy, dw, db, dz, None, None, None, None, None, None
+
+
+class _InProjSplit(torch.autograd.Function):
+    """x_all, z_all = xn @ Wx^T, xn @ Wz^T for block-structured (C, C) weights: the four in_proj layers of a GroupMambaLayer
+    (ss2d.py:504-506) as two GEMMs whose outputs are separate dense tensors, so that neither the split nor its backward costs
+    a pass over memory (a chunk() of one GEMM output would: slice_backward zero-fills and copies). Library GEMMs under the
+    ambient autocast; the backward accumulates the two input-gradient products inside the second GEMM."""
+
+    @staticmethod
+    def forward(ctx, xn, Wx, Wz):
+        ctx.save_for_backward(xn, Wx, Wz)
+        return torch.nn.functional.linear(xn, Wx), torch.nn.functional.linear(xn, Wz)
+
+    @staticmethod
+    def backward(ctx, dx, dz):
+        xn, Wx, Wz = ctx.saved_tensors
+        C = Wx.shape[1]
+        dx2, dz2, x2 = dx.reshape(-1, Wx.shape[0]), dz.reshape(-1, Wz.shape[0]), xn.reshape(-1, C)
+        dxn = dWx = dWz = None
+        if ctx.needs_input_grad[0]:
+            acc = torch.matmul(dx2, Wx.to(dx2.dtype))
+            acc.addmm_(dz2.to(acc.dtype), Wz.to(acc.dtype))
+            dxn = acc.view(xn.shape).to(xn.dtype)
+        if ctx.needs_input_grad[1]:
+            dWx = torch.matmul(dx2.t(), x2.to(dx2.dtype)).to(Wx.dtype)
+        if ctx.needs_input_grad[2]:
+            dWz = torch.matmul(dz2.t(), x2.to(dz2.dtype)).to(Wz.dtype)
+        return dxn, dWx, dWz
+
+
+class _ToPlanes(torch.autograd.Function):
+    """(B, H, W, 4 D) channels-last, channel blocks in PLANE order -> (B, 4 D, H, W) channel-major with the last two blocks
+    TRANSPOSED (stored as (W, H) images; H == W): the NHWC->NCHW copy of ss2d.py:510 for the four SS2Ds at once, with the
+    transposition that turns the column-major scans 2 / 4 into row-major scans folded into the same copy."""
+
+    @staticmethod
+    def forward(ctx, x, D2):
+        Bn, H, W, C = x.shape
+        out = torch.empty((Bn, C, H, W), dtype=x.dtype, device=x.device)
+        out[:, :D2].copy_(x[..., :D2].permute(0, 3, 1, 2))
+        out[:, D2:].copy_(x[..., D2:].permute(0, 3, 2, 1))
+        ctx.D2 = D2
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        D2 = ctx.D2
+        Bn, C, H, W = dout.shape
+        dx = torch.empty((Bn, H, W, C), dtype=dout.dtype, device=dout.device)
+        dx[..., :D2].copy_(dout[:, :D2].permute(0, 2, 3, 1))
+        dx[..., D2:].copy_(dout[:, D2:].permute(0, 3, 2, 1))
+        return dx, None
+
+
 # ---- small projections with a tall-skinny weight gradient -------------------------------------------
 _TS_MIN_ROWS = 8192      # below this a library GEMM is as good (measured on the four GM-UNet stage shapes)
 

@@ -213,6 +213,60 @@ class GroupMambaLayer(nn.Module):
         self.proj = nn.Linear(input_dim, output_dim)
         self.skip_scale = nn.Parameter(torch.ones(1))
 
+    # plane p of the grouped tensors holds group _PLANES[p]: the two row-major directions first (natural pixel order), then the
+    # two column-major ones (stored transposed, where they are row-major too); the permutation is its own inverse
+    _PLANES = (0, 2, 1, 3)
+    grouped = True          # False: run the four SS2D modules one after the other (the reference's own sequence of calls)
+
+    def _can_group(self, x, H, W) -> bool:
+        ms = [self.mamba_g1, self.mamba_g2, self.mamba_g3, self.mamba_g4]
+        m0 = ms[0]
+        return (self.grouped and H == W and x.is_cuda and m0.with_dconv and m0.k_group == 1 and not m0.disable_force32
+                and m0.in_proj.bias is None and m0.out_proj.bias is None and isinstance(m0.dropout, nn.Identity)
+                and m0.conv2d.kernel_size == (3, 3) and m0.conv2d.bias is not None
+                and m0.d_inner <= Fn.ops.out_gate_max_D(backward=torch.is_grad_enabled()))
+
+    def _ss2d_grouped(self, xn, H, W):
+        """The four single-direction SS2Ds (ss2d.py:502-519, called at groupmamba.py:143-146) as ONE pipeline: block-structured
+        projections, one depthwise convolution, one scan launch (G = 4, one direction per group), one epilogue launch that
+        also concatenates. xn: (B, L, C) normalised input -> (B, L, C) = cat_g SS2D_g(xn_g)."""
+        ms = [self.mamba_g1, self.mamba_g2, self.mamba_g3, self.mamba_g4]
+        PL = self._PLANES
+        Bn, L, C = xn.shape
+        D, N, R = ms[0].d_inner, ms[0].d_state, ms[0].dt_rank
+        # in_proj of the four groups (ss2d.py:504): x part with its output blocks in plane order, z part in group order
+        w_in = [m.in_proj.weight for m in ms]                                       # (2 D, C / 4) each
+        Cq = C // 4
+        Wx = torch.cat([F.pad(w_in[g][:D], (g * Cq, (3 - g) * Cq)) for g in PL])    # row block p = group PL[p], its own input columns
+        Wz = torch.block_diag(*[w[D:] for w in w_in])
+        x_all, z_all = Fn._InProjSplit.apply(xn, Wx, Wz)                            # (B, L, 4 D) each
+        u = Fn._ToPlanes.apply(x_all.view(Bn, H, W, 4 * D), 2 * D)                  # (B, 4 D, H, W), planes 2, 3 transposed (:510)
+        # depthwise 3 x 3 (:512): a transposed image is convolved with the transposed kernel
+        Wc = torch.cat([ms[PL[0]].conv2d.weight, ms[PL[1]].conv2d.weight,
+                        ms[PL[2]].conv2d.weight.transpose(2, 3), ms[PL[3]].conv2d.weight.transpose(2, 3)])
+        bc = torch.cat([ms[g].conv2d.bias for g in PL])
+        if Bn * L >= Fn._TS_MIN_ROWS:
+            u = Fn._DWConv3.apply(u, Wc, bc)
+        else:
+            u = F.conv2d(u, Wc, bc, padding=1, groups=4 * D)
+        u = F.silu(u).view(Bn, 4 * D, L)                                            # :513
+        # x_proj / dt_proj (:465-469) as two block-structured GEMMs from u: delta = (W_dt W_x[:R]) u and [B; C] = W_x[R:] u
+        wxp = [ms[g].x_proj_weight[0] for g in PL]                                  # (R + 2 N, D)
+        W_dt = torch.block_diag(*[torch.matmul(ms[g].dt_projs_weight[0], wx[:R]) for g, wx in zip(PL, wxp)])     # (4 D, 4 D)
+        W_bc = torch.block_diag(*[wx[R:] for wx in wxp])                            # (4 * 2 N, 4 D)
+        dts = Fn.proj_cm(W_dt.to(u.dtype), u)                                       # (B, 4 D, L)
+        BC = Fn.proj_cm(W_bc.to(u.dtype), u).view(Bn, 4, 2 * N, L)
+        As = -torch.exp(torch.cat([ms[g].A_logs for g in PL]).float())              # :473
+        Ds = torch.cat([ms[g].Ds for g in PL]).float()
+        bias = torch.cat([ms[g].dt_projs_bias.reshape(-1) for g in PL]).float()
+        uf, dts, BC = u.float().contiguous(), dts.float(), BC.float()               # force_fp32 (:479-480)
+        ys = Fn._SS2DScanNatural.apply(uf, dts, As, BC[:, :, :N], BC[:, :, N:], Ds, bias, H, W, (1, 3, 1, 3), 4)
+        lnw = torch.stack([m.out_norm.weight for m in ms]).float()
+        lnb = torch.stack([m.out_norm.bias for m in ms]).float()
+        y = Fn._GroupGate.apply(ys.view(Bn, 4, D, L), lnw, lnb, z_all.contiguous(), ms[0].out_norm.eps, u.dtype, H, W, PL, 0b1100)
+        W_out = torch.block_diag(*[m.out_proj.weight for m in ms])                  # (C, 4 D)  (:518)
+        return Fn.linear_ts(y, W_out, None)
+
     def forward(self, x, H, W):
         if x.dtype == torch.float16:
             x = x.type(torch.float32)
@@ -220,11 +274,15 @@ class GroupMambaLayer(nn.Module):
         x = Fn.layer_norm_rows(x, self.norm.weight, self.norm.bias, self.norm.eps)   # :131 (row-wise LN kernel)
         aff = self.sigmoid(self.fc2(self.relu(self.fc1(x.mean(dim=1)))))        # :134-137 channel affinity
         x4 = x.view(Bn, H, W, C)
-        parts = torch.chunk(x4, 4, dim=-1)
-        pairs = ((Fn.CrossScan_1, Fn.CrossMerge_1), (Fn.CrossScan_2, Fn.CrossMerge_2),
-                 (Fn.CrossScan_3, Fn.CrossMerge_3), (Fn.CrossScan_4, Fn.CrossMerge_4))
-        outs = [getattr(self, f"mamba_g{i + 1}")(parts[i], CrossScan=pairs[i][0], CrossMerge=pairs[i][1]) for i in range(4)]
-        xm = torch.cat(outs, dim=-1) * self.skip_scale * x4                     # :149
+        if self._can_group(x, H, W):
+            ycat = self._ss2d_grouped(x, H, W).view(Bn, H, W, C)
+        else:
+            parts = torch.chunk(x4, 4, dim=-1)
+            pairs = ((Fn.CrossScan_1, Fn.CrossMerge_1), (Fn.CrossScan_2, Fn.CrossMerge_2),
+                     (Fn.CrossScan_3, Fn.CrossMerge_3), (Fn.CrossScan_4, Fn.CrossMerge_4))
+            outs = [getattr(self, f"mamba_g{i + 1}")(parts[i], CrossScan=pairs[i][0], CrossMerge=pairs[i][1]) for i in range(4)]
+            ycat = torch.cat(outs, dim=-1)
+        xm = ycat * self.skip_scale * x4                                        # :149
         xm = xm.view(Bn, L, C) * aff.unsqueeze(1)                               # :154
         xm = Fn.layer_norm_rows(xm, self.norm.weight, self.norm.bias, self.norm.eps)   # :156 (same LayerNorm, shared weights)
         return Fn.linear_ts(xm, self.proj.weight, self.proj.bias)               # :157

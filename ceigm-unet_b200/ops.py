@@ -273,6 +273,44 @@ def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[t
     return dy, sums[0], sums[1]
 
 
+# ---- grouped epilogue: the four SS2Ds of a GroupMambaLayer in one launch ------------------------------
+def group_gate_fwd(ys, plane_of, tbits: int, ln_w, ln_b, z, eps: float, out_dtype, hw):
+    """ys (B, G, D, L) fp32 planes (group g in plane plane_of[g]; bit p of tbits: plane p in transposed pixel order);
+    ln_w / ln_b (G, D) fp32; z (B, L, G*D) raw gates, contiguous -> out (B, L, G*D) = concat_g LN_g(ys_g) * SiLU(z_g), stats."""
+    _require(ys.is_cuda and ys.dtype == torch.float32 and ys.is_contiguous() and ys.dim() == 4, "ys must be contiguous CUDA fp32 (B, G, D, L)")
+    Bn, G, D, L = ys.shape
+    _require(z.is_contiguous() and tuple(z.shape) == (Bn, L, G * D) and z.dtype in _DT, "z must be a contiguous (B, L, G*D) tensor")
+    _require(ln_w.is_contiguous() and ln_b.is_contiguous() and tuple(ln_w.shape) == (G, D), "ln_w / ln_b must be (G, D)")
+    out = torch.empty((Bn, L, G * D), dtype=out_dtype, device=ys.device)
+    stats = torch.empty((G, Bn, L, 2), dtype=torch.float32, device=ys.device)
+    arr = (ctypes.c_int32 * G)(*[int(p) for p in plane_of])
+    with torch.cuda.device(ys.device):
+        rc = _lib.lib().ss2d_group_gate_fwd(_ptr(ys), G, arr, ctypes.c_uint32(tbits), _ptr(ln_w), _ptr(ln_b), _ptr(z), G * D, 0, D,
+                                            _ptr(out), G * D, _ptr(stats), Bn, D, L, ctypes.c_float(eps), _DT[z.dtype],
+                                            _DT[out_dtype], int(hw[0]), int(hw[1]), _stream(ys.device))
+    _lib.check(rc, "ss2d_group_gate_fwd")
+    return out, stats
+
+
+def group_gate_bwd(ys, plane_of, tbits: int, ln_w, ln_b, z, dout, stats, hw):
+    """-> dy (B, G, D, L) fp32 (plane p in its own pixel order), dz (B, L, G*D) like z, dln_w (G, D), dln_b (G, D)."""
+    Bn, G, D, L = ys.shape
+    dout = dout.contiguous()
+    dy = torch.empty((Bn, G, D, L), dtype=torch.float32, device=ys.device)
+    dz = torch.empty_like(z)
+    npart = int(_lib.lib().ss2d_out_gate_bwd_partials(Bn, L))
+    part = torch.empty((2, G, npart, D), dtype=torch.float32, device=ys.device)
+    arr = (ctypes.c_int32 * G)(*[int(p) for p in plane_of])
+    with torch.cuda.device(ys.device):
+        rc = _lib.lib().ss2d_group_gate_bwd(_ptr(ys), G, arr, ctypes.c_uint32(tbits), _ptr(ln_w), _ptr(ln_b), _ptr(z), G * D, 0, D,
+                                            _ptr(dout), G * D, _ptr(stats), _ptr(dy), _ptr(dz), G * D, _ptr(part[0]),
+                                            _ptr(part[1]), npart, Bn, D, L, _DT[z.dtype], _DT[dout.dtype], int(hw[0]),
+                                            int(hw[1]), _stream(ys.device))
+    _lib.check(rc, "ss2d_group_gate_bwd")
+    sums = part.sum(dim=2)
+    return dy, dz, sums[0], sums[1]
+
+
 # ---- tall-skinny weight gradient ---------------------------------------------------------------
 def wgrad_ts_supported(M: int, N: int) -> bool:
     return 0 < M <= 256 and 0 < N <= 256 and ((M + 3) // 4) * ((N + 3) // 4) <= 256

@@ -54,6 +54,8 @@ typedef enum { SS2D_LAYOUT_SCAN = 0, SS2D_LAYOUT_NATURAL = 1 } ss2d_layout;
 
 #define SS2D_MAX_DSTATE 256
 #define SS2D_MAX_GROUP_DIRS 8
+/* groups of one grouped epilogue call (the four SS2Ds of a GroupMambaLayer) */
+#define SS2D_MAX_EPI_GROUPS 4
 /* checkpoint interval of the chunked scan (elements of L between saved states) */
 #define SS2D_CHUNK 32
 
@@ -165,6 +167,29 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                       int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, int32_t H, int32_t W,
                       uint32_t transposed_mask, ss2d_stream_t stream);
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
+
+/* ---- grouped epilogue: the G single-direction SS2Ds of one GroupMambaLayer in one launch ---------------------
+ * (model/gm/groupmamba.py:143-149: four SS2D modules on channel quarters, outputs concatenated along C.)
+ * ys: fp32 (batch, G, D, L) scan outputs, one plane per group; group g's plane is plane_of[g]; bit p of transposed_planes:
+ *     plane p is stored in the pixel order of the TRANSPOSED image (column-major directions run as row-major scans of it).
+ * ln_weight / ln_bias: fp32 (G, D) — each group's own out_norm (ss2d.py:498). z: rows of z_row_stride elements; group g's
+ * D gate values start at column z_col0 + g * z_group_stride of a row (raw, SiLU applied here: ss2d.py:506-508, 517).
+ * out: (batch, L, ...) rows of out_row_stride elements; group g writes columns g*D ... g*D + D - 1 — the concatenation.
+ * mean_rstd: fp32 (G, batch, L, 2), kept for the backward.
+ * backward: dy fp32 (batch, G, D, L), plane p in plane p's own pixel order; dz has z's column layout and its own row stride;
+ * dln_*_partial: fp32 (G, n_partials, D) with n_partials = ss2d_out_gate_bwd_partials(batch, L), summed by the caller. */
+int ss2d_group_gate_fwd(const float* ys, int32_t G, const int32_t* plane_of, uint32_t transposed_planes,
+                        const float* ln_weight, const float* ln_bias, const void* z, int64_t z_row_stride,
+                        int64_t z_col0, int64_t z_group_stride, void* out, int64_t out_row_stride, float* mean_rstd,
+                        int32_t batch, int32_t D, int32_t L, float eps, int32_t z_dtype, int32_t out_dtype, int32_t H,
+                        int32_t W, ss2d_stream_t stream);
+int ss2d_group_gate_bwd(const float* ys, int32_t G, const int32_t* plane_of, uint32_t transposed_planes,
+                        const float* ln_weight, const float* ln_bias, const void* z, int64_t z_row_stride,
+                        int64_t z_col0, int64_t z_group_stride, const void* dout, int64_t dout_row_stride,
+                        const float* mean_rstd, float* dy, void* dz, int64_t dz_row_stride,
+                        float* dln_weight_partial, float* dln_bias_partial, int32_t n_partials, int32_t batch,
+                        int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, int32_t H, int32_t W,
+                        ss2d_stream_t stream);
 
 /* ---- weight / bias gradient of SS2D's depthwise 3 x 3 convolution -----------------------------------
  * dweight[c][ky][kx] = sum_(b,h,w) dy[b,c,h,w] * x[b,c,h+ky-1,w+kx-1] (zero padding 1), dbias[c] = sum dy[b,c,h,w]:

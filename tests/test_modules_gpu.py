@@ -282,3 +282,33 @@ def test_second_device_launches_with_opted_in_shared_memory():
         torch.cuda.synchronize(dev)
         outs.append((o.detach().cpu(), a["u"].grad.cpu()))
     assert torch.allclose(outs[0][0], outs[1][0], atol=1e-5) and torch.allclose(outs[0][1], outs[1][1], atol=1e-5)
+
+
+@pytest.mark.parametrize("C,H", [(64, 56), (348, 14), (448, 7), (32, 6)])
+def test_grouped_layer_equals_the_four_separate_ss2ds(C, H):
+    """GroupMambaLayer's grouped pipeline (block-structured projections, one conv, one G = 4 scan launch, one grouped
+    epilogue launch) against the same module running its four SS2Ds one after the other (grouped = False)."""
+    import copy
+
+    import ceigm_unet_b200 as P
+    torch.manual_seed(C + H)
+    a = P.GroupMambaLayer(C, C).cuda()
+    with torch.no_grad():
+        for n, p_ in a.named_parameters():
+            if "norm" in n or n == "skip_scale":
+                p_.add_(0.1 * torch.randn_like(p_))
+    b = copy.deepcopy(a)
+    b.grouped = False
+    x = torch.randn(2, H * H, C, device="cuda")
+    gy = torch.randn(2, H * H, C, device="cuda")
+    res = []
+    for m in (a, b):
+        xi = x.clone().requires_grad_(True)
+        y = m(xi, H, H)
+        y.backward(gy)
+        res.append((y.detach(), xi.grad, {n: p_.grad for n, p_ in m.named_parameters()}))
+    (y1, gx1, gp1), (y2, gx2, gp2) = res
+    assert rel_err(y1, y2.cpu().numpy()) < 1e-4
+    assert rel_err(gx1, gx2.cpu().numpy()) < 1e-4
+    for n in gp1:
+        assert rel_err(gp1[n], gp2[n].cpu().numpy()) < 5e-4, n
