@@ -16,7 +16,8 @@ Workloads (`--workload`):
   vm_d192 (default)  K=4 directions, d_state N=16, D=192 (Dt=768), L=56^2, batch 24, fp32 — the north-star
                      SS2D regime on the stage-1 map of a 224^2 Synapse slice at the config-2 batch.
   vm_d96 / vm_d384 / vm_d768_l112 ... other points of BASELINE config 4.
-  gm_live            the 104 single-direction N=1 scan calls of one GM-UNet forward+backward at batch 24.
+  gm_live            the 104 single-direction N=1 scan calls of one GM-UNet forward+backward at batch 24
+                     (gm_live_g4: the same scans as 26 grouped G=4 calls, the way the fused GroupMambaLayer issues them).
 Multi-GPU: the batch is sharded, every rank runs an independent replica of the per-GPU workload (weak scaling,
 no data-path collective — SURVEY.md §8e); the timed region is bracketed by barrier + synchronize and the
 slowest rank's device time is used.
@@ -53,6 +54,8 @@ for _i, (_c, _b, _d, _l, _n, _g) in enumerate(WORKLOADS["gm_live"], 1):
     WORKLOADS[f"gm_s{_i}"] = [(1, _b, _d, _l, _n, _g)]
     WORKLOADS[f"gm_s{_i}_g4"] = [(1, _b, 4 * _d, _l, _n, 4)]
 WORKLOADS["gm_s1_b64_512"] = [(1, 64, 64, 16384, 1, 4)]
+# the same 104 scans as the fused GroupMambaLayer issues them: the four SS2Ds of a layer in one G = 4 launch (26 calls)
+WORKLOADS["gm_live_g4"] = [(c // 4, b, 4 * d, l, n, 4) for c, b, d, l, n, g in WORKLOADS["gm_live"]]
 # small-batch points of the north-star shape (BASELINE config 1 runs batch 1): grid-fill regime
 WORKLOADS["vm_d192_b1"] = [(1, 1, 768, 3136, 16, 4)]
 WORKLOADS["vm_d192_b2"] = [(1, 2, 768, 3136, 16, 4)]
@@ -201,18 +204,18 @@ def run_ours(args, rank, world, local_rank):
         bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
         ach = bwd_b / (bwd_ms * 1e-3) / 1e9
         if all(c[4] == 1 for c in calls):
-            kname = "scan_par_bwd_kernel"
+            kname = "scan_n1_bwd_rows_kernel"
         elif all(8 < c[4] <= 16 for c in calls):
             kname = "scan_bwd2_kernel"         # fp32 + TMA fast path (csrc/scan_bwd2.cu)
         else:
             kname = "scan_bwd_kernel"
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 for key, rec in json.load(f).items():
                     if key.startswith(kname) and key.endswith("@ " + args.workload):
-                        traffic, traffic_src = rec["traffic"], f"profiles/r1_traffic.json ({rec['report']}, dram read+write of one launch)"
+                        traffic, traffic_src = rec["traffic"], f"profiles/r2_traffic.json ({rec['report']}, dram read+write of one launch)"
         roofline = {"bound": "hbm", "kernel": kname + " (+ finalize and dB/dC memsets inside the bwd call)",
                     "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                     "traffic": traffic, "traffic_source": traffic_src, "alg_bytes_per_launch": bwd_b, "peak_source": peak_src,
@@ -322,7 +325,7 @@ def other_workloads(core, device, peak, exclude):
     224^2 batch-24 training step, one layer's grouped call, the 512^2 batch-64 stage-1 shape of config 5), and — when
     baseline/_ref/ext holds it — the REFERENCE's own CUDA kernel recompiled for sm_100 on the same box and inputs."""
     out = []
-    names = [n for n in SWEEP_CONFIG4 if n != exclude] + ["vm_d192_b1", "vm_d192_b2", "gm_live", "gm_s1_g4", "gm_s1_b64_512"]
+    names = [n for n in SWEEP_CONFIG4 if n != exclude] + ["vm_d192_b1", "vm_d192_b2", "gm_live", "gm_live_g4", "gm_s1_g4", "gm_s1_b64_512"]
     ref_ext = None
     try:
         from harness import refmodel
@@ -341,7 +344,7 @@ def other_workloads(core, device, peak, exclude):
             rec.update({"fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms, 4), "fwd_GBps": round(fb / ms_f / 1e6, 1),
                         "fwd_bwd_GBps": round((fb + bb) / ms / 1e6, 1), "frac_of_hbm_peak": round((fb + bb) / ms / 1e6 / peak, 4),
                         "timing": "CUDA graph replay"})
-            if name == "gm_live":
+            if name in ("gm_live", "gm_live_g4"):
                 rec["scan_only_slices_per_s"] = round(calls[0][1] / (ms * 1e-3), 1)
         if ref_ext is not None and name in ref_points:
             try:

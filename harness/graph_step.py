@@ -56,61 +56,84 @@ def make_capturable() -> None:
 
 
 class GraphedTrainStep:
-    """Same contract as workloads.TrainStep (`step(x_host, y_host) -> loss`), replayed from CUDA graphs."""
+    """Same contract as workloads.TrainStep (`step(x_host, y_host) -> loss`), replayed from CUDA graphs.
+
+    world > 1: graph A = forward + loss + backward + ONE concatenation of every gradient into a flat fp32 buffer; then the
+    NCCL all-reduce (mean) of that buffer, eagerly, between the graphs; graph B = AdamW reading its gradients as views of the
+    flat buffer. (Accumulating into bucket views inside the captured backward, the way the eager GradReducer works, costs one
+    extra add kernel per parameter — 1 100 of them, 7 ms per step.)"""
 
     def __init__(self, net, batch, size, num_classes=9, lr=5e-4, weight_decay=1e-3, amp_dtype=torch.bfloat16,
-                 reducer=None, warmup_iters=3):
+                 world=1, warmup_iters=3):
         self.net = net.train()
         self.device = next(net.parameters()).device
         self.crit = refmodel.load_losses().DiceCELoss(ce_weight=0.4, dc_weight=0.6)
-        self.opt = torch.optim.AdamW(net.parameters(), lr=lr, weight_decay=weight_decay, eps=1e-8, betas=(0.9, 0.999),
-                                     capturable=True)
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, eps=1e-8, betas=(0.9, 0.999), capturable=True)
         self.amp_dtype = amp_dtype
-        self.reducer = reducer
+        self.world = world
         self.x = torch.zeros(batch, 3, size, size, device=self.device)
         self.y = torch.zeros(batch, 1, size, size, device=self.device)
-        if reducer is not None:
-            reducer.defer = True          # hooks must not launch collectives while the backward is being captured
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=self.device) if world > 1 else None
+        self.allreduce_bytes = self.flat.numel() * 4 if world > 1 else 0
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):     # warm-up off the capture: cuDNN autotuning, lazy handles, optimizer state
             for _ in range(warmup_iters):
                 self._fwd_bwd()
-                if reducer is not None:
-                    reducer.finish()
+                self._reduce_eager_grads()
                 self.opt.step()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.g_fb = torch.cuda.CUDAGraph()
-        if reducer is None:
-            self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.g_fb):
             self.loss = self._fwd_bwd()
-            if reducer is None:
+            if world == 1:
                 self.opt.step()
+            else:
+                zero = None
+                pieces = []
+                for p in self.params:
+                    if p.grad is None:      # parameter outside this step's graph: contributes zeros
+                        zero = torch.zeros(max(q.numel() for q in self.params), device=self.device) if zero is None else zero
+                        pieces.append(zero[:p.numel()])
+                    else:
+                        pieces.append(p.grad.reshape(-1))
+                torch.cat(pieces, out=self.flat)
         self.g_opt = None
-        if reducer is not None:
+        if world > 1:
+            off = 0
+            for p in self.params:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt):
                 self.opt.step()
 
+    def _reduce_eager_grads(self):
+        if self.world > 1:
+            for p in self.params:
+                if p.grad is not None:
+                    torch.distributed.all_reduce(p.grad, op=torch.distributed.ReduceOp.AVG)
+
     def _fwd_bwd(self):
-        if self.reducer is not None:
-            self.reducer.zero_grad()
-        else:
-            self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             pred = self.net(self.x)
             loss = self.crit(pred.float(), self.y)
         loss.backward()
         return loss
 
+    def allreduce(self):
+        torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)
+
     def __call__(self, x_host, y_host) -> float:
         self.x.copy_(x_host, non_blocking=True)
         self.y.copy_(y_host, non_blocking=True)
         self.g_fb.replay()
-        if self.reducer is not None:
-            self.reducer.finish()
+        if self.world > 1:
+            self.allreduce()
             self.g_opt.replay()
         return float(self.loss.item())
 

@@ -83,14 +83,14 @@ def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_clas
     import ceigm_unet_b200 as pkg
     from ceigm_unet_b200 import dist as D
     net = build(num_classes, level, device)
-    reducer = D.GradReducer(net) if world > 1 else None
+    reducer = D.GradReducer(net) if world > 1 and not graphs else None
     if world > 1:      # same initial weights on every rank, as DDP's constructor broadcast does
         for p in list(net.parameters()) + list(net.buffers()):
             torch.distributed.broadcast(p.data, src=0)
     if graphs:
         from . import graph_step
         graph_step.make_capturable()
-        step = graph_step.GraphedTrainStep(net, per_gpu_batch, size, num_classes, amp_dtype=amp_dtype, reducer=reducer,
+        step = graph_step.GraphedTrainStep(net, per_gpu_batch, size, num_classes, amp_dtype=amp_dtype, world=world,
                                            weight_decay=weight_decay)
     else:
         step = TrainStep(net, num_classes, amp_dtype=amp_dtype, reducer=reducer, weight_decay=weight_decay)
@@ -112,16 +112,18 @@ def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_clas
     launches = pkg.launch_count()
     # all-reduce alone (same buckets, nothing to overlap with) for its share of the step
     ar_ms = None
-    if reducer is not None:
+    if world > 1:
+        one_allreduce = reducer.finish if reducer is not None else step.allreduce
         _sync_all(world, device)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(3):
-            reducer.finish()
+            one_allreduce()
         a1.record()
         _sync_all(world, device)
         ar_ms = D.max_over_ranks(a0.elapsed_time(a1), device) / 3
-        reducer.remove()
+        if reducer is not None:
+            reducer.remove()
     out = {"slices_per_s": round(world * per_gpu_batch / (ms * 1e-3), 2), "ms_per_step": round(ms, 2),
            "wall_ms_per_step": round(wall / steps * 1e3, 2), "per_gpu_batch": per_gpu_batch, "size": size,
            "num_classes": num_classes, "level": level, "cuda_graphs": bool(graphs), "amp": str(amp_dtype).replace("torch.", "") if amp_dtype else "fp32",
@@ -129,8 +131,9 @@ def train_bench(device, rank=0, world=1, *, per_gpu_batch=24, size=224, num_clas
            "ss2d_launches_per_step": launches // steps,
            "h2d_bytes_per_step": x.numel() * 4 + y.numel() * 4, "d2h_bytes_per_step": 4,
            "optimizer": "AdamW lr 5e-4", "loss": "DiceCELoss(0.4, 0.6)"}
-    if reducer is not None:
-        out["allreduce"] = {"bytes": reducer.bytes, "buckets": len(reducer.buckets), "alone_ms": round(ar_ms, 3),
+    if world > 1:
+        out["allreduce"] = {"bytes": reducer.bytes if reducer is not None else step.allreduce_bytes,
+                            "buckets": len(reducer.buckets) if reducer is not None else 1, "alone_ms": round(ar_ms, 3),
                             "share_of_step_if_exposed": round(ar_ms / ms, 4), "backend": torch.distributed.get_backend(),
                             "overlapped_with_backward": not graphs}
     del step, net
