@@ -82,6 +82,13 @@ __device__ __forceinline__ void tma_load_4d32(uint32_t dst, const void* tmap, in
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void red_add2(float* dst, float a, float c) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(a), "f"(c) : "memory");
+}
+__device__ __forceinline__ float2 sel2(bool c, float2 a, float2 b) { return make_float2(c ? a.x : b.x, c ? a.y : b.y); }
+__device__ __forceinline__ float2 shfl2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
 __device__ __forceinline__ int atom_add_acqrel32(uint32_t addr, int v) {
   int old;
   asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
@@ -112,6 +119,7 @@ struct B2ReduceScatter {
   }
 };
 
+template <bool SOFTPLUS>
 __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanParams p, const __grid_constant__ Bwd2Maps maps) {
   extern __shared__ __align__(16) unsigned char smem_rawb2[];
   unsigned char* smem = smem_rawb2 + ((1024 - (smem_u32(smem_rawb2) & 1023)) & 1023);
@@ -172,12 +180,13 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   }
 
   const int q = lane & 7, rp = lane >> 3;
+  const int sw = rp >> 1;              // the upper two row pairs hold their two states in swapped order (see the dB / dC sum)
   const bool v0 = 2 * rp < rows_valid, v1 = 2 * rp + 1 < rows_valid;
-  // main role: row pair rp, states n_j = q + 8 j
+  // main role: row pair rp, states n_j = q + 8 (j ^ sw)
   float2 A2p[2], carry2[2], dA2[2];      // A2 = A log2(e)
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const int n = q + 8 * j;
+    const int n = q + 8 * (j ^ sw);
     const bool okn = n < p.N;
     A2p[j].x = (okn && v0) ? p.A[(int64_t)(d0 + 2 * rp) * p.A_ld + n] * kLog2e : 0.f;
     A2p[j].y = (okn && v1) ? p.A[(int64_t)(d0 + 2 * rp + 1) * p.A_ld + n] * kLog2e : 0.f;
@@ -193,10 +202,9 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
   float2 biasp;
   biasp.x = (p.bias && v0) ? p.bias[d0 + 2 * rp] : 0.f;
   biasp.y = (p.bias && v1) ? p.bias[d0 + 2 * rp + 1] : 0.f;
-  const bool softplus = p.softplus != 0;
   // shared-memory offsets as (lane constant) ^ (uniform term): one LOP3 per access inside the loops
   const int rowc = (rp * 256) | (rp << 4);                                   // b2_p_off(rp, ch) = rowc ^ (su(ch) << 4)
-  const int qc = (q * 128) | (q << 4);                                       // b2_t_off(q + 8 j, c4) = (qc ^ (c4 << 4)) + 1024 j
+  const int qc0 = ((q * 128) | (q << 4)) + 1024 * sw, qc1 = qc0 ^ 1024;     // b2_t_off(n_j, c4) = qcj ^ (c4 << 4)
   // The finisher's scalar slot, kept in an opaque register: at the 128-register cap ptxas otherwise re-derives it from
   // %tid in every group.
   uint32_t pk;
@@ -204,13 +212,16 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
     const uint32_t v = (rowc ^ ((fe >> 1) << 4)) | (((fe & 1) * 2 + rr) * 4);
     asm volatile("mov.b32 %0, %1;" : "=r"(pk) : "r"(v));
   }
-  // dB / dC destination of this lane: tensor rp >> 1, state q (state q + 8 lies 8 L further)
-  float* const red_lane = ((rp >> 1) == 0 ? p.dB : p.dC) + ((int64_t)(b * p.G + g) * p.A_ld + q) * L;
+  // dB / dC destination of this lane after the sum over the row-pair lanes: state n_0 = q + 8 sw, both tensors,
+  // positions 2 (rp & 1), + 1 of every group. Lanes of padded states (n_0 >= N: B = C = 0 there, zero-filled by TMA, so
+  // their totals are exactly 0) add their zeros to the last real state instead of being predicated off.
+  float* const red_B = p.dB + ((int64_t)(b * p.G + g) * p.A_ld + min(q + 8 * sw, p.N - 1)) * L;
+  const int64_t red_CmB = p.dC - p.dB;
 
   auto load_ckpt = [&](int t, float2* h) {     // state before tile t = checkpoint at the end of tile t - 1
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int n = q + 8 * j;
+      const int n = q + 8 * (j ^ sw);
       const bool ok = t > 0 && n < p.N;
       h[j].x = (ok && v0) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp) * p.nck + (t - 1)) * p.N + n) : 0.f;
       h[j].y = (ok && v1) ? __ldg(p.ckpt_in + (((int64_t)b * p.dim + d0 + 2 * rp + 1) * p.nck + (t - 1)) * p.N + n) : 0.f;
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float x = f4_at(dv[r], e) + (r == 0 ? biasp.x : biasp.y);
-            if (softplus) x = softplus20(x);
+            if (SOFTPLUS) x = softplus20(x);
             const bool live = q * 4 + e < len && (r == 0 ? v0 : v1);
             dl[r][e] = live ? x : 0.f;
             du[r][e] = live ? x * f4_at(uv[r], e) : 0.f;
@@ -272,21 +283,31 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
       const uint32_t a_B = a_bc + s * B2_BC_STAGE;
 
       // ---- (1) forward recompute of h over the tile from the chunk checkpoint; the state after each of the first
-      //          7 groups is parked in shared memory. 
+      //          7 groups is parked in shared memory. Fully unrolled, with the loads of group gi + 1 requested before the
+      //          arithmetic of group gi (the shared-memory accessors are volatile: ptxas keeps their order).
       {
         float2 h[2] = {h0[0], h0[1]};
         sts128(a_hs + 7 * 512, make_float4(h0[0].x, h0[0].y, h0[1].x, h0[1].y));     // read back by the last group (gi = 0)
-#pragma unroll 1
-        for (int gi = 0; gi < 7; ++gi) {
+        struct FwdIn { float4 d01, d23, u01, u23, B0, B1; };
+        auto fwd_load = [&](const int gi) {
+          FwdIn r;
           const uint32_t pa = a_dl + (rowc ^ (((2 * gi ^ (gi >> 2)) & 15) << 4));
-          const float4 d01 = lds128(pa), d23 = lds128(pa ^ 16);
-          const float4 u01 = lds128(pa + 1024), u23 = lds128((pa ^ 16) + 1024);
-          const float2 dl2[4] = {make_float2(d01.x, d01.y), make_float2(d01.z, d01.w), make_float2(d23.x, d23.y), make_float2(d23.z, d23.w)};
-          const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
-          const uint32_t ba = a_B + (qc ^ ((REVV ? 7 - gi : gi) << 4));
+          const int gsh = (REVV ? 7 - gi : gi) << 4;
+          r.d01 = lds128(pa); r.d23 = lds128(pa ^ 16);
+          r.u01 = lds128(pa + 1024); r.u23 = lds128((pa ^ 16) + 1024);
+          r.B0 = lds128(a_B + (qc0 ^ gsh)); r.B1 = lds128(a_B + (qc1 ^ gsh));
+          return r;
+        };
+        FwdIn cur = fwd_load(0);
+#pragma unroll
+        for (int gi = 0; gi < 7; ++gi) {
+          FwdIn nxt = cur;
+          if (gi < 6) nxt = fwd_load(gi + 1);
+          const float2 dl2[4] = {make_float2(cur.d01.x, cur.d01.y), make_float2(cur.d01.z, cur.d01.w), make_float2(cur.d23.x, cur.d23.y), make_float2(cur.d23.z, cur.d23.w)};
+          const float2 du2[4] = {make_float2(cur.u01.x, cur.u01.y), make_float2(cur.u01.z, cur.u01.w), make_float2(cur.u23.x, cur.u23.y), make_float2(cur.u23.z, cur.u23.w)};
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            float4 Bq = lds128(ba + 1024 * j);
+            float4 Bq = j == 0 ? cur.B0 : cur.B1;
             if (REVV) Bq = make_float4(Bq.w, Bq.z, Bq.y, Bq.x);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -297,33 +318,36 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
             }
           }
           sts128(a_hs + gi * 512, make_float4(h[0].x, h[0].y, h[1].x, h[1].y));
+          cur = nxt;
         }
       }
 
       // ---- (2) groups of 4 positions, last to first: re-expand a and h, run the adjoint recurrence ----
       // unrolled by 4: the swizzle / parity terms of a group become constants and the tail of one group overlaps the
-      // head of the next (1.234 -> 1.180 ms; by 8 the instruction cache gives it back: 1.258 ms)
+      // head of the next
+      float* red_t = red_B + (REVV ? L - 2 - (l0 + 2 * (rp & 1)) : l0 + 2 * (rp & 1));
+      asm volatile("mov.b64 %0, %0;" : "+l"(red_t));       // kept as one 64-bit register pair; the groups add immediates
 #pragma unroll 4
       for (int gi = 7; gi >= 0; --gi) {
         const int su4 = ((2 * gi ^ (gi >> 2)) & 15) << 4;
         const uint32_t pa = a_dl + (rowc ^ su4);
+        const int gsh = (REVV ? 7 - gi : gi) << 4;
         const float4 d01 = lds128(pa), d23 = lds128(pa ^ 16);
         const float4 u01 = lds128(pa + 1024), u23 = lds128((pa ^ 16) + 1024);
         const float4 y01 = lds128(pa + 2048), y23 = lds128((pa ^ 16) + 2048);
+        const float4 hin4 = lds128(a_hs + ((gi + 7) & 7) * 512);   // state before the group; slot 7 holds the tile's entry state
+        const float4 Bq1 = lds128(a_B + (qc1 ^ gsh)), Cq1 = lds128(a_B + 2048 + (qc1 ^ gsh));
+        // the finisher's scalars (row 2 rp + rr, position fe of this group), requested long before their use
+        const uint32_t foff = pk ^ su4;
+        const float de = lds32(a_dl + foff), dyv = lds32(a_dy + foff), uu = lds32(a_up + foff);
         const float2 dl2[4] = {make_float2(d01.x, d01.y), make_float2(d01.z, d01.w), make_float2(d23.x, d23.y), make_float2(d23.z, d23.w)};
         const float2 du2[4] = {make_float2(u01.x, u01.y), make_float2(u01.z, u01.w), make_float2(u23.x, u23.y), make_float2(u23.z, u23.w)};
         const float2 dy2[4] = {make_float2(y01.x, y01.y), make_float2(y01.z, y01.w), make_float2(y23.x, y23.y), make_float2(y23.z, y23.w)};
-        float4 hin4;
-        hin4 = lds128(a_hs + ((gi + 7) & 7) * 512);       // state before the group; slot 7 holds the tile's entry state
-        const uint32_t ba = a_B + (qc ^ ((REVV ? 7 - gi : gi) << 4));
         float2 sB2[4], sA2[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { sB2[e] = make_float2(0.f, 0.f); sA2[e] = make_float2(0.f, 0.f); }
-        float pout[2][2];                                // after the row-pair-lane reduction: [j][2 positions]
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          float4 Bq = lds128(ba + 1024 * j);
-          float4 Cq = lds128(ba + 2048 + 1024 * j);
+        // one state of the lane: part = [dB (e0, e1) | dB (e2, e3) | dC (e0, e1) | dC (e2, e3)], the two rows of the pair added
+        auto state_pass = [&](const int j, float4 Bq, float4 Cq, float2* part) {
           if (REVV) { Bq = make_float4(Bq.w, Bq.z, Bq.y, Bq.x); Cq = make_float4(Cq.w, Cq.z, Cq.y, Cq.x); }
           const float2 hprev = j == 0 ? make_float2(hin4.x, hin4.y) : make_float2(hin4.z, hin4.w);
           float2 a2[4], hh2[4];
@@ -335,7 +359,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
             hh2[e] = __ffma2_rn(a2[e], e == 0 ? hprev : hh2[e - 1], __fmul2_rn(du2[e], make_float2(be, be)));
           }
           float2 carry = carry2[j];
-          float part[8];                                 // [dB | dC][e], the two rows of the pair already added
+          float sb[4], sc[4];
 #pragma unroll
           for (int e = 3; e >= 0; --e) {
             const float be = f4_at(Bq, e), ce = f4_at(Cq, e);
@@ -344,35 +368,64 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
             carry = t2;
             const float2 pb = __fmul2_rn(g2, du2[e]);
             const float2 pc = __fmul2_rn(dy2[e], hh2[e]);
-            part[e] = pb.x + pb.y;
-            part[4 + e] = pc.x + pc.y;
+            sb[e] = pb.x + pb.y;
+            sc[e] = pc.x + pc.y;
             sB2[e] = __ffma2_rn(g2, make_float2(be, be), sB2[e]);
             const float2 w2 = __fmul2_rn(t2, e == 0 ? hprev : hh2[e - 1]);        // g_e (h_e - delta u B_e)
             sA2[e] = __ffma2_rn(w2, A2p[j], sA2[e]);                           // scaled by log2(e): undone below
             dA2[j] = __ffma2_rn(w2, dl2[e], dA2[j]);
           }
           carry2[j] = carry;
-          // sum over the 4 row-pair lanes: lane (rp, q) keeps positions 2 (rp & 1), + 1 of tensor rp >> 1, state q + 8 j
-          B2ReduceScatter<8, 8, 2>::run(part, rp);
-          pout[j][0] = part[0]; pout[j][1] = part[1];
-        }
-        // ---- sum over the 8 state lanes; lane q ends up with (sB, sA) of row parity q >> 2, position q & 3 ----
-        float vals[16];                                  // [row parity][e][sB | sA]
+          part[0] = make_float2(sb[0], sb[1]); part[1] = make_float2(sb[2], sb[3]);
+          part[2] = make_float2(sc[0], sc[1]); part[3] = make_float2(sc[2], sc[3]);
+        };
+        // ---- sum over the 4 row-pair lanes (dB, dC). The lanes of row pairs 2, 3 hold their states in swapped order, so the
+        //      first exchange (lane ^ 16) needs no selects: every lane sends its local state 1 and keeps its local state 0 —
+        //      the same global state n_0 = q + 8 sw on both sides. The second (lane ^ 8) splits the positions. ----
+        float2 p0[4], p1[4], r1[4];
+        state_pass(1, Bq1, Cq1, p1);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          vals[e * 2] = sB2[e].x; vals[e * 2 + 1] = sA2[e].x;
-          vals[8 + e * 2] = sB2[e].y; vals[8 + e * 2 + 1] = sA2[e].y;
-        }
-        B2ReduceScatter<1, 16, 4>::run(vals, q);
+        for (int i = 0; i < 4; ++i)
+          r1[i] = make_float2(__shfl_xor_sync(0xffffffffu, p1[i].x, 16), __shfl_xor_sync(0xffffffffu, p1[i].y, 16));
         {
-          const uint32_t off = pk ^ su4;
-          const float de = lds32(a_dl + off);
-          const float dyv = lds32(a_dy + off);
-          const float uu = lds32(a_up + off);
-          const float sBe = vals[0], sAe = vals[1] * kLn2;
+          const float4 Bq0 = lds128(a_B + (qc0 ^ gsh)), Cq0 = lds128(a_B + 2048 + (qc0 ^ gsh));
+          state_pass(0, Bq0, Cq0, p0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p0[i] = __fadd2_rn(p0[i], r1[i]);
+        float2 oB, oC;                  // positions 2 (rp & 1), + 1 of the group, state n_0, summed over the warp's 8 rows
+        {
+          const bool up = (rp & 1) != 0;
+          oB = __fadd2_rn(sel2(up, p0[1], p0[0]), shfl2(sel2(up, p0[0], p0[1]), 8));
+          oC = __fadd2_rn(sel2(up, p0[3], p0[2]), shfl2(sel2(up, p0[2], p0[3]), 8));
+        }
+        // this warp's totals go straight to global memory: two red.global.add.v2.f32 per lane (the branch is warp-uniform:
+        // idle warps, and the groups past the end of the sequence in its last tile)
+        if (rows_valid > 0 && 4 * gi < len) {
+          float* const dst = red_t + (REVV ? -4 * gi : 4 * gi);
+          red_add2(dst, REVV ? oB.y : oB.x, REVV ? oB.x : oB.y);
+          red_add2(dst + red_CmB, REVV ? oC.y : oC.x, REVV ? oC.x : oC.y);
+        }
+        // ---- sum over the 8 state lanes on row-packed pairs: positions first (lane bits 0, 1), the row parity last; lane q ends
+        //      up with (sB, sA) of row parity q >> 2, position q & 3 ----
+        float sBe, sAe;
+        {
+          const bool b0 = (q & 1) != 0, b1 = (q & 2) != 0, b2 = (q & 4) != 0;
+          float2 RB[2], RA[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            RB[k] = __fadd2_rn(sel2(b0, sB2[2 * k + 1], sB2[2 * k]), shfl2(sel2(b0, sB2[2 * k], sB2[2 * k + 1]), 1));
+            RA[k] = __fadd2_rn(sel2(b0, sA2[2 * k + 1], sA2[2 * k]), shfl2(sel2(b0, sA2[2 * k], sA2[2 * k + 1]), 1));
+          }
+          const float2 SB = __fadd2_rn(sel2(b1, RB[1], RB[0]), shfl2(sel2(b1, RB[0], RB[1]), 2));
+          const float2 SA = __fadd2_rn(sel2(b1, RA[1], RA[0]), shfl2(sel2(b1, RA[0], RA[1]), 2));
+          sBe = (b2 ? SB.y : SB.x) + __shfl_xor_sync(0xffffffffu, b2 ? SB.x : SB.y, 4);
+          sAe = ((b2 ? SA.y : SA.x) + __shfl_xor_sync(0xffffffffu, b2 ? SA.x : SA.y, 4)) * kLn2;
+        }
+        {
           const float du_out = fmaf(Dr, dyv, de * sBe);
           float ddl = fmaf(uu, sBe, sAe);
-          if (softplus) {   // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
+          if (SOFTPLUS) {   // sigmoid(raw) = 1 - exp(-softplus(raw)); series for small delta avoids cancellation
             const float sig = de < 0.015625f ? de * (1.f - de * (0.5f - de * 0.16666667f)) : 1.f - ex2f(-de * kLog2e);
             ddl *= sig;
           }
@@ -380,23 +433,8 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
           dDacc = fmaf(dyv, uu, dDacc);
           dbacc += ddl;
           // every lane of the row pair has consumed this group's delta' / dout' (the shuffles above ordered them)
-          sts32(a_dy + off, du_out);
-          sts32(a_dl + off, ddl);
-        }
-        // ---- dB / dC: this warp's totals go straight to global memory, one red.global.add.v2.f32 per lane and state
-        //      (lane (rp, q): tensor rp >> 1, positions 2 (rp & 1), + 1 of the group, states q and q + 8) ----
-        {
-          const int l = l0 + gi * 4 + 2 * (rp & 1);
-          if (rows_valid > 0 && l < L) {
-            float* dst = red_lane + (REVV ? L - 2 - l : l);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              if (q + 8 * j < p.N) {
-                const float a = REVV ? pout[j][1] : pout[j][0], c = REVV ? pout[j][0] : pout[j][1];
-                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + (int64_t)8 * j * L), "f"(a), "f"(c) : "memory");
-              }
-            }
-          }
+          sts32(a_dy + foff, du_out);
+          sts32(a_dl + foff, ddl);
         }
       }
       __syncwarp();
@@ -449,7 +487,7 @@ __global__ void __launch_bounds__(B2_NW * 32, 4) scan_bwd2_kernel(const ScanPara
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int n = q + 8 * j;
+      const int n = q + 8 * (j ^ sw);
       if (n < p.N) {
         if (v0) p.part[((int64_t)b * p.dim + d0 + 2 * rp) * (p.N + 2) + n] = dA2[j].x;
         if (v1) p.part[((int64_t)b * p.dim + d0 + 2 * rp + 1) * (p.N + 2) + n] = dA2[j].y;
@@ -484,13 +522,16 @@ bool scan_bwd2_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   Bwd2Maps maps;
   if (!bwd2_maps(p, &maps)) return false;
 
-  static PerDeviceOnce once;
+  static PerDeviceOnce once, once_nosp;
   {
-    cudaError_t e = func_attr_once(once, reinterpret_cast<const void*>(scan_bwd2_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
+    cudaError_t e = func_attr_once(once, reinterpret_cast<const void*>(scan_bwd2_kernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
+    if (e == cudaSuccess)
+      e = func_attr_once(once_nosp, reinterpret_cast<const void*>(scan_bwd2_kernel<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM);
     if (e != cudaSuccess) { *err = e; return true; }
   }
   dim3 grid((p.dpg + B2_CH - 1) / B2_CH, p.G, p.batch);
-  scan_bwd2_kernel<<<grid, B2_NW * 32, B2_SMEM, stream>>>(p, maps);
+  if (p.softplus) scan_bwd2_kernel<true><<<grid, B2_NW * 32, B2_SMEM, stream>>>(p, maps);
+  else scan_bwd2_kernel<false><<<grid, B2_NW * 32, B2_SMEM, stream>>>(p, maps);
   *err = cudaGetLastError();
   return true;
 }

@@ -3,6 +3,10 @@
 import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch, bench
+for _a in sys.argv[1:]:
+    if _a.startswith("--lib="):          # development A/B: time another build of the library (e.g. variants/base.so)
+        import ceigm_unet_b200  # noqa: F401
+        sys.modules["ceigm_unet_b200._lib"].LIB_PATH = os.path.abspath(_a[6:])
 from ceigm_unet_b200.dropin import selective_scan_cuda_core as core
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 use_graph = "--graph" in sys.argv
