@@ -61,6 +61,10 @@ cudaError_t group_gate_bwd_launch(const float* ys, int G, const int* plane_of, u
                                   float* db_part, int n_partials, int batch, int D, int L, int z_dtype, int out_dtype, int H,
                                   int W, cudaStream_t stream);
 
+bool linear_tc_supported(int N_part, int K, int dtype);
+int linear_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int N, int K, int dtype,
+                     int n_parts, const ss2d_linear_part* parts, cudaStream_t stream, cudaError_t* cerr);
+
 thread_local char g_cuda_err[256] = "";
 // process-wide: the autograd engine launches the backward kernels from its own per-device threads
 static std::atomic<int64_t> g_launches{0};
@@ -441,6 +445,17 @@ int ss2d_wgrad_ts(const void* dY, const void* X, float* dW, int32_t batch, int32
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += 2;
   return SS2D_OK;
+}
+
+int32_t ss2d_linear_tc_supported(int32_t n_cols, int32_t K, int32_t dtype) { return linear_tc_supported(n_cols, K, dtype) ? 1 : 0; }
+
+int ss2d_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int32_t M, int32_t N, int32_t K,
+                   int32_t dtype, int32_t n_parts, const ss2d_linear_part* parts, ss2d_stream_t stream) {
+  cudaError_t e = cudaSuccess;
+  const int rc = linear_tc_launch(A, lda, W, ldw, bias, M, N, K, dtype, n_parts, parts, static_cast<cudaStream_t>(stream), &e);
+  if (rc == SS2D_ERR_CUDA) return cuda_fail(e);
+  if (rc == SS2D_OK) ++g_launches;
+  return rc;
 }
 
 const char* ss2d_strerror(int status) {

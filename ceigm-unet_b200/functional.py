@@ -352,6 +352,112 @@ def proj_cm(W, u):
     return _ProjCM.apply(W, u)
 
 
+# ---- tensor-core projections (ops.linear_tc: tcgen05, TMA-fed, accumulators in tensor memory) ---------------
+def _tc_operands(x, W):
+    """The operand dtype nn.Linear would compute in: the autocast dtype when autocast is on, else x's own."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        return x.to(dt), W.to(dt)
+    return x, W.to(x.dtype)
+
+
+def _tc_dtype_ok(x) -> bool:
+    """bf16 operands always (the tensor core multiplies them exactly); fp32 operands only when the user has allowed TF32
+    matmuls (torch.backends.cuda.matmul.allow_tf32 / set_float32_matmul_precision("high" | "medium"), as the reference's
+    train_synapse.py:21 does) — the same switch that governs cuBLAS."""
+    _need_cuda(x, "projection")
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return dt == torch.bfloat16 or (dt == torch.float32 and torch.backends.cuda.matmul.allow_tf32)
+
+
+def _tc_shape_ok(n_cols: int, K: int, x) -> bool:
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return ops.linear_tc_supported(n_cols, K, dt)
+
+
+class _InProjPlanes(torch.autograd.Function):
+    """xi (B, D, H, W), z (B, H, W, D) = in_proj + chunk + the NHWC -> NCHW copy of the x half (ss2d.py:504-510): ONE
+    tcgen05 launch whose epilogue stores the x half as channel-major planes and the gate half as rows."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        xc, Wc = _tc_operands(x, W)
+        Bn, H, Wd, _ = x.shape
+        D = W.shape[0] // 2
+        xi, z = ops.linear_tc(xc, Wc, bias, [(D, ("planes", H * Wd), False), (D, "rows", False)])
+        ctx.save_for_backward(xc, Wc)
+        ctx.meta = (bias is not None, x.dtype, W.dtype)
+        return xi.view(Bn, D, H, Wd), z
+
+    @staticmethod
+    def backward(ctx, dxi, dz):
+        xc, Wc = ctx.saved_tensors
+        has_bias, x_dtype, W_dtype = ctx.meta
+        Bn, H, Wd, C = xc.shape
+        D, L = Wc.shape[0] // 2, H * Wd
+        dxi3 = dxi.reshape(Bn, D, L).to(Wc.dtype)             # channel-major, as the forward wrote it
+        dz2 = dz.reshape(Bn * L, D).to(Wc.dtype)
+        x3 = xc.reshape(Bn, L, C)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            acc = torch.matmul(dxi3.transpose(1, 2), Wc[:D]).view(Bn * L, C)
+            acc.addmm_(dz2, Wc[D:])
+            dx = acc.view(xc.shape).to(x_dtype)
+        if ctx.needs_input_grad[1]:
+            dWx = torch.matmul(dxi3, x3).sum(dim=0)
+            dWz = torch.matmul(dz2.t(), x3.reshape(Bn * L, C))
+            dW = torch.cat([dWx, dWz], dim=0).to(W_dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = torch.cat([dxi3.float().sum(dim=(0, 2)), dz2.float().sum(dim=0)])
+        return dx, dW, db
+
+
+class _LinearTC(torch.autograd.Function):
+    """y = x W^T + b on the tensor cores (out_proj, ss2d.py:518); backward as _LinearTS."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        xc, Wc = _tc_operands(x, W)
+        (out,) = ops.linear_tc(xc, Wc, bias, [(W.shape[0], "rows", False)])
+        ctx.save_for_backward(xc, Wc)
+        ctx.meta = (bias is not None, x.dtype, W.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, Wc = ctx.saved_tensors
+        has_bias, x_dtype, W_dtype = ctx.meta
+        M, N = Wc.shape
+        dy2, x2 = dy.reshape(-1, M).to(Wc.dtype), xc.reshape(-1, N)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.matmul(dy2, Wc).view(xc.shape).to(x_dtype)
+        if ctx.needs_input_grad[1]:
+            if dy2.shape[0] >= _TS_MIN_ROWS and ops.wgrad_ts_supported(M, N):
+                dW = ops.wgrad_ts(dy2.unsqueeze(0), x2.unsqueeze(0)).to(W_dtype)
+            else:
+                dW = torch.matmul(dy2.t(), x2).to(W_dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dy2.float().sum(dim=0)
+        return dx, dW, db
+
+
+def in_proj_planes(x, W, bias=None):
+    """(xi (B, D, H, W), z (B, H, W, D)) through the tensor-core kernel, or None when the shape / dtype is not eligible
+    (the caller then composes F.linear + chunk + permute as the reference does)."""
+    D = W.shape[0] // 2
+    if x.dim() != 4 or W.shape[0] != 2 * D or not _tc_dtype_ok(x) or not _tc_shape_ok(D, W.shape[1], x):
+        return None
+    return _InProjPlanes.apply(x, W, bias)
+
+
+def linear_tc(x, W, bias=None):
+    """nn.Linear on the tensor-core kernel when eligible, else linear_ts (library GEMM, tall-skinny weight gradient)."""
+    if _tc_dtype_ok(x) and _tc_shape_ok(W.shape[0], W.shape[1], x):
+        return _LinearTC.apply(x, W, bias)
+    return linear_ts(x, W, bias)
+
+
 # ---- row-wise LayerNorm (GroupMambaLayer.norm) ------------------------------------------------------
 class _LayerNormRows(torch.autograd.Function):
     """nn.LayerNorm over the last dimension (C <= 512) of a channels-last tensor: ops.layernorm_fwd/bwd. Runs in the
@@ -378,7 +484,7 @@ class _LayerNormRows(torch.autograd.Function):
 
 def layer_norm_rows(x, weight, bias, eps):
     _need_cuda(x, "layer_norm_rows")
-    if torch.is_autocast_enabled() and x.dtype in (torch.float16, torch.bfloat16):
+    if torch.is_autocast_enabled("cuda") and x.dtype in (torch.float16, torch.bfloat16):
         x = x.float()      # nn.LayerNorm is on autocast's fp32 list: 16-bit inputs are normalised in, and returned as, fp32
     if x.shape[-1] > ops.LN_MAX_C or x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)      # wide rows: library kernel

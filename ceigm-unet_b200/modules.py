@@ -186,14 +186,18 @@ class SS2D(nn.Module, mamba_init):
             dirs = Fn.directions_of(CrossScan, CrossMerge)
             if dirs is None:
                 raise NotImplementedError("SS2D.forward needs a matching (CrossScan*, CrossMerge*) pair")
-        xz = Fn.linear_ts(x, self.in_proj.weight, self.in_proj.bias)    # ss2d.py:504 (tall-skinny weight gradient)
-        xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
-        xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
+        pz = Fn.in_proj_planes(x, self.in_proj.weight, self.in_proj.bias)    # ss2d.py:504-510 in one tensor-core launch
+        if pz is not None:
+            xi, z = pz
+        else:
+            xz = Fn.linear_ts(x, self.in_proj.weight, self.in_proj.bias)    # ss2d.py:504 (tall-skinny weight gradient)
+            xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
+            xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
         if self.with_dconv:
             xi = Fn.dwconv3(xi, self.conv2d)                      # :512 (reduction-shaped parameter gradient)
         xi = self.act(xi)                                         # :513
         y = self.forward_core(xi, z, dirs)                        # :514-517 (scan, merge, out_norm, gate)
-        return self.dropout(Fn.linear_ts(y, self.out_proj.weight, self.out_proj.bias))    # :518
+        return self.dropout(Fn.linear_tc(y, self.out_proj.weight, self.out_proj.bias))    # :518 (tensor cores when eligible)
 
 
 class GroupMambaLayer(nn.Module):

@@ -338,6 +338,47 @@ def wgrad_ts(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return dW
 
 
+# ---- tensor-core projections (tcgen05): out = A W^T (+ bias) with split / permuted epilogues ---------------
+def linear_tc_supported(n_cols: int, K: int, dtype: torch.dtype) -> bool:
+    return dtype in (torch.float32, torch.bfloat16) and bool(_lib.lib().ss2d_linear_tc_supported(int(n_cols), int(K), _DT[dtype]))
+
+
+def linear_tc(x: torch.Tensor, W: torch.Tensor, bias, parts):
+    """x (..., K) rows with unit inner stride, W (N, K) -> one tensor per part.
+    parts: list of (n_cols, kind, act) with kind "rows" -> (..., n_cols) row-major, or ("planes", L) -> the rows are
+    (B, L) pixels and the part is returned channel-major as (B, n_cols, L); act: apply SiLU.
+    fp32 operands run as TF32 on the tensor cores, bf16 operands as bf16; accumulation is fp32 either way."""
+    _require(x.is_cuda and W.is_cuda and x.dtype == W.dtype and x.dtype in (torch.float32, torch.bfloat16),
+             "linear_tc: CUDA fp32 or bf16 operands of one dtype")
+    K = x.shape[-1]
+    N = W.shape[0]
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    _require(W.dim() == 2 and W.shape[1] == K and W.stride(1) == 1, "linear_tc: W must be (N, K) with unit inner stride")
+    M = x2.shape[0]
+    _require(sum(p[0] for p in parts) == N, "linear_tc: the parts must cover the N columns")
+    arr = (_lib.LinearPart * len(parts))()
+    outs = []
+    for i, (n_cols, kind, act) in enumerate(parts):
+        if kind == "rows":
+            o = torch.empty(x.shape[:-1] + (n_cols,), dtype=x.dtype, device=x.device)
+            arr[i].ld, arr[i].planes_L = n_cols, 0
+        else:
+            Lp = int(kind[1])
+            _require(M % Lp == 0, "linear_tc: rows must be whole (batch, L) images for a planes part")
+            o = torch.empty((M // Lp, n_cols, Lp), dtype=x.dtype, device=x.device)
+            arr[i].ld, arr[i].planes_L = 0, Lp
+        arr[i].out, arr[i].n_cols, arr[i].act = o.data_ptr(), n_cols, 1 if act else 0
+        outs.append(o)
+    b32 = None if bias is None else bias.float().contiguous()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_linear_tc(_ptr(x2), x2.stride(0), _ptr(W), W.stride(0), _ptr(b32), M, N, K, _DT[x.dtype], len(parts),
+                                       arr, _stream(x.device))
+    _lib.check(rc, "ss2d_linear_tc")
+    return outs
+
+
 # ---- row-wise LayerNorm ------------------------------------------------------------------------
 LN_MAX_C = 512
 

@@ -228,6 +228,30 @@ int ss2d_wgrad_ts(const void* dY, const void* X, float* dW, int32_t batch, int32
                   size_t workspace_bytes, ss2d_stream_t stream);
 size_t ss2d_wgrad_ts_workspace_bytes(int32_t batch, int32_t rows, int32_t M, int32_t N);
 
+/* ---- tensor-core projections: out = A W^T (+ bias), split into column parts with their own layouts -------------
+ * Replaces nn.Linear in_proj + chunk + the NHWC -> NCHW copy of the x half (model/gm/ss2d.py:504-510) and out_proj
+ * (ss2d.py:518): tall, skinny GEMMs on tcgen05 tensor cores (TF32 math for fp32 operands, bf16 for bf16; fp32
+ * accumulation in tensor memory), A streamed once by TMA, W resident in shared memory.
+ * A: (M, K) rows lda elements apart; W: (N, K) rows ldw elements apart (nn.Linear's weight layout); bias: (N) fp32 or NULL.
+ * dtype: SS2D_F32 or SS2D_BF16, the type of A, W and every output. A, W and row-major outputs 16-byte aligned with
+ * row strides that are multiples of 16 bytes, else SS2D_ERR_ALIGNMENT.
+ * The N columns are cut into n_parts <= 4 consecutive parts of n_cols columns each (16 <= n_cols <= 256, multiple of 16;
+ * ss2d_linear_tc_supported(n_cols, K, dtype) tells whether W's part fits next to the A ring in shared memory):
+ *   planes_L == 0: row-major part, out[m * ld + c];
+ *   planes_L  > 0: channel-major planes of planes_L pixels, out[((m / planes_L) * n_cols + c) * planes_L + m % planes_L]
+ *                  (M % planes_L == 0): (B, H, W, C) rows in, (B, n_cols, H, W) planes out;
+ *   act != 0: SiLU applied to the part. */
+typedef struct ss2d_linear_part {
+  void* out;
+  int64_t ld;
+  int32_t n_cols;
+  int32_t planes_L;
+  int32_t act;
+} ss2d_linear_part;
+int ss2d_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int32_t M, int32_t N, int32_t K,
+                   int32_t dtype, int32_t n_parts, const ss2d_linear_part* parts, ss2d_stream_t stream);
+int32_t ss2d_linear_tc_supported(int32_t n_cols, int32_t K, int32_t dtype);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* ss2d_strerror(int status);
 const char* ss2d_last_cuda_error(void);   /* thread-local text of the last SS2D_ERR_CUDA */

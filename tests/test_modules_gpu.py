@@ -312,3 +312,67 @@ def test_grouped_layer_equals_the_four_separate_ss2ds(C, H):
     assert rel_err(gx1, gx2.cpu().numpy()) < 1e-4
     for n in gp1:
         assert rel_err(gp1[n], gp2[n].cpu().numpy()) < 5e-4, n
+
+
+def _tc_calls(monkeypatch):
+    from ceigm_unet_b200 import ops
+    calls = []
+    real = ops.linear_tc
+    monkeypatch.setattr(ops, "linear_tc", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    return calls
+
+
+def test_ss2d_tensor_core_projections_tf32_vs_fp32(monkeypatch):
+    """in_proj + chunk + NHWC->NCHW (ss2d.py:504-510) and out_proj (:518) on the tcgen05 kernel (TF32 math, taken when the
+    user allows TF32 matmuls as train_synapse.py:21 does) against the same module with full-fp32 library GEMMs: outputs and
+    input gradient rel <= 1e-3, parameter gradients <= 2e-3, at the north-star shape (K = 4, D = 192, 56 x 56)."""
+    import ceigm_unet_b200 as P
+    torch.manual_seed(3)
+    m = P.SS2D(d_model=96, d_state=16, ssm_ratio=2.0, k_group=4).cuda()
+    x = torch.randn(2, 56, 56, 96, device="cuda")
+    dy = torch.randn(2, 56, 56, 96, device="cuda")
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    res = {}
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            calls = _tc_calls(monkeypatch) if tf32 else []
+            m.zero_grad(set_to_none=True)
+            xg = x.clone().requires_grad_(True)
+            y = m(xg)
+            y.backward(dy)
+            res[tf32] = (y.detach().clone(), xg.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+            if tf32:
+                assert len(calls) == 2, "in_proj and out_proj must both run on the tensor-core kernel"
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
+    assert rel_err(y1, y0.cpu().numpy()) < 1e-3
+    assert rel_err(dx1, dx0.cpu().numpy()) < 1e-3
+    for n in g0:
+        assert rel_err(g1[n], g0[n].cpu().numpy()) < 2e-3, n
+
+
+def test_ss2d_tensor_core_projections_bf16_autocast(monkeypatch):
+    """Under bf16 autocast (the training configuration) both projections run on the tensor-core kernel with bf16 operands;
+    result within 2e-2 of the fp32 module, like the library path."""
+    import ceigm_unet_b200 as P
+    torch.manual_seed(4)
+    m = P.SS2D(d_model=96, d_state=16, ssm_ratio=2.0, k_group=4).cuda()
+    x = torch.randn(2, 28, 28, 96, device="cuda", requires_grad=True)
+    dy = torch.randn(2, 28, 28, 96, device="cuda")
+    y32 = m(x)
+    y32.backward(dy)
+    ref = (y32.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+    m.zero_grad(set_to_none=True)
+    x.grad = None
+    calls = _tc_calls(monkeypatch)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = m(x)
+    y16.backward(dy.to(y16.dtype))
+    assert len(calls) == 2 and y16.dtype == torch.bfloat16
+    assert rel_err(y16.float(), ref[0].cpu().numpy()) < 2e-2
+    assert rel_err(x.grad, ref[1].cpu().numpy()) < 2e-2
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad.float(), ref[2][n].cpu().numpy()) < 4e-2, n
