@@ -226,14 +226,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) linear_tc_kernel(const TcParams
     if (TF32) {
       constexpr uint32_t CT = 32u * TC_CVT_WARPS;
       const uint32_t ct = (warp - 2) * 32 + lane;
-      auto rna = [](float4 v) {
-        uint32_t r0, r1, r2, r3;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r0) : "f"(v.x));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r1) : "f"(v.y));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(v.z));
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r3) : "f"(v.w));
-        return make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
-      };
+      // round to nearest TF32 (ties away from zero) on the bit pattern: add half an ulp of the 10-bit mantissa to the
+      // magnitude, clear the 13 low bits (cvt.rna.tf32.f32 does the same but ptxas expands it to ~8 instructions per value)
+      auto rna1 = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
+      auto rna = [&](float4 v) { return make_float4(rna1(v.x), rna1(v.y), rna1(v.z), rna1(v.w)); };
       auto round_block = [&](uint32_t base, uint32_t bytes) {      // bytes: multiple of 1024
         for (uint32_t o0 = 0; o0 < bytes; o0 += CT * 16u * 4u) {   // 4 pieces per thread in flight
           float4 v[4];

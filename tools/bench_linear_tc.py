@@ -4,6 +4,10 @@ import os, sys, statistics
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 import torch.nn.functional as F
+for _a in sys.argv[1:]:
+    if _a.startswith('--lib='):
+        import ceigm_unet_b200  # noqa
+        sys.modules['ceigm_unet_b200._lib'].LIB_PATH = os.path.abspath(_a[6:])
 from ceigm_unet_b200 import ops
 
 def timeit(fn, iters=20):
