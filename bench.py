@@ -286,6 +286,7 @@ def run_ours(args, rank, world, local_rank):
                              "frac": round(ex2 / 4.6e12 * 1e3 / ms_per_step, 4)}
     if rank == 0 and world == 1 and not args.no_extras:
         line["other_workloads"] = other_workloads(core, device, peak, exclude=args.workload)
+        line["projections"] = projection_workloads(device, peak)
     if not args.no_model:
         # every rank takes part (batch-sharded data parallel, gradient all-reduce on NCCL); rank 0 reports
         line["model"] = model_workloads(device, rank, world)
@@ -360,6 +361,63 @@ def other_workloads(core, device, peak, exclude):
         out.append(rec)
         del sets
         torch.cuda.empty_cache()
+    return out
+
+
+def projection_workloads(device, peak):
+    """The dense contractions around the scan on the tcgen05 kernel (csrc/linear_tc.cu) at the north-star SS2D shape
+    (d_model 96, d_inner 192, batch 24, 56 x 56): in_proj + chunk + NHWC->NCHW in one launch and out_proj, next to the
+    library composition they replace (F.linear [+ chunk + permute().contiguous()]); CUDA-graph replay, L2 flushed between
+    replays, algorithmic bytes = operands read once + outputs written once."""
+    import torch.nn.functional as F
+    from ceigm_unet_b200 import ops
+    Bn, H, W, C, D = 24, 56, 56, 96, 192
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def timed(fn, iters=10):
+        g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            fn()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=st):
+                fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    out = []
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for dtype, name in ((torch.float32, "f32 (tf32 math)"), (torch.bfloat16, "bf16")):
+            es = 4 if dtype == torch.float32 else 2
+            x = torch.randn(Bn, H, W, C, device=device).to(dtype)
+            y = torch.randn(Bn, H, W, D, device=device).to(dtype)
+            Win = (torch.randn(2 * D, C, device=device) / C ** 0.5).to(dtype)
+            Wout = (torch.randn(C, D, device=device) / D ** 0.5).to(dtype)
+            M = Bn * H * W
+            torch.backends.cuda.matmul.allow_tf32 = True      # the library column gets tensor cores too
+
+            def lib_in():
+                xi, z = F.linear(x, Win).chunk(2, dim=-1)
+                return xi.permute(0, 3, 1, 2).contiguous(), z
+            for op, ours, lib, nbytes in (
+                    ("in_proj + chunk + NHWC->NCHW (ss2d.py:504-510)",
+                     lambda: ops.linear_tc(x, Win, None, [(D, ("planes", H * W), False), (D, "rows", False)]), lib_in, es * M * (C + 2 * D)),
+                    ("out_proj (ss2d.py:518)", lambda: ops.linear_tc(y, Wout, None, [(C, "rows", False)]),
+                     lambda: F.linear(y, Wout), es * M * (C + D))):
+                ms, ms_lib = timed(ours), timed(lib)
+                out.append({"op": op, "kernel": "linear_tc_kernel (tcgen05.mma, TMA, TMEM)", "dtype": name, "rows": M, "K_N": [x.shape[-1] if "in_proj" in op else D, 2 * D if "in_proj" in op else C],
+                            "ms": round(ms, 4), "alg_GBps": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / peak, 4),
+                            "library_ms": round(ms_lib, 4), "speedup_vs_library": round(ms_lib / ms, 2)})
+    except Exception as e:      # noqa: BLE001
+        out.append({"error": repr(e)[:300]})
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
     return out
 
 
