@@ -61,6 +61,8 @@ cudaError_t group_gate_bwd_launch(const float* ys, int G, const int* plane_of, u
                                   float* db_part, int n_partials, int batch, int D, int L, int z_dtype, int out_dtype, int H,
                                   int W, cudaStream_t stream);
 
+cudaError_t dwconv3_fused_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, void* y,
+                                 int batch, int C, int H, int W, int dt, cudaStream_t stream);
 bool linear_tc_supported(int N_part, int K, int dtype);
 int linear_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int N, int K, int dtype,
                      int n_parts, const ss2d_linear_part* parts, cudaStream_t stream, cudaError_t* cerr);
@@ -444,6 +446,20 @@ int ss2d_wgrad_ts(const void* dY, const void* X, float* dW, int32_t batch, int32
                                   static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   g_launches += 2;
+  return SS2D_OK;
+}
+
+int ss2d_dwconv3_act(int32_t mode, const void* x, const float* weight, const float* bias, const void* dy, void* y,
+                     int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, ss2d_stream_t stream) {
+  if (!x || !weight || !y || (mode == 1 && !dy)) return SS2D_ERR_NULL_POINTER;
+  if (mode < 0 || mode > 2) return SS2D_ERR_UNSUPPORTED;
+  if (batch <= 0 || C <= 0 || H <= 0 || W <= 0) return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  const size_t va = (W & 3) == 0 ? 4 * esize(dtype) : esize(dtype);
+  if (!aligned(x, va) || !aligned(y, va) || (dy && !aligned(dy, va)) || !aligned(weight, 4)) return SS2D_ERR_ALIGNMENT;
+  cudaError_t e = dwconv3_fused_launch(mode, x, weight, bias, dy, y, batch, C, H, W, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
   return SS2D_OK;
 }
 

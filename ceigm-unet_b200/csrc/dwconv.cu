@@ -8,6 +8,7 @@
 // butterflies + one shared-memory fold per CTA, per-slab partials, fixed-order finalize (deterministic).
 // HBM-bound: X and dY are read once (4 bytes per pixel-channel each). fp32, NCHW contiguous.
 #include "common.cuh"
+#include "host_util.h"
 
 namespace ss2d {
 
@@ -85,6 +86,84 @@ cudaError_t dwconv3_wgrad_launch(const float* x, const float* dy, float* dW, flo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dwconv3_wgrad_finalize_kernel<<<(C * 10 + 255) / 256, 256, 0, stream>>>(workspace, dW, db, C, slabs);
+  return cudaGetLastError();
+}
+
+// ---- depthwise 3 x 3 convolution fused with its activation (ss2d.py:512-513: conv2d -> SiLU) ------------------------
+// MODE 0 (forward):        y  = SiLU(bias + conv3x3(x))
+// MODE 1 (backward, 1/2):  y  = dy * SiLU'(bias + conv3x3(x))     the gradient of the pre-activation, recomputed from x
+// MODE 2 (backward, 2/2):  y  = conv3x3 of x with the FLIPPED kernel, no bias / activation (the input gradient from MODE 1's
+//                               output; zero padding makes the transposed convolution a plain correlation)
+// HBM-bound stencils: a thread produces PX consecutive pixels of one row (PX = 4 when W % 4 == 0: one vector load per row
+// plus the two edge neighbours, which hit L1), every input element is fetched from HBM once. fp32 math; fp32 / bf16 / fp16
+// tensors, NCHW contiguous. Replaces cuDNN / ATen depthwise conv forward + SiLU (2 kernels, one extra round trip of the
+// activation tensor) and SiLU backward + conv input gradient.
+template <int PX, int MODE>
+__global__ void __launch_bounds__(256)
+dwconv3_fused_kernel(const void* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                     const void* __restrict__ dy, void* __restrict__ y, int64_t planes, int C, int H, int W, int dt) {
+  const int WQ = W / PX;
+  const int64_t per_plane = (int64_t)H * WQ, total = planes * per_plane;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t pl = i / per_plane;
+    const int r = (int)(i - pl * per_plane);
+    const int h = r / WQ, w0 = (r - h * WQ) * PX;
+    const int c = (int)(pl % C);
+    float k[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) k[j] = __ldg(wgt + c * 9 + (MODE == 2 ? 8 - j : j));
+    const float b0 = (MODE != 2 && bias) ? __ldg(bias + c) : 0.f;
+    float acc[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) acc[q] = b0;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= H) continue;
+      const int64_t ro = (pl * H + hh) * W + w0;
+      float v[PX + 2];
+      v[0] = w0 > 0 ? load1(x, ro - 1, dt) : 0.f;
+      if (PX == 4) {
+        const float4 m = load4(x, ro, dt);
+        v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+      } else {
+        v[1] = load1(x, ro, dt);
+      }
+      v[PX + 1] = w0 + PX < W ? load1(x, ro + PX, dt) : 0.f;
+#pragma unroll
+      for (int q = 0; q < PX; ++q)
+        acc[q] = fmaf(k[ky * 3 + 2], v[q + 2], fmaf(k[ky * 3 + 1], v[q + 1], fmaf(k[ky * 3], v[q], acc[q])));
+    }
+    const int64_t o = (pl * H + h) * W + w0;
+    float g[PX];
+    if (MODE == 1) {
+      if (PX == 4) { const float4 t = load4(dy, o, dt); g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w; }
+      else g[0] = load1(dy, o, dt);
+    }
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      if (MODE == 2) continue;
+      const float sgm = __fdividef(1.f, 1.f + ex2f(-acc[q] * kLog2e));
+      acc[q] = MODE == 0 ? acc[q] * sgm : g[q] * sgm * (1.f + acc[q] * (1.f - sgm));
+    }
+    if (PX == 4) store4(y, o, dt, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    else store1(y, o, dt, acc[0]);
+  }
+}
+
+cudaError_t dwconv3_fused_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, void* y,
+                                 int batch, int C, int H, int W, int dt, cudaStream_t stream) {
+  const int64_t planes = (int64_t)batch * C;
+  const bool v4 = (W & 3) == 0;      // plane rows then start on 16-byte (fp32) / 8-byte (16-bit) boundaries
+  const int64_t total = planes * H * (v4 ? W / 4 : W);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count_current_device() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define SS2D_DW(PXV, M) dwconv3_fused_kernel<PXV, M><<<(unsigned)blocks, 256, 0, stream>>>(x, wgt, bias, dy, y, planes, C, H, W, dt)
+  if (v4) { if (mode == 0) SS2D_DW(4, 0); else if (mode == 1) SS2D_DW(4, 1); else SS2D_DW(4, 2); }
+  else { if (mode == 0) SS2D_DW(1, 0); else if (mode == 1) SS2D_DW(1, 1); else SS2D_DW(1, 2); }
+#undef SS2D_DW
   return cudaGetLastError();
 }
 

@@ -514,6 +514,39 @@ class _DWConv3(torch.autograd.Function):
         return dx, dW, db
 
 
+class _DWConv3SiLU(torch.autograd.Function):
+    """SiLU(conv2d(x, W (C,1,3,3), b, padding=1, groups=C)) (ss2d.py:512-513) as ONE kernel (ops.dwconv3_act); backward: the
+    pre-activation gradient is recomputed from x in one pass, the input gradient is the flipped-kernel pass over it, dW / db
+    come from ops.dwconv3_wgrad. Runs in the autocast dtype like nn.Conv2d."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        if torch.is_autocast_enabled("cuda"):
+            x = x.to(torch.get_autocast_dtype("cuda"))
+        x = x.contiguous()
+        ctx.save_for_backward(x, W, bias)
+        return ops.dwconv3_act(0, x, W, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, bias = ctx.saved_tensors
+        dpre = ops.dwconv3_act(1, x, W, bias, dy.to(x.dtype).contiguous())
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.dwconv3_act(2, dpre, W, None)
+        if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
+            dW, db = ops.dwconv3_wgrad(x.float(), dpre.float(), bias is not None)
+            dW = dW.to(W.dtype)
+            db = None if db is None else db.to(bias.dtype)
+        return dx, dW, db
+
+
+def dwconv3_silu(x, W, bias):
+    """SiLU(depthwise 3 x 3 conv) as one kernel (weights given explicitly: the grouped layer assembles them per call)."""
+    _need_cuda(x, "dwconv3_silu")
+    return _DWConv3SiLU.apply(x, W, bias)
+
+
 def dwconv3(x, conv: "torch.nn.Conv2d"):
     """SS2D.conv2d through _DWConv3 when it is the reference's depthwise 3 x 3 / padding 1 layer on a CUDA tensor."""
     _need_cuda(x, "dwconv3")

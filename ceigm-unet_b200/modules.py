@@ -193,9 +193,15 @@ class SS2D(nn.Module, mamba_init):
             xz = Fn.linear_ts(x, self.in_proj.weight, self.in_proj.bias)    # ss2d.py:504 (tall-skinny weight gradient)
             xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
             xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
-        if self.with_dconv:
-            xi = Fn.dwconv3(xi, self.conv2d)                      # :512 (reduction-shaped parameter gradient)
-        xi = self.act(xi)                                         # :513
+        cv = self.conv2d if self.with_dconv else None
+        if (cv is not None and isinstance(self.act, nn.SiLU) and cv.kernel_size == (3, 3) and cv.padding == (1, 1)
+                and cv.stride == (1, 1) and cv.dilation == (1, 1) and cv.groups == cv.in_channels == cv.out_channels
+                and cv.padding_mode == "zeros" and xi.is_cuda):
+            xi = Fn.dwconv3_silu(xi, cv.weight, cv.bias)          # :512-513 as one kernel
+        else:
+            if cv is not None:
+                xi = Fn.dwconv3(xi, cv)                           # :512 (reduction-shaped parameter gradient)
+            xi = self.act(xi)                                     # :513
         y = self.forward_core(xi, z, dirs)                        # :514-517 (scan, merge, out_norm, gate)
         return self.dropout(Fn.linear_tc(y, self.out_proj.weight, self.out_proj.bias))    # :518 (tensor cores when eligible)
 
@@ -249,11 +255,7 @@ class GroupMambaLayer(nn.Module):
         Wc = torch.cat([ms[PL[0]].conv2d.weight, ms[PL[1]].conv2d.weight,
                         ms[PL[2]].conv2d.weight.transpose(2, 3), ms[PL[3]].conv2d.weight.transpose(2, 3)])
         bc = torch.cat([ms[g].conv2d.bias for g in PL])
-        if Bn * L >= Fn._TS_MIN_ROWS:
-            u = Fn._DWConv3.apply(u, Wc, bc)
-        else:
-            u = F.conv2d(u, Wc, bc, padding=1, groups=4 * D)
-        u = F.silu(u).view(Bn, 4 * D, L)                                            # :513
+        u = Fn.dwconv3_silu(u, Wc, bc).view(Bn, 4 * D, L)                            # :512-513, one kernel
         # x_proj / dt_proj (:465-469) as two block-structured GEMMs from u: delta = (W_dt W_x[:R]) u and [B; C] = W_x[R:] u
         wxp = [ms[g].x_proj_weight[0] for g in PL]                                  # (R + 2 N, D)
         W_dt = torch.block_diag(*[torch.matmul(ms[g].dt_projs_weight[0], wx[:R]) for g, wx in zip(PL, wxp)])     # (4 D, 4 D)

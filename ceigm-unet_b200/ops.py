@@ -338,6 +338,22 @@ def wgrad_ts(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return dW
 
 
+def dwconv3_act(mode: int, x: torch.Tensor, weight: torch.Tensor, bias, dy=None) -> torch.Tensor:
+    """Depthwise 3 x 3 convolution (padding 1) fused with SiLU. mode 0: SiLU(b + conv(x)); 1: dy * SiLU'(b + conv(x));
+    2: conv with the flipped kernel, no bias (input gradient of mode 1's result). x, dy: (B, C, H, W) contiguous."""
+    _require(x.is_cuda and x.dim() == 4 and x.is_contiguous() and x.dtype in _DT, "dwconv3_act: contiguous CUDA (B, C, H, W) tensor")
+    _require(dy is None or (dy.shape == x.shape and dy.dtype == x.dtype and dy.is_contiguous()), "dwconv3_act: dy must match x")
+    Bn, C, H, W = x.shape
+    w32 = weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_dwconv3_act(mode, _ptr(x), _ptr(w32), _ptr(b32), _ptr(dy), _ptr(y), Bn, C, H, W, _DT[x.dtype],
+                                         _stream(x.device))
+    _lib.check(rc, "ss2d_dwconv3_act")
+    return y
+
+
 # ---- tensor-core projections (tcgen05): out = A W^T (+ bias) with split / permuted epilogues ---------------
 def linear_tc_supported(n_cols: int, K: int, dtype: torch.dtype) -> bool:
     return dtype in (torch.float32, torch.bfloat16) and bool(_lib.lib().ss2d_linear_tc_supported(int(n_cols), int(K), _DT[dtype]))

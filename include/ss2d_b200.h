@@ -200,6 +200,16 @@ int ss2d_dwconv3_wgrad(const float* x, const float* dy, float* dweight, float* d
                        int32_t W, void* workspace, size_t workspace_bytes, ss2d_stream_t stream);
 size_t ss2d_dwconv3_wgrad_workspace_bytes(int32_t batch, int32_t C, int32_t H, int32_t W);
 
+/* ---- depthwise 3 x 3 convolution fused with SiLU: forward and input gradient -------------------------------
+ * nn.Conv2d(D, D, groups=D, kernel_size=3, padding=1) followed by SiLU (model/gm/ss2d.py:512-513) as one pass.
+ * x, dy, y: (batch, C, H, W) contiguous tensors of `dtype`; weight: (C, 1, 3, 3) fp32; bias: (C) fp32 or NULL.
+ *   mode 0: y = SiLU(bias + conv(x))                       (forward)
+ *   mode 1: y = dy * SiLU'(bias + conv(x))                 (gradient of the pre-activation, recomputed from x)
+ *   mode 2: y = conv of x with the flipped kernel, no bias (input gradient: pass mode 1's output as x)
+ * The parameter gradients come from ss2d_dwconv3_wgrad(x, <mode 1 output>). */
+int ss2d_dwconv3_act(int32_t mode, const void* x, const float* weight, const float* bias, const void* dy, void* y,
+                     int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, ss2d_stream_t stream);
+
 /* ---- row-wise LayerNorm over C <= 512 channels of channels-last rows --------------------------------
  * Replaces nn.LayerNorm as used by GroupMambaLayer.norm (model/gm/groupmamba.py:131, 156; two applications per layer
  * call with shared weights). x, y, dy, dx: (rows, C) contiguous, dtype = ss2d_dtype; weight / bias: (C) fp32 or NULL.
