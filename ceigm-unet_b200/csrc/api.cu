@@ -63,6 +63,9 @@ cudaError_t group_gate_bwd_launch(const float* ys, int G, const int* plane_of, u
 
 cudaError_t dwconv3_fused_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, void* y,
                                  int batch, int C, int H, int W, int dt, cudaStream_t stream);
+cudaError_t dwconv3_tiled_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, const void* dyT,
+                                 void* y, void* yT, int batch, int C, int H, int W, int64_t x_bs, int64_t y_bs, int64_t yT_bs,
+                                 int64_t dy_bs, int64_t dyT_bs, int dt, cudaStream_t stream);
 bool linear_tc_supported(int N_part, int K, int dtype);
 int linear_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int N, int K, int dtype,
                      int n_parts, const ss2d_linear_part* parts, cudaStream_t stream, cudaError_t* cerr);
@@ -458,6 +461,27 @@ int ss2d_dwconv3_act(int32_t mode, const void* x, const float* weight, const flo
   const size_t va = (W & 3) == 0 ? 4 * esize(dtype) : esize(dtype);
   if (!aligned(x, va) || !aligned(y, va) || (dy && !aligned(dy, va)) || !aligned(weight, 4)) return SS2D_ERR_ALIGNMENT;
   cudaError_t e = dwconv3_fused_launch(mode, x, weight, bias, dy, y, batch, C, H, W, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+int ss2d_dwconv3_act_planes(int32_t mode, const void* x, int64_t x_batch_stride, const float* weight, const float* bias,
+                            const void* dy, int64_t dy_batch_stride, const void* dyT, int64_t dyT_batch_stride, void* y,
+                            int64_t y_batch_stride, void* yT, int64_t yT_batch_stride, int32_t batch, int32_t C, int32_t H,
+                            int32_t W, int32_t dtype, ss2d_stream_t stream) {
+  if (!x || !weight || !y || (mode == 1 && !dy)) return SS2D_ERR_NULL_POINTER;
+  if (mode < 0 || mode > 1) return SS2D_ERR_UNSUPPORTED;
+  if (batch <= 0 || C <= 0 || H <= 0 || W <= 0 || C > 65535 || batch > 65535) return SS2D_ERR_BAD_SHAPE;
+  if ((H & 3) || (W & 3)) return SS2D_ERR_UNSUPPORTED;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  const size_t va = 4 * esize(dtype);
+  auto ok = [&](const void* p, int64_t bs) { return !p || (aligned(p, va) && (bs * (int64_t)esize(dtype)) % (int64_t)va == 0); };
+  if (!ok(x, x_batch_stride) || !ok(y, y_batch_stride) || !ok(yT, yT_batch_stride) || !ok(dy, dy_batch_stride) ||
+      !ok(dyT, dyT_batch_stride) || !aligned(weight, 4))
+    return SS2D_ERR_ALIGNMENT;
+  cudaError_t e = dwconv3_tiled_launch(mode, x, weight, bias, dy, dyT, y, yT, batch, C, H, W, x_batch_stride, y_batch_stride,
+                                       yT_batch_stride, dy_batch_stride, dyT_batch_stride, dtype, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
   return SS2D_OK;

@@ -151,6 +151,96 @@ dwconv3_fused_kernel(const void* __restrict__ x, const float* __restrict__ wgt, 
   }
 }
 
+// Tiled variant for H % 4 == 0 and W % 4 == 0: a CTA owns a 32 x 32 pixel tile of one (batch, channel) plane, a thread
+// 4 consecutive pixels of a row. On top of the flat kernel it can
+//   * (MODE 0) store the result a second time in TRANSPOSED pixel order (the (W, H) image the column-major scan directions
+//     2 / 4 traverse as row-major: model/gm/csms6s.py:95-129, 172-206) — both orientations leave in 128-byte row pieces, the
+//     transposition goes through a padded shared-memory tile, so no separate permuted-copy pass (and no torch.cat of the two
+//     planes: y and yT are the two halves of ONE (B, 2 C, L) buffer addressed by their batch strides) ever runs;
+//   * (MODE 1) read a second upstream gradient dyT given in transposed pixel order and add it to dy on the fly — the adjoint
+//     of the double store, instead of a transpose-copy + add.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+dwconv3_tiled_kernel(const void* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                     const void* __restrict__ dy, const void* __restrict__ dyT, void* __restrict__ y, void* __restrict__ yT,
+                     int C, int H, int W, int tiles_w, int64_t x_bs, int64_t y_bs, int64_t yT_bs, int64_t dy_bs, int64_t dyT_bs,
+                     int dt) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
+  const int h0 = th * 32, w0 = tw * 32;
+  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  const int h = h0 + ty, w = w0 + 4 * tx;
+  const int64_t HW = (int64_t)H * W;
+  const bool in = h < H && w < W;                       // whole quads are inside or outside (W % 4 == 0)
+  if (MODE == 1 && dyT) {                               // transposed upstream gradient of this tile: rows = w, columns = h
+    const int wt = w0 + ty, ht = h0 + 4 * tx;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wt < W && ht < H) t = load4(dyT, (int64_t)b * dyT_bs + (int64_t)c * HW + (int64_t)wt * H + ht, dt);
+    tile[ty][4 * tx] = t.x; tile[ty][4 * tx + 1] = t.y; tile[ty][4 * tx + 2] = t.z; tile[ty][4 * tx + 3] = t.w;
+    __syncthreads();
+  }
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (in) {
+    float k[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) k[j] = __ldg(wgt + c * 9 + j);
+    const float b0 = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = b0;
+    const int64_t xb = (int64_t)b * x_bs + (int64_t)c * HW;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + ky - 1;
+      if (hh < 0 || hh >= H) continue;
+      const int64_t ro = xb + (int64_t)hh * W + w;
+      float v[6];
+      v[0] = w > 0 ? load1(x, ro - 1, dt) : 0.f;
+      const float4 m = load4(x, ro, dt);
+      v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+      v[5] = w + 4 < W ? load1(x, ro + 4, dt) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        acc[q] = fmaf(k[ky * 3 + 2], v[q + 2], fmaf(k[ky * 3 + 1], v[q + 1], fmaf(k[ky * 3], v[q], acc[q])));
+    }
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE == 1) {
+      const float4 t = load4(dy, (int64_t)b * dy_bs + (int64_t)c * HW + (int64_t)h * W + w, dt);
+      g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+      if (dyT) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] += tile[4 * tx + q][ty];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float sgm = __fdividef(1.f, 1.f + ex2f(-acc[q] * kLog2e));
+      acc[q] = MODE == 0 ? acc[q] * sgm : g[q] * sgm * (1.f + acc[q] * (1.f - sgm));
+    }
+    store4(y, (int64_t)b * y_bs + (int64_t)c * HW + (int64_t)h * W + w, dt, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  }
+  if (MODE == 0 && yT) {
+    tile[ty][4 * tx] = acc[0]; tile[ty][4 * tx + 1] = acc[1]; tile[ty][4 * tx + 2] = acc[2]; tile[ty][4 * tx + 3] = acc[3];
+    __syncthreads();
+    const int wt = w0 + ty, ht = h0 + 4 * tx;            // this thread now owns column wt, rows ht .. ht + 3
+    if (wt < W && ht < H)
+      store4(yT, (int64_t)b * yT_bs + (int64_t)c * HW + (int64_t)wt * H + ht, dt,
+             make_float4(tile[4 * tx][ty], tile[4 * tx + 1][ty], tile[4 * tx + 2][ty], tile[4 * tx + 3][ty]));
+  }
+}
+
+cudaError_t dwconv3_tiled_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, const void* dyT,
+                                 void* y, void* yT, int batch, int C, int H, int W, int64_t x_bs, int64_t y_bs, int64_t yT_bs,
+                                 int64_t dy_bs, int64_t dyT_bs, int dt, cudaStream_t stream) {
+  const int tiles_w = (W + 31) / 32, tiles_h = (H + 31) / 32;
+  dim3 grid(tiles_w * tiles_h, C, batch);
+  if (mode == 0)
+    dwconv3_tiled_kernel<0><<<grid, 256, 0, stream>>>(x, wgt, bias, dy, dyT, y, yT, C, H, W, tiles_w, x_bs, y_bs, yT_bs, dy_bs, dyT_bs, dt);
+  else
+    dwconv3_tiled_kernel<1><<<grid, 256, 0, stream>>>(x, wgt, bias, dy, dyT, y, yT, C, H, W, tiles_w, x_bs, y_bs, yT_bs, dy_bs, dyT_bs, dt);
+  return cudaGetLastError();
+}
+
 cudaError_t dwconv3_fused_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, void* y,
                                  int batch, int C, int H, int W, int dt, cudaStream_t stream) {
   const int64_t planes = (int64_t)batch * C;

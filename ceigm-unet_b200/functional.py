@@ -541,6 +541,42 @@ class _DWConv3SiLU(torch.autograd.Function):
         return dx, dW, db
 
 
+class _DWConv3SiLUPlanes(torch.autograd.Function):
+    """u (B, 2 D, L) = [SiLU(conv(x)) | its transposed image]: ss2d.py:512-513 and the two input planes of the K = 4 scan
+    (directions 1 / 3 read the natural plane, 2 / 4 the transposed one as row-major traversals) in ONE kernel — what the
+    reference does with conv, SiLU and CrossScan's permuted copies (csms6s.py:11-29). Backward: one pass adds the two planes'
+    gradients (the transposed one through a shared-memory tile) and applies SiLU'; then the flipped-kernel pass."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        if torch.is_autocast_enabled("cuda"):
+            x = x.to(torch.get_autocast_dtype("cuda"))
+        x = x.contiguous()
+        ctx.save_for_backward(x, W, bias)
+        return ops.dwconv3_act_planes_fwd(x, W, bias)
+
+    @staticmethod
+    def backward(ctx, du):
+        x, W, bias = ctx.saved_tensors
+        dpre = ops.dwconv3_act_planes_bwd(x, W, bias, du.to(x.dtype).contiguous())
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.dwconv3_act(2, dpre, W, None)
+        if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
+            dW, db = ops.dwconv3_wgrad(x.float(), dpre.float(), bias is not None)
+            dW = dW.to(W.dtype)
+            db = None if db is None else db.to(bias.dtype)
+        return dx, dW, db
+
+
+def dwconv3_silu_planes(x, W, bias):
+    """(B, 2 D, H W) natural + transposed planes of SiLU(conv(x)), or None when the shape is not eligible."""
+    _need_cuda(x, "dwconv3_silu_planes")
+    if not ops.dwconv3_act_planes_ok(x):
+        return None
+    return _DWConv3SiLUPlanes.apply(x, W, bias)
+
+
 def dwconv3_silu(x, W, bias):
     """SiLU(depthwise 3 x 3 conv) as one kernel (weights given explicitly: the grouped layer assembles them per call)."""
     _need_cuda(x, "dwconv3_silu")

@@ -121,8 +121,10 @@ class SS2D(nn.Module, mamba_init):
             return 2, (tflag[0], tflag[1]), kdirs
         return None
 
-    def forward_core(self, x: torch.Tensor, z, dirs):
-        """x: (B, D, H, W) activated conv output; z: (B, H, W, D) raw gate view or None -> (B, H, W, D)."""
+    def forward_core(self, x: torch.Tensor, z, dirs, planes_u=None):
+        """x: (B, D, H, W) activated conv output; z: (B, H, W, D) raw gate view or None -> (B, H, W, D).
+        planes_u: (B, 2 D, L) = [x | x transposed] already written by the convolution kernel (Fn.dwconv3_silu_planes); x is
+        then only consulted for its shape."""
         Bn, D, H, W = x.shape
         K, _, R = self.dt_projs_weight.shape
         N = self.A_logs.shape[1]
@@ -134,10 +136,18 @@ class SS2D(nn.Module, mamba_init):
             P, tflags, kdirs = 1, (False,), tuple(dirs)
         else:
             P, tflags, kdirs = plan
-        planes = [x.transpose(2, 3).reshape(Bn, D, L) if t else x.reshape(Bn, D, L) for t in tflags]
+        if planes_u is not None and not (P == 2 and tflags == (False, True)):
+            planes_u = None
+        Wx = self.x_proj_weight.to(planes_u.dtype if planes_u is not None else x.dtype)
+        planes = None if planes_u is not None else [x.transpose(2, 3).reshape(Bn, D, L) if t else x.reshape(Bn, D, L) for t in tflags]
         # pointwise projections evaluated in each plane's own pixel order (identical values to projecting the permuted xs)
-        Wx = self.x_proj_weight.to(x.dtype)
-        if P == 1:
+        if planes_u is not None:
+            # both planes come from the convolution kernel in ONE buffer: one GEMM with block-structured weights (direction k
+            # reads plane k % 2) gives x_dbl in group order — no transposed copy, no cat, no stack
+            u = planes_u
+            W_blk = torch.cat([F.pad(Wx[k], ((k % 2) * D, (1 - k % 2) * D)) for k in range(K)])         # (K C, 2 D)
+            x_dbl = Fn.proj_cm(W_blk, u).view(Bn, K, C, L)
+        elif P == 1:
             u = planes[0]
             x_dbl = Fn.proj_cm(Wx.reshape(K * C, D), u).view(Bn, K, C, L)
         else:
@@ -194,15 +204,21 @@ class SS2D(nn.Module, mamba_init):
             xi, z = xz.chunk(2, dim=-1)                               # :506  (views; SiLU(z) is fused into the epilogue)
             xi = xi.permute(0, 3, 1, 2).contiguous()                  # :510
         cv = self.conv2d if self.with_dconv else None
+        planes_u = None
         if (cv is not None and isinstance(self.act, nn.SiLU) and cv.kernel_size == (3, 3) and cv.padding == (1, 1)
                 and cv.stride == (1, 1) and cv.dilation == (1, 1) and cv.groups == cv.in_channels == cv.out_channels
                 and cv.padding_mode == "zeros" and xi.is_cuda):
-            xi = Fn.dwconv3_silu(xi, cv.weight, cv.bias)          # :512-513 as one kernel
+            plan = self._plan(dirs)
+            if plan is not None and plan[0] == 2 and plan[1] == (False, True):
+                # K = 4 (directions 1, 2, 3, 4): the convolution kernel writes the natural AND the transposed plane
+                planes_u = Fn.dwconv3_silu_planes(xi, cv.weight, cv.bias)      # :512-513 + CrossScan's layout, one kernel
+            if planes_u is None:
+                xi = Fn.dwconv3_silu(xi, cv.weight, cv.bias)      # :512-513 as one kernel
         else:
             if cv is not None:
                 xi = Fn.dwconv3(xi, cv)                           # :512 (reduction-shaped parameter gradient)
             xi = self.act(xi)                                     # :513
-        y = self.forward_core(xi, z, dirs)                        # :514-517 (scan, merge, out_norm, gate)
+        y = self.forward_core(xi, z, dirs, planes_u)              # :514-517 (scan, merge, out_norm, gate)
         return self.dropout(Fn.linear_tc(y, self.out_proj.weight, self.out_proj.bias))    # :518 (tensor cores when eligible)
 
 

@@ -354,6 +354,41 @@ def dwconv3_act(mode: int, x: torch.Tensor, weight: torch.Tensor, bias, dy=None)
     return y
 
 
+def dwconv3_act_planes_ok(x: torch.Tensor) -> bool:
+    return x.dim() == 4 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and x.shape[0] <= 65535 and x.shape[1] <= 65535
+
+
+def dwconv3_act_planes_fwd(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+    """u (B, 2 C, H W) = [SiLU(b + conv(x)) in natural pixel order | the same image transposed]: the two input planes of a
+    K = 4 SS2D scan written by the convolution kernel itself (no permuted copy, no cat)."""
+    _require(x.is_cuda and x.is_contiguous() and x.dtype in _DT and dwconv3_act_planes_ok(x), "dwconv3_act_planes: contiguous CUDA (B, C, H, W), H and W multiples of 4")
+    Bn, C, H, W = x.shape
+    w32 = weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    u = torch.empty((Bn, 2 * C, H * W), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_dwconv3_act_planes(0, _ptr(x), C * H * W, _ptr(w32), _ptr(b32), None, 0, None, 0, _ptr(u), 2 * C * H * W,
+                                                ctypes.c_void_p(u.data_ptr() + C * H * W * u.element_size()), 2 * C * H * W,
+                                                Bn, C, H, W, _DT[x.dtype], _stream(x.device))
+    _lib.check(rc, "ss2d_dwconv3_act_planes")
+    return u
+
+
+def dwconv3_act_planes_bwd(x: torch.Tensor, weight: torch.Tensor, bias, du: torch.Tensor) -> torch.Tensor:
+    """Gradient of the pre-activation from du (B, 2 C, H W) = [gradient of the natural plane | of the transposed plane]."""
+    Bn, C, H, W = x.shape
+    _require(du.is_cuda and du.is_contiguous() and du.dtype == x.dtype and du.shape == (Bn, 2 * C, H * W), "dwconv3_act_planes: du must be (B, 2 C, H W) like the forward's output")
+    w32 = weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    dpre = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_dwconv3_act_planes(1, _ptr(x), C * H * W, _ptr(w32), _ptr(b32), _ptr(du), 2 * C * H * W,
+                                                ctypes.c_void_p(du.data_ptr() + C * H * W * du.element_size()), 2 * C * H * W,
+                                                _ptr(dpre), C * H * W, None, 0, Bn, C, H, W, _DT[x.dtype], _stream(x.device))
+    _lib.check(rc, "ss2d_dwconv3_act_planes")
+    return dpre
+
+
 # ---- tensor-core projections (tcgen05): out = A W^T (+ bias) with split / permuted epilogues ---------------
 def linear_tc_supported(n_cols: int, K: int, dtype: torch.dtype) -> bool:
     return dtype in (torch.float32, torch.bfloat16) and bool(_lib.lib().ss2d_linear_tc_supported(int(n_cols), int(K), _DT[dtype]))

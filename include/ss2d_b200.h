@@ -210,6 +210,18 @@ size_t ss2d_dwconv3_wgrad_workspace_bytes(int32_t batch, int32_t C, int32_t H, i
 int ss2d_dwconv3_act(int32_t mode, const void* x, const float* weight, const float* bias, const void* dy, void* y,
                      int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, ss2d_stream_t stream);
 
+/* Same convolution + SiLU on (batch, C, H, W) planes addressed by explicit BATCH strides (elements; channel planes are
+ * contiguous), H % 4 == 0 and W % 4 == 0, with the cross-scan layout change folded in:
+ *   mode 0: y = SiLU(bias + conv(x)); when yT != NULL the result is ALSO stored in transposed pixel order (offset w * H + h)
+ *           — the image the column-major scan directions traverse as row-major (model/gm/csms6s.py:95-129, 172-206). y and yT
+ *           may be the two halves of one (batch, 2 C, H * W) buffer (batch stride 2 C H W): the scan's input planes, written
+ *           by the kernel that produces them, with no permuted copy and no concatenation pass;
+ *   mode 1: y = (dy + dyT^T) * SiLU'(bias + conv(x)): dyT (optional) is a second upstream gradient in transposed pixel order. */
+int ss2d_dwconv3_act_planes(int32_t mode, const void* x, int64_t x_batch_stride, const float* weight, const float* bias,
+                            const void* dy, int64_t dy_batch_stride, const void* dyT, int64_t dyT_batch_stride, void* y,
+                            int64_t y_batch_stride, void* yT, int64_t yT_batch_stride, int32_t batch, int32_t C, int32_t H,
+                            int32_t W, int32_t dtype, ss2d_stream_t stream);
+
 /* ---- row-wise LayerNorm over C <= 512 channels of channels-last rows --------------------------------
  * Replaces nn.LayerNorm as used by GroupMambaLayer.norm (model/gm/groupmamba.py:131, 156; two applications per layer
  * call with shared weights). x, y, dy, dx: (rows, C) contiguous, dtype = ss2d_dtype; weight / bias: (C) fp32 or NULL.
