@@ -95,7 +95,7 @@ def lib() -> ctypes.CDLL:
                                     ctypes.c_uint32, vp]
     L.ss2d_out_gate_fwd.restype = ctypes.c_int
     L.ss2d_out_gate_bwd.argtypes = [fp, i32, fp, fp, vp, i64, i32, vp, fp, fp, vp, i64, fp, fp, i32, i32, i32, i32,
-                                    i32, i32, i32, i32, ctypes.c_uint32, vp]
+                                    i32, i32, i32, i32, ctypes.c_uint32, i32, vp]
     L.ss2d_out_gate_bwd.restype = ctypes.c_int
     L.ss2d_out_gate_max_width.argtypes = [i32]
     L.ss2d_out_gate_max_width.restype = i32

@@ -33,7 +33,7 @@ cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const 
 cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
                                 int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
-                                int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream);
+                                int out_dtype, int H, int W, unsigned tmask, int dy_two_planes, cudaStream_t stream);
 int epi_bwd_partials(int batch, int L);
 int layernorm_bwd_partials(int64_t rows);
 int layernorm_max_C();
@@ -320,16 +320,17 @@ int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const 
                       int64_t z_row_stride, int32_t z_act, const void* dout, const float* mean_rstd, float* dy,
                       void* dz, int64_t dz_row_stride, float* dln_weight_partial, float* dln_bias_partial,
                       int32_t n_partials, int32_t batch, int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype,
-                      int32_t H, int32_t W, uint32_t transposed_mask, ss2d_stream_t stream) {
+                      int32_t H, int32_t W, uint32_t transposed_mask, int32_t dy_two_planes, ss2d_stream_t stream) {
   if (!ys || !dout || !mean_rstd || !dy || !dln_weight_partial || !dln_bias_partial) return SS2D_ERR_NULL_POINTER;
   if (batch <= 0 || D <= 0 || L <= 0 || K <= 0 || K > SS2D_MAX_GROUP_DIRS) return SS2D_ERR_BAD_SHAPE;
-  if (transposed_mask && (H <= 0 || W <= 0 || (int64_t)H * W != L)) return SS2D_ERR_BAD_SHAPE;
+  if ((transposed_mask || dy_two_planes) && (H <= 0 || W <= 0 || (int64_t)H * W != L)) return SS2D_ERR_BAD_SHAPE;
+  if (dy_two_planes && (K < 2 || !transposed_mask)) return SS2D_ERR_UNSUPPORTED;      // patch tiles are what makes the second store cheap
   if (n_partials != epi_bwd_partials(batch, L)) return SS2D_ERR_WORKSPACE;
   if (!dtype_ok(z_dtype) || !dtype_ok(out_dtype)) return SS2D_ERR_BAD_DTYPE;
   if (D > epi_max_D(true)) return SS2D_ERR_UNSUPPORTED;
   cudaError_t e = out_gate_bwd_launch(ys, K, ln_weight, ln_bias, z, z_row_stride, z_act, dout, mean_rstd, dy, dz,
                                       dz_row_stride, dln_weight_partial, dln_bias_partial, n_partials, batch, D, L,
-                                      z_dtype, out_dtype, H, W, transposed_mask, static_cast<cudaStream_t>(stream));
+                                      z_dtype, out_dtype, H, W, transposed_mask, dy_two_planes, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
   return SS2D_OK;

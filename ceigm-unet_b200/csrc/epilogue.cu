@@ -34,6 +34,7 @@ struct PlaneIdx {
 struct EpiGroups {
   int G;
   int64_t ys_bs, dy_bs, io_rs;
+  int dy_two_planes;     // backward, K > 1: dy is (batch, 2, D, L) — plane 0 natural pixel order, plane 1 transposed
   int64_t ys_off[SS2D_MAX_EPI_GROUPS], dy_off[SS2D_MAX_EPI_GROUPS], z_off[SS2D_MAX_EPI_GROUPS];
   int io_off[SS2D_MAX_EPI_GROUPS];
   unsigned tmask[SS2D_MAX_EPI_GROUPS];
@@ -234,7 +235,12 @@ out_gate_bwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
       // K == 1: the gradient belongs to the single plane and is written in ITS pixel order (transposed when tmask is set)
       int lo = l;
       if (K == 1 && pi.tmask) { const int h = l / pi.W, w = l - h * pi.W; lo = w * pi.H + h; }
-      dy[(int64_t)b * eg.dy_bs + (int64_t)d * L + lo] = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
+      const float gval = rstd * (s_g[d * (kEpiTL + 1) + px] - s_stat[px][2] - yn * s_stat[px][3]);
+      dy[(int64_t)b * eg.dy_bs + (int64_t)d * L + lo] = gval;
+      if (eg.dy_two_planes) {      // the same gradient once more in the pixel order of the transposed image (directions 2 / 4)
+        const int h = l / pi.W, w = l - h * pi.W;
+        dy[(int64_t)b * eg.dy_bs + (int64_t)(D + d) * L + w * pi.H + h] = gval;
+      }
     }
   }
   if (PP == 1) {
@@ -503,9 +509,11 @@ cudaError_t out_gate_fwd_launch(const float* ys, int K, const float* lnw, const 
 cudaError_t out_gate_bwd_launch(const float* ys, int K, const float* lnw, const float* lnb, const void* z, int64_t z_rs,
                                 int z_act, const void* dout, const float* mean_rstd, float* dy, void* dz, int64_t dz_rs,
                                 float* dw_part, float* db_part, int n_partials, int batch, int D, int L, int z_dtype,
-                                int out_dtype, int H, int W, unsigned tmask, cudaStream_t stream) {
+                                int out_dtype, int H, int W, unsigned tmask, int dy_two_planes, cudaStream_t stream) {
+  EpiGroups eg = epi_single(K, D, L, tmask);
+  if (dy_two_planes) { eg.dy_two_planes = 1; eg.dy_bs = (int64_t)2 * D * L; }
   return epi_bwd_launch(ys, K, lnw, lnb, z, z_rs, z_act, dout, mean_rstd, dy, dz, dz_rs, dw_part, db_part, n_partials, batch, D,
-                        L, z_dtype, out_dtype, H, W, epi_single(K, D, L, tmask), stream);
+                        L, z_dtype, out_dtype, H, W, eg, stream);
 }
 
 // G single-plane groups in one launch: ys (batch, G, D, L) with group g in plane plane_of[g]; out / dout / z / dz rows hold the

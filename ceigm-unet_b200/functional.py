@@ -186,7 +186,11 @@ class _OutGate(torch.autograd.Function):
         z_act, has_z, H, W, tmask, tplanes = ctx.meta
         Bn, G, P, D, L = ys.shape
         dz = torch.empty(z.shape, dtype=z.dtype, device=z.device) if has_z else None
-        dy, dw, db = ops.out_gate_bwd(ys.view(Bn, G * P, D, L), ln_w, ln_b, z, z_act, dout, stats, dz, (H, W), tmask)
+        two = P == 2 and tplanes == 0b10 and G * P > 1          # (natural, transposed) plane pairs: the kernel writes both orientations
+        dy, dw, db = ops.out_gate_bwd(ys.view(Bn, G * P, D, L), ln_w, ln_b, z, z_act, dout, stats, dz, (H, W), tmask, two_planes=two)
+        if two:      # (B, 2, D, L) straight from the kernel: no transposed copy, no stack
+            return (dy.unsqueeze(1).expand(Bn, G, P, D, L), (dw if ln_w is not None else None), (db if ln_b is not None else None), dz,
+                    None, None, None, None, None, None)
         # dy is the gradient of the merged y in natural pixel order; every group receives it (transposed for the groups
         # that ran on the transposed image). Returned as a stride-0 expansion over the K/P repeats: no K-fold copy.
         if G * P == 1:      # a single plane: the kernel already wrote dy in that plane's own (possibly transposed) pixel order

@@ -252,11 +252,13 @@ def _row_stride(z, Bn, L) -> int:
     return rs
 
 
-def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[torch.Tensor], hw=(0, 0), tmask: int = 0):
-    """-> dy (B, D, L) fp32, dln_w, dln_b. dz is written into `dz_out` (a (B, L, D) uniformly strided view)."""
+def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[torch.Tensor], hw=(0, 0), tmask: int = 0,
+                 two_planes: bool = False):
+    """-> dy (B, D, L) fp32, dln_w, dln_b. dz is written into `dz_out` (a (B, L, D) uniformly strided view).
+    two_planes (K > 1, tmask != 0): dy is (B, 2, D, L) — the merged gradient in natural and in transposed pixel order."""
     Bn, K, D, L = ys.shape
     dout = dout.contiguous()
-    dy = torch.empty((Bn, D, L), dtype=torch.float32, device=ys.device)
+    dy = torch.empty((Bn, 2, D, L) if two_planes else (Bn, D, L), dtype=torch.float32, device=ys.device)
     npart = int(_lib.lib().ss2d_out_gate_bwd_partials(Bn, L))
     part = torch.empty((2, npart, D), dtype=torch.float32, device=ys.device)
     zrs, zdt, dzrs = 0, _lib.SS2D_F32, 0
@@ -267,7 +269,7 @@ def out_gate_bwd(ys, ln_w, ln_b, z, z_act: bool, dout, stats, dz_out: Optional[t
         rc = _lib.lib().ss2d_out_gate_bwd(_ptr(ys), K, _ptr(ln_w), _ptr(ln_b), _ptr(z), zrs, int(z_act), _ptr(dout),
                                           _ptr(stats), _ptr(dy), _ptr(dz_out) if z is not None else None, dzrs,
                                           _ptr(part[0]), _ptr(part[1]), npart, Bn, D, L, zdt, _DT[dout.dtype],
-                                          int(hw[0]), int(hw[1]), ctypes.c_uint32(tmask), _stream(ys.device))
+                                          int(hw[0]), int(hw[1]), ctypes.c_uint32(tmask), 1 if two_planes else 0, _stream(ys.device))
     _lib.check(rc, "ss2d_out_gate_bwd")
     sums = part.sum(dim=1)
     return dy, sums[0], sums[1]

@@ -158,14 +158,17 @@ int ss2d_out_gate_fwd(const float* ys, int32_t K, const float* ln_weight, const 
  *     gradient of the single plane and is written in THAT plane's pixel order (transposed when bit 0 of
  *     transposed_mask is set) — (every direction receives the same gradient: pass it to
  *     ss2d_scan_bwd as a shared dout through u_dim_modulo). dz: gradient of the RAW z when z_act != 0, rows
- *     strided by dz_row_stride, or NULL. dln_*_partial: (n_partials, D) fp32, n_partials =
+ *     strided by dz_row_stride, or NULL. dy_two_planes != 0 (K > 1, some plane transposed): dy is (batch, 2, D, L) and receives
+ *     the merged gradient TWICE, plane 0 in natural and plane 1 in transposed pixel order — the two shared dout planes of
+ *     the K = 4 scan backward, written by the kernel that computes them instead of by a transpose-copy + stack.
+ *     dln_*_partial: (n_partials, D) fp32, n_partials =
  *     ss2d_out_gate_bwd_partials(batch, L); the caller sums over the first axis. */
 int ss2d_out_gate_bwd(const float* ys, int32_t K, const float* ln_weight, const float* ln_bias,
                       const void* z, int64_t z_row_stride, int32_t z_act, const void* dout,
                       const float* mean_rstd, float* dy, void* dz, int64_t dz_row_stride,
                       float* dln_weight_partial, float* dln_bias_partial, int32_t n_partials, int32_t batch,
                       int32_t D, int32_t L, int32_t z_dtype, int32_t out_dtype, int32_t H, int32_t W,
-                      uint32_t transposed_mask, ss2d_stream_t stream);
+                      uint32_t transposed_mask, int32_t dy_two_planes, ss2d_stream_t stream);
 int32_t ss2d_out_gate_bwd_partials(int32_t batch, int32_t L);
 
 /* ---- grouped epilogue: the G single-direction SS2Ds of one GroupMambaLayer in one launch ---------------------
