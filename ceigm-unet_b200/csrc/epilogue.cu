@@ -85,7 +85,7 @@ __device__ __forceinline__ void load_merged_tile(float* s_y, const float* __rest
     const float* p1 = base + plane + ((pi.tmask & 2u) ? lt : l);
     const float* p2 = base + 2 * plane + ((pi.tmask & 4u) ? lt : l);
     const float* p3 = base + 3 * plane + ((pi.tmask & 8u) ? lt : l);
-#pragma unroll 4
+#pragma unroll 12
     for (int d = threadIdx.x >> 5; d < D; d += kEpiThreads / 32) {
       const int64_t o = (int64_t)d * L;
       const float a = __ldg(p0 + o) + __ldg(p2 + o);
@@ -154,7 +154,7 @@ out_gate_fwd_kernel(const float* __restrict__ ys, int K, const float* __restrict
     for (int d = threadIdx.x; d < D; d += kEpiThreads) {
       const float wv = lnw ? __ldg(lnw + d) : 1.f, bv = (lnw && lnb) ? __ldg(lnb + d) : 0.f;
       const float* col = s_y + d * (kEpiTL + 1);
-#pragma unroll 8
+#pragma unroll 16
       for (int px = 0; px < kEpiTL; ++px) {
         const int l = s_pix[px];
         if (l < 0) continue;
