@@ -20,11 +20,38 @@ dwconv3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   const int c = blockIdx.x, slab = blockIdx.y;
   const int HW = H * W;
   const int64_t total = (int64_t)batch * HW;                 // pixels of this channel over the batch
-  const int64_t per = (total + slabs - 1) / slabs;
-  const int64_t p0 = (int64_t)slab * per, p1 = p0 + per < total ? p0 + per : total;
+  const int64_t per = ((total + slabs - 1) / slabs + 3) & ~(int64_t)3;      // slabs start on pixel quads
+  const int64_t p0 = (int64_t)slab * per < total ? (int64_t)slab * per : total, p1 = p0 + per < total ? p0 + per : total;
   float acc[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  if ((W & 3) == 0 && (p0 & 3) == 0) {
+    // four consecutive pixels of a row per thread: one vector load per input row (+ the two edge neighbours, L1 hits) and
+    // one of dy instead of forty scalar loads (the scalar walk below ran at 0.84 TB/s: 137 us at B = 24, C = 192, 56^2)
+    for (int64_t p = p0 + 4 * (int64_t)threadIdx.x; p < p1; p += 4 * kDwThreads) {
+      const int b = (int)(p / HW), hw = (int)(p - (int64_t)b * HW);
+      const int h = hw / W, w = hw - h * W;
+      const float* xp = x + ((int64_t)b * C + c) * HW;
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)b * C + c) * HW + hw));
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      const int nq = (int)(p1 - p < 4 ? p1 - p : 4);         // the slab may end inside the quad
+      float gm[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { gm[q] = q < nq ? g[q] : 0.f; acc[9] += gm[q]; }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h + ky - 1;
+        if (hh < 0 || hh >= H) continue;
+        const float* row = xp + hh * W + w;
+        const float4 m = __ldg(reinterpret_cast<const float4*>(row));
+        const float v[6] = {w > 0 ? __ldg(row - 1) : 0.f, m.x, m.y, m.z, m.w, w + 4 < W ? __ldg(row + 4) : 0.f};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[ky * 3 + kx] = fmaf(gm[q], v[q + kx], acc[ky * 3 + kx]);
+      }
+    }
+  } else
   for (int64_t p = p0 + threadIdx.x; p < p1; p += kDwThreads) {
     const int b = (int)(p / HW), hw = (int)(p - (int64_t)b * HW);
     const int h = hw / W, w = hw - h * W;
