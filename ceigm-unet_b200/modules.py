@@ -155,10 +155,17 @@ class SS2D(nn.Module, mamba_init):
             per_plane = [Fn.proj_cm(Wx[j::2].reshape((K // 2) * C, D), planes[j]).view(Bn, K // 2, C, L) for j in range(2)]
             x_dbl = torch.stack(per_plane, dim=2).view(Bn, K, C, L)                          # group order restored
         dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-        if K == 1:
-            dts = Fn.proj_cm(self.dt_projs_weight[0].to(dts_r.dtype), dts_r[:, 0])            # (B, D, L)
-        else:
-            dts = torch.matmul(self.dt_projs_weight.to(dts_r.dtype).unsqueeze(0), dts_r).reshape(Bn, K * D, L)
+        # dt_proj (ss2d.py:469). The scan takes delta in fp32 (force_fp32, :479-480): under autocast the R = dt_rank rows are
+        # cast up (a few MB) and the projection runs in fp32, so delta — the largest tensor of the call — is written once, in
+        # the type the scan reads, instead of once in bf16, read again and written again in fp32.
+        up = (not self.disable_force32) and dts_r.dtype != torch.float32
+        with torch.autocast("cuda", enabled=not up and torch.is_autocast_enabled("cuda")):
+            w_dt = self.dt_projs_weight.float() if up else self.dt_projs_weight.to(dts_r.dtype)
+            r_in = dts_r.float() if up else dts_r
+            if K == 1:
+                dts = Fn.proj_cm(w_dt[0], r_in[:, 0])                                        # (B, D, L)
+            else:
+                dts = torch.matmul(w_dt.unsqueeze(0), r_in).reshape(Bn, K * D, L)
         As = -torch.exp(self.A_logs.float())
         Ds = self.Ds.float()
         bias = self.dt_projs_bias.reshape(-1).float()
@@ -276,12 +283,20 @@ class GroupMambaLayer(nn.Module):
         wxp = [ms[g].x_proj_weight[0] for g in PL]                                  # (R + 2 N, D)
         W_dt = torch.block_diag(*[torch.matmul(ms[g].dt_projs_weight[0], wx[:R]) for g, wx in zip(PL, wxp)])     # (4 D, 4 D)
         W_bc = torch.block_diag(*[wx[R:] for wx in wxp])                            # (4 * 2 N, 4 D)
-        dts = Fn.proj_cm(W_dt.to(u.dtype), u)                                       # (B, 4 D, L)
+        if u.dtype != torch.float32:
+            # delta is consumed in fp32 by the scan (:479-480): project the fp32 copy of u the scan reads anyway, so delta is
+            # written once in that type (no bf16 round trip + cast of the largest tensor of the call)
+            uf = u.float()
+            with torch.autocast("cuda", enabled=False):
+                dts = Fn.proj_cm(W_dt.float(), uf)                                  # (B, 4 D, L) fp32
+        else:
+            uf = u
+            dts = Fn.proj_cm(W_dt.to(u.dtype), u)                                   # (B, 4 D, L)
         BC = Fn.proj_cm(W_bc.to(u.dtype), u).view(Bn, 4, 2 * N, L)
         As = -torch.exp(torch.cat([ms[g].A_logs for g in PL]).float())              # :473
         Ds = torch.cat([ms[g].Ds for g in PL]).float()
         bias = torch.cat([ms[g].dt_projs_bias.reshape(-1) for g in PL]).float()
-        uf, dts, BC = u.float().contiguous(), dts.float(), BC.float()               # force_fp32 (:479-480)
+        uf, dts, BC = uf.contiguous(), dts.float(), BC.float()                      # force_fp32 (:479-480)
         ys = Fn._SS2DScanNatural.apply(uf, dts, As, BC[:, :, :N], BC[:, :, N:], Ds, bias, H, W, (1, 3, 1, 3), 4)
         lnw = torch.stack([m.out_norm.weight for m in ms]).float()
         lnb = torch.stack([m.out_norm.bias for m in ms]).float()
