@@ -67,3 +67,33 @@ def test_rejects_bad_shapes():
         ops.linear_tc(x, W, None, [(24, "rows", False)])          # n_cols not a multiple of 16
     with pytest.raises(RuntimeError):
         ops.linear_tc(x.cpu(), W.cpu(), None, [(24, "rows", False)])
+
+
+def test_no_write_outside_the_outputs():
+    """Guard bands around both output parts (rows and planes), M not a multiple of the 128-row tile: the epilogue's row
+    clipping must keep every store inside [0, M) — checked through the C ABI with outputs placed inside sentinel buffers."""
+    import ctypes
+    from ceigm_unet_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Bn, Lp, K, D = 3, 50, 64, 48                       # M = 150: one full tile + a 22-row tail
+    M = Bn * Lp
+    x = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(2 * D, K, device="cuda", generator=g) / 8
+    PAD = 4096
+    buf_p = torch.full((PAD + Bn * D * Lp + PAD,), 777.0, device="cuda")
+    buf_r = torch.full((PAD + M * D + PAD,), 777.0, device="cuda")
+    parts = (_lib.LinearPart * 2)()
+    parts[0].out, parts[0].ld, parts[0].n_cols, parts[0].planes_L, parts[0].act = buf_p.data_ptr() + 4 * PAD, 0, D, Lp, 0
+    parts[1].out, parts[1].ld, parts[1].n_cols, parts[1].planes_L, parts[1].act = buf_r.data_ptr() + 4 * PAD, D, D, 0, 0
+    rc = L.ss2d_linear_tc(ctypes.c_void_p(x.data_ptr()), K, ctypes.c_void_p(W.data_ptr()), K, None, M, 2 * D, K, _lib.SS2D_F32, 2, parts,
+                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = x.double() @ W.double().t()
+    for buf, n in ((buf_p, Bn * D * Lp), (buf_r, M * D)):
+        assert bool((buf[:PAD] == 777.0).all()) and bool((buf[PAD + n:] == 777.0).all())
+    planes = buf_p[PAD:PAD + Bn * D * Lp].view(Bn, D, Lp)
+    rows = buf_r[PAD:PAD + M * D].view(M, D)
+    assert _rel(planes, ref[:, :D].reshape(Bn, Lp, D).transpose(1, 2)) < 4e-4
+    assert _rel(rows, ref[:, D:]) < 4e-4
