@@ -97,11 +97,27 @@ class ScanProblem:
         d.u_dim_modulo = self.u_mod
         self.desc = d
         self.ckpt_floats = int(_lib.lib().ss2d_scan_ckpt_floats(ctypes.byref(d)))
+        # 16-bit I/O: the kernels compute in fp32 either way, but only fp32 operands are staged by TMA and reach the fast
+        # backward (csrc/scan_bwd2.cu); 16-bit tensors go through an index-mapped staging path that is 3 x slower
+        # (fwd 1.47 vs 0.43 ms, bwd 3.21 vs 1.12 ms at B = 24, Dt = 768, L = 3136, N = 16). The scan is compute-bound there, so
+        # the 16-bit call is routed through the fp32 kernels with cast passes around them (HBM-bound, ~15 % of the call):
+        # identical arithmetic (the 16-bit values are exact in fp32), results rounded once on the way out.
+        self._upcast = u.dtype != torch.float32
+        self._inner = None
+
+    def _fp32_twin(self):
+        if self._inner is None:
+            self._inner = ScanProblem(self.u.float(), self.delta.float(), self.A, self.B.float(), self.C.float(), self.D, self.bias,
+                                      self.softplus, out_float=True, hw=self.hw, dirs=self.dirs, u_mod=self.u_mod)
+        return self._inner
 
     # ---- forward ----
     def forward(self, want_state: bool = True):
         """-> (out (B, Dt, L), x). `x` has the reference's shape convention (B, Dt, 1, 2N): x[:, :, -1, 1::2] is the
         final state; the chunk checkpoints for the backward live in front of it in the same storage."""
+        if self._upcast:
+            out32, x = self._fp32_twin().forward(want_state)
+            return out32.to(self.out_dtype), x
         d, dev = self.desc, self.delta.device
         out = torch.empty((self.batch, self.dim, self.L), dtype=self.out_dtype, device=dev)
         d.out_batch_stride, d.out_dim_stride = out.stride(0), out.stride(1)
@@ -138,6 +154,12 @@ class ScanProblem:
         dch = self.u_mod if self.u_mod else self.dim
         _require(dout.is_cuda and dout.dtype == self.out_dtype, "dout must be a CUDA tensor of out's dtype")
         _require(tuple(dout.shape) == (self.batch, dch, self.L), "dout must be (batch, dim, seqlen)")
+        if self._upcast:
+            du, ddelta, dA, dB, dC, dD, dbias = self._fp32_twin().backward(dout.float(), x)
+            dB, dC = dB.to(self.B.dtype), dC.to(self.C.dtype)
+            if self.squeeze_BC:
+                dB, dC = dB[:, 0], dC[:, 0]
+            return [du.to(self.u.dtype), ddelta.to(self.delta.dtype), dA, dB, dC, dD, dbias]
         if dout.stride(-1) != 1:                                  # csms6s.py:360-361 does the same before calling bwd
             dout = dout.contiguous()
         d.out_batch_stride, d.out_dim_stride = dout.stride(0), dout.stride(1)
