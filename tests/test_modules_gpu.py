@@ -376,3 +376,36 @@ def test_ss2d_tensor_core_projections_bf16_autocast(monkeypatch):
     assert rel_err(x.grad, ref[1].cpu().numpy()) < 2e-2
     for n, p in m.named_parameters():
         assert rel_err(p.grad.float(), ref[2][n].cpu().numpy()) < 4e-2, n
+
+
+def test_ss2d_tensor_core_path_cuda_graphs_match_eager():
+    """The tcgen05 projections (tensor maps encoded per call, passed by value) and the two-plane convolution kernel under
+    graphed(): replays with new input values reproduce the eager module (TF32 matmuls allowed on both sides)."""
+    import copy
+
+    import ceigm_unet_b200 as P
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        torch.manual_seed(2)
+        eager = P.SS2D(d_model=32, d_state=16, ssm_ratio=2.0, k_group=4).cuda()
+        captured = copy.deepcopy(eager)
+        x = torch.randn(3, 12, 16, 32, device="cuda", requires_grad=True)
+        gy = torch.randn(3, 12, 16, 32, device="cuda")
+        g = P.graphed(captured, (x.detach().clone().requires_grad_(True),))
+        res = []
+        for fn, mod in ((g, captured), (eager, eager)):
+            for rep in range(2):
+                xin = (x.detach() * (1.0 + 0.5 * rep)).requires_grad_(True)
+                for p_ in mod.parameters():
+                    p_.grad = None
+                y = fn(xin)
+                y.backward(gy)
+            res.append((y.detach().clone(), xin.grad.clone(), [p_.grad.clone() for p_ in mod.parameters()]))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    (y1, gx1, gp1), (y2, gx2, gp2) = res
+    assert rel_err(y1, y2.cpu().numpy()) < 1e-5
+    assert rel_err(gx1, gx2.cpu().numpy()) < 1e-4
+    for a, b in zip(gp1, gp2):
+        assert rel_err(a, b.cpu().numpy()) < 1e-3
