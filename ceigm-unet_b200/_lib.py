@@ -24,7 +24,7 @@ EXPORTS = [
     "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_out_gate_fwd", "ss2d_out_gate_bwd",
     "ss2d_out_gate_bwd_partials", "ss2d_group_gate_fwd", "ss2d_group_gate_bwd", "ss2d_out_gate_max_width", "ss2d_wgrad_ts", "ss2d_wgrad_ts_workspace_bytes",
     "ss2d_layernorm_fwd", "ss2d_layernorm_bwd", "ss2d_layernorm_bwd_partials",
-    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_dwconv3_act", "ss2d_dwconv3_act_planes", "ss2d_linear_tc", "ss2d_linear_tc_supported", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count",
+    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_dwconv3_act", "ss2d_dwconv3_act_planes", "ss2d_gate_proj_fwd", "ss2d_gate_proj_supported", "ss2d_linear_tc", "ss2d_linear_tc_supported", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count",
 ]
 
 
@@ -126,6 +126,11 @@ def lib() -> ctypes.CDLL:
     L.ss2d_dwconv3_act.restype = ctypes.c_int
     L.ss2d_dwconv3_act_planes.argtypes = [i32, vp, i64, fp, fp, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
     L.ss2d_dwconv3_act_planes.restype = ctypes.c_int
+    L.ss2d_gate_proj_fwd.argtypes = [fp, i32, ctypes.c_uint32, fp, fp, ctypes.c_float, vp, i64, i32, vp, i64, fp, vp, i64, vp, i64, fp,
+                                     i32, i32, i32, i32, i32, i32, i32, vp]
+    L.ss2d_gate_proj_fwd.restype = ctypes.c_int
+    L.ss2d_gate_proj_supported.argtypes = [i32, i32, i32, i32]
+    L.ss2d_gate_proj_supported.restype = i32
     L.ss2d_linear_tc.argtypes = [vp, i64, vp, i64, fp, i32, i32, i32, i32, i32, ctypes.POINTER(LinearPart), vp]
     L.ss2d_linear_tc.restype = ctypes.c_int
     L.ss2d_linear_tc_supported.argtypes = [i32, i32, i32]

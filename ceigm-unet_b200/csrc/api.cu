@@ -66,6 +66,11 @@ cudaError_t dwconv3_fused_launch(int mode, const void* x, const float* wgt, cons
 cudaError_t dwconv3_tiled_launch(int mode, const void* x, const float* wgt, const float* bias, const void* dy, const void* dyT,
                                  void* y, void* yT, int batch, int C, int H, int W, int64_t x_bs, int64_t y_bs, int64_t yT_bs,
                                  int64_t dy_bs, int64_t dyT_bs, int dt, cudaStream_t stream);
+bool gate_proj_tc_supported(int D, int C, int K, int dtype);
+int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw, const float* lnb, float eps, const void* z,
+                        int64_t z_rs, int z_act, const void* W, int64_t ldw, const float* bias, void* out, int64_t out_rs,
+                        void* g_out, int64_t g_rs, float* mean_rstd, int batch, int D, int L, int H, int Wd, int C, int dtype,
+                        cudaStream_t stream, cudaError_t* cerr);
 bool linear_tc_supported(int N_part, int K, int dtype);
 int linear_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, int M, int N, int K, int dtype,
                      int n_parts, const ss2d_linear_part* parts, cudaStream_t stream, cudaError_t* cerr);
@@ -486,6 +491,21 @@ int ss2d_dwconv3_act_planes(int32_t mode, const void* x, int64_t x_batch_stride,
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
   return SS2D_OK;
+}
+
+int32_t ss2d_gate_proj_supported(int32_t D, int32_t C, int32_t K, int32_t dtype) { return gate_proj_tc_supported(D, C, K, dtype) ? 1 : 0; }
+
+int ss2d_gate_proj_fwd(const float* ys, int32_t K, uint32_t transposed_mask, const float* ln_weight, const float* ln_bias, float eps,
+                       const void* z, int64_t z_row_stride, int32_t z_act, const void* W, int64_t ldw, const float* bias, void* out,
+                       int64_t out_row_stride, void* g_out, int64_t g_row_stride, float* mean_rstd, int32_t batch, int32_t D,
+                       int32_t L, int32_t H, int32_t Wd, int32_t C, int32_t dtype, ss2d_stream_t stream) {
+  cudaError_t e = cudaSuccess;
+  const int rc = gate_proj_tc_launch(ys, K, transposed_mask, ln_weight, ln_bias, eps, z, z_row_stride, z_act, W, ldw, bias, out,
+                                     out_row_stride, g_out, g_row_stride, mean_rstd, batch, D, L, H, Wd, C, dtype,
+                                     static_cast<cudaStream_t>(stream), &e);
+  if (rc == SS2D_ERR_CUDA) return cuda_fail(e);
+  if (rc == SS2D_OK) ++g_launches;
+  return rc;
 }
 
 int32_t ss2d_linear_tc_supported(int32_t n_cols, int32_t K, int32_t dtype) { return linear_tc_supported(n_cols, K, dtype) ? 1 : 0; }

@@ -1,0 +1,438 @@
+// The SS2D epilogue with the output projection folded in (north-star property 5): merge over the K directions +
+// un-transposition + (B, D, L) -> (B, L, D) + out_norm LayerNorm(D) + SiLU(z) gate + out_proj, ONE kernel.
+//
+// Replaces CrossMerge, the transpose copy, out_norm, act(z), `y * z` and out_proj of
+// /root/reference/gm-unet/model/gm/ss2d.py:486-498, 506-508, 515-518 (the two-kernel version is csrc/epilogue.cu's
+// out_gate_fwd followed by linear_tc). The gated tensor never has to reach HBM: the producer warps build it directly in shared
+// memory in the layout the tensor core reads (K-major, 128-byte swizzle), a 128-pixel x D tile at a time, and one thread issues
+// tcgen05.mma against the resident out_proj weight; the accumulators live in tensor memory and leave through the epilogue warps
+// as whole row pieces. For the backward of a training step the gated tensor can be written out as well (g_out != NULL).
+//
+// Warp roles (512 threads): warp 0 loads W once by TMA; warp 1 issues the MMAs; warp 2 owns the TMEM allocation; warps 4-11
+// (256 threads) PRODUCE the A tile; warps 12-15 are the epilogue. A tile is an 8 (h) x 16 (w) pixel patch, so that planes in
+// natural pixel order are read in 64-byte runs and planes in transposed order (column-major directions run as row-major scans of
+// the transposed image) in 32-byte runs. Per tile the producers
+//   A. sum the natural-order planes:   lanes along w, a thread owns (pixel, 4 channels) -> one conflict-free 16-byte store into
+//      the fp32 tile, which already has the tensor core's layout (pixel m = row, channels = K);
+//   B. add the transposed-order planes: lanes along h (a different pixel <-> lane map), read-modify-write of the tile;
+//      (the pixel numbering m(h, w) = 16 h + ((w + h) & 15) makes both maps hit 8 distinct swizzle slots per quarter warp)
+//   C. two-pass LayerNorm statistics per pixel (two threads per pixel, halves combined through shared memory);
+//   D. normalise, affine, multiply by SiLU(z), round (TF32: in place; bf16: into a second, bf16 tile), optionally store G.
+// Handshakes: `ready` (producers -> MMA), `afree` (tcgen05.commit -> producers: the tile may be overwritten), tmem_full /
+// tmem_empty per accumulator stage (MMA <-> epilogue; the producers also wait for tmem_empty before they reuse the pixel table
+// of that stage). The only CTA-wide barrier is in the prologue; the producers synchronise among themselves with a named barrier.
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace ss2d {
+
+constexpr int GP_THREADS = 512;
+constexpr int GP_PROD0 = 4, GP_PROD_WARPS = 8, GP_EPI0 = 12, GP_EPI_WARPS = 4;
+constexpr int GP_PT = 32 * GP_PROD_WARPS;     // producer threads
+constexpr int GP_TILE = 128, GP_TH = 8, GP_TW = 16;
+constexpr int GP_BLOCK = GP_TILE * 128;       // one K block of an operand tile: 128 rows x 128 bytes
+
+struct GpParams {
+  const float* ys;            // (batch, K, D, L) fp32
+  int K;
+  unsigned tmask;             // bit k: plane k is in the pixel order of the transposed image
+  int64_t ys_bs;
+  const float* lnw;
+  const float* lnb;
+  float eps;
+  const void* z;              // rows (batch * L) x D (+ column offset folded into the pointer), dtype of the operands
+  int64_t z_rs;
+  int z_act;
+  void* out;                  // (batch * L, C) rows
+  int64_t out_rs;
+  void* g_out;                // optional (batch * L, D) rows: the gated tensor, for the backward
+  int64_t g_rs;
+  float* mean_rstd;           // optional (batch * L, 2)
+  const float* bias;          // optional (C)
+  int batch, D, L, H, W, C;
+  int tiles_w, tiles_per_batch, n_tiles;
+  int kb32;                   // D / 32: K blocks of the fp32 tile
+  int kblocks;                // K blocks of the MMA operands (D * esize / 128)
+  int acc_stride;
+};
+
+__device__ __forceinline__ void gp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GP_PT) : "memory"); }
+// byte offset of channels [4 cq, 4 cq + 4) of pixel row m in the fp32 tile (K-major, 128-byte swizzle)
+__device__ __forceinline__ uint32_t gp_y_off(int m, int cq) { return (uint32_t)(cq >> 3) * GP_BLOCK + m * 128 + (((cq & 7) ^ (m & 7)) << 4); }
+__device__ __forceinline__ float gp_silu(float x) { return __fdividef(x, 1.f + ex2f(-x * kLog2e)); }
+__device__ __forceinline__ float gp_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+template <bool TF32>
+__global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpParams p, const __grid_constant__ TMap wmap) {
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  const uint32_t sm = (smem_u32(gp_smem_raw) + 1023u) & ~1023u;
+  unsigned char* smp = gp_smem_raw + (sm - smem_u32(gp_smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_bytes = (uint32_t)p.kblocks * p.C * 128u;
+  const uint32_t a_w = sm;
+  const uint32_t a_y = sm + ((w_bytes + 1023u) & ~1023u);            // fp32 tile: kb32 blocks
+  const uint32_t a_a16 = a_y + (uint32_t)p.kb32 * GP_BLOCK;           // bf16 operand tile (bf16 variant only)
+  const uint32_t a_slabs = a_a16 + (TF32 ? 0u : (uint32_t)p.kblocks * GP_BLOCK);
+  const uint32_t a_misc = a_slabs + GP_EPI_WARPS * 4096u;
+  // misc: barriers + tmem pointer (128 B) | pixel tables 2 x 128 ints | statistics partials 2 x 256 floats
+  const uint32_t b_w = a_misc, b_ready = a_misc + 8, b_afree = a_misc + 16, b_tfull = a_misc + 24, b_tempty = a_misc + 40, a_tptr = a_misc + 56;
+  const uint32_t b_wready = a_misc + 64;                                // TF32: W rounded in place by the producers
+  int* s_pix = reinterpret_cast<int*>(smp + (a_misc - sm) + 128);       // [2][128]
+  float* s_part = reinterpret_cast<float*>(s_pix + 2 * GP_TILE);       // [2][256]
+  const uint32_t tmem_cols = 2u * p.acc_stride;
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_w));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_ready), "r"(GP_PROD_WARPS));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_afree));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_wready), "r"(GP_PROD_WARPS));
+    for (int a = 0; a < 2; ++a) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_tfull + 8 * a));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_tempty + 8 * a), "r"(GP_EPI_WARPS));
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_tptr), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(a_tptr));
+
+  const int D = p.D, L = p.L, H = p.H, W = p.W;
+  const int64_t plane = (int64_t)D * L;
+
+  if (warp == 0) {
+    // ================================ W: one TMA load per K block ================================
+    if (lane == 0) {
+      tma_prefetch_desc(&wmap);
+      const int kb_elems = TF32 ? 32 : 64;
+      tc_mbar_expect(b_w, w_bytes);
+      for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(a_w + (uint32_t)kb * p.C * 128u, &wmap, kb * kb_elems, 0, b_w);
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t fmt = TF32 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(GP_TILE >> 4) << 24);
+      const uint32_t a_op = TF32 ? a_y : a_a16;
+      tc_mbar_wait(TF32 ? b_wready : b_w, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        tc_mbar_wait(b_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator stage
+        tc_mbar_wait(b_ready, it & 1);                               // the producers have finished the operand tile
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma<TF32>(d_tmem, tc_smem_desc(a_op + (uint32_t)kb * GP_BLOCK + kk * 32), tc_smem_desc(a_w + (uint32_t)kb * p.C * 128u + kk * 32),
+                         idesc, (kb | kk) != 0);
+        }
+        tc_commit(b_afree);              // the operand tile may be overwritten once these MMAs have read it
+        tc_commit(b_tfull + 8 * acc);    // accumulator complete
+      }
+    }
+  } else if (warp >= GP_PROD0 && warp < GP_EPI0) {
+    // ================================ producers ================================
+    const int pt = threadIdx.x - 32 * GP_PROD0, pw = pt >> 5;
+    const bool any_t = p.tmask != 0u;
+    if (TF32) {      // the tensor core truncates fp32 containers: round the resident weight to nearest TF32 once
+      tc_mbar_wait(b_w, 0);
+      for (uint32_t o = (uint32_t)pt * 16u; o < w_bytes; o += GP_PT * 16u) {
+        const float4 v = lds128(a_w + o);
+        sts128(a_w + o, make_float4(gp_rna(v.x), gp_rna(v.y), gp_rna(v.z), gp_rna(v.w)));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(b_wready);
+    }
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
+      const int th = tib / p.tiles_w, tw = tib - th * p.tiles_w;
+      const int h0 = th * GP_TH, w0 = tw * GP_TW;
+      int* pix = s_pix + (it & 1) * GP_TILE;
+      tc_mbar_wait(b_tempty + 8 * (it & 1), ((it >> 1) & 1) ^ 1);    // epilogue of tile it - 2 done: its pixel table is free
+      tc_mbar_wait(b_afree, (it & 1) ^ 1);                           // MMAs of tile it - 1 have read the operand tile
+      if (pt < GP_TILE) {
+        const int hh = pt >> 4, ww = ((pt & 15) - hh) & 15;
+        const int h = h0 + hh, w = w0 + ww;
+        pix[pt] = (h < H && w < W) ? h * W + w : -1;
+      }
+      const float* ysb = p.ys + (int64_t)b * p.ys_bs;
+      // ---- A / B: one pass per plane, UNR channel quads (4 UNR independent loads) in flight per thread. Natural-order planes:
+      //      warp = patch row hh, lanes 0-15 / 16-31 = two channel-quad streams along w. Transposed-order planes: lanes = 8 h x 4 w
+      //      (32-byte runs along h), warp = w quad + channel-quad stream. The first pass stores, the others read-modify-write
+      //      (same thread, same elements within a kind; a named barrier separates the two kinds).
+      constexpr int UNR = 12;
+      bool first = true;
+      {
+        const int hh = pw, ww = lane & 15;
+        const int h = h0 + hh, w = w0 + ww;
+        const bool ok = h < H && w < W;
+        const int m = hh * 16 + ((ww + hh) & 15);
+        const int nq = D / 8;                               // quads of this thread's stream: cq = (lane >> 4) + 2 i
+        for (int k = 0; k < p.K; ++k) {
+          if ((p.tmask >> k) & 1u) continue;
+          const float* src = ysb + k * plane + (int64_t)h * W + w;
+          for (int i0 = 0; i0 < nq; i0 += UNR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const int cq = (lane >> 4) + 2 * (i0 + u);
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok && i0 + u < nq) {
+                const float* q = src + (int64_t)(4 * cq) * L;
+                v[u] = make_float4(__ldg(q), __ldg(q + L), __ldg(q + 2 * (int64_t)L), __ldg(q + 3 * (int64_t)L));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              if (i0 + u >= nq) break;
+              const uint32_t o = a_y + gp_y_off(m, (lane >> 4) + 2 * (i0 + u));
+              if (!first) { const float4 t4 = lds128(o); v[u].x += t4.x; v[u].y += t4.y; v[u].z += t4.z; v[u].w += t4.w; }
+              sts128(o, v[u]);
+            }
+          }
+          first = false;
+        }
+      }
+      gp_bar_sync();
+      if (any_t) {
+        const int hh = lane & 7, ww = 4 * (pw & 3) + (lane >> 3);
+        const int h = h0 + hh, w = w0 + ww;
+        const bool ok = h < H && w < W;
+        const int m = hh * 16 + ((ww + hh) & 15);
+        const int nq = D / 8;                               // cq = (pw >> 2) + 2 i
+        for (int k = 0; k < p.K; ++k) {
+          if (!((p.tmask >> k) & 1u)) continue;
+          const float* src = ysb + k * plane + (int64_t)w * H + h;
+          for (int i0 = 0; i0 < nq; i0 += UNR) {
+            float4 v[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              const int cq = (pw >> 2) + 2 * (i0 + u);
+              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok && i0 + u < nq) {
+                const float* q = src + (int64_t)(4 * cq) * L;
+                v[u] = make_float4(__ldg(q), __ldg(q + L), __ldg(q + 2 * (int64_t)L), __ldg(q + 3 * (int64_t)L));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+              if (i0 + u >= nq) break;
+              const uint32_t o = a_y + gp_y_off(m, (pw >> 2) + 2 * (i0 + u));
+              if (!first) { const float4 t4 = lds128(o); v[u].x += t4.x; v[u].y += t4.y; v[u].z += t4.z; v[u].w += t4.w; }
+              sts128(o, v[u]);
+            }
+          }
+          first = false;
+        }
+        gp_bar_sync();
+      }
+      // ---- C: LayerNorm statistics, two threads per pixel (channel halves), two passes ----
+      const int m = pt & (GP_TILE - 1), hf = pt >> 7;
+      const int cq0 = hf * (D / 8), cq1 = cq0 + D / 8;
+      const int l = pix[m];
+      {
+        float s = 0.f;
+        for (int cq = cq0; cq < cq1; ++cq) { const float4 v = lds128(a_y + gp_y_off(m, cq)); s += (v.x + v.y) + (v.z + v.w); }
+        s_part[pt] = s;
+      }
+      gp_bar_sync();
+      const float mean = (s_part[m] + s_part[m + GP_TILE]) / D;
+      {
+        float q = 0.f;
+        for (int cq = cq0; cq < cq1; ++cq) {
+          const float4 v = lds128(a_y + gp_y_off(m, cq));
+          const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+          q = fmaf(a0, a0, q); q = fmaf(a1, a1, q); q = fmaf(a2, a2, q); q = fmaf(a3, a3, q);
+        }
+        s_part[GP_PT + pt] = q;
+      }
+      gp_bar_sync();
+      const float rstd = rsqrtf((s_part[GP_PT + m] + s_part[GP_PT + m + GP_TILE]) / D + p.eps);
+      const int64_t row = (int64_t)b * L + (l >= 0 ? l : 0);
+      if (hf == 0 && l >= 0 && p.mean_rstd) { p.mean_rstd[row * 2] = mean; p.mean_rstd[row * 2 + 1] = rstd; }
+      // ---- D: normalise, affine, gate, round into the operand tile (ZU gate quads requested before they are used) ----
+      constexpr int ZU = 8;
+      for (int c0 = cq0; c0 < cq1; c0 += ZU) {
+        float zq[ZU][4];
+        if (p.z && l >= 0) {
+#pragma unroll
+          for (int u = 0; u < ZU; ++u) {
+            const int cq = c0 + u;
+            if (cq >= cq1) break;
+            if (TF32) {
+              const float4 zv = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.z) + row * p.z_rs) + cq);
+              zq[u][0] = zv.x; zq[u][1] = zv.y; zq[u][2] = zv.z; zq[u][3] = zv.w;
+            } else {
+              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.z) + row * p.z_rs) + cq);
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+              const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+              zq[u][0] = a.x; zq[u][1] = a.y; zq[u][2] = c.x; zq[u][3] = c.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < ZU; ++u) {
+          const int cq = c0 + u;
+          if (cq >= cq1) break;
+          const float4 v = lds128(a_y + gp_y_off(m, cq));
+          float g[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+          if (p.lnw) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(p.lnw) + cq);
+            const float4 bv = p.lnb ? __ldg(reinterpret_cast<const float4*>(p.lnb) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g[0] = fmaf(g[0], wv.x, bv.x); g[1] = fmaf(g[1], wv.y, bv.y); g[2] = fmaf(g[2], wv.z, bv.z); g[3] = fmaf(g[3], wv.w, bv.w);
+          }
+          if (l < 0) { g[0] = g[1] = g[2] = g[3] = 0.f; }
+          if (p.z && l >= 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g[i] *= p.z_act ? gp_silu(zq[u][i]) : zq[u][i];
+          }
+          if (TF32) {
+            if (p.g_out && l >= 0)
+              *(reinterpret_cast<float4*>(static_cast<float*>(p.g_out) + row * p.g_rs) + cq) = make_float4(g[0], g[1], g[2], g[3]);
+            sts128(a_y + gp_y_off(m, cq), make_float4(gp_rna(g[0]), gp_rna(g[1]), gp_rna(g[2]), gp_rna(g[3])));
+          } else {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(g[0], g[1]), hi = __floats2bfloat162_rn(g[2], g[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            if (p.g_out && l >= 0) *(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.g_out) + row * p.g_rs) + cq) = pk;
+            // bf16 operand tile: 64 channels per 128-byte row, 16-byte chunk = 8 channels = two quads
+            const uint32_t o = (uint32_t)(cq >> 4) * GP_BLOCK + m * 128 + ((((cq >> 1) & 7) ^ (m & 7)) << 4) + ((cq & 1) << 3);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_a16 + o), "r"(pk.x), "r"(pk.y) : "memory");
+          }
+        }
+      }
+      fence_proxy_async();           // generic-proxy writes before the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(b_ready);
+    }
+  } else if (warp >= GP_EPI0) {
+    // ================================ epilogue ================================
+    const int lq = warp & 3;                    // TMEM lanes 32 lq ... (warp id % 4)
+    const uint32_t slab = a_slabs + (uint32_t)(warp - GP_EPI0) * 4096u;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int b = t / p.tiles_per_batch;
+      const int* pix = s_pix + (it & 1) * GP_TILE;
+      tc_mbar_wait(b_tfull + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)acc * p.acc_stride;
+      for (int c = 0; c < p.C; c += 32) {
+        const int nc = min(32, p.C - c);
+        float v[32];
+        if (nc == 32) tc_ld32(taddr + c, v); else tc_ld16(taddr + c, v);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < nc) v[i] += __ldg(p.bias + c + i);
+        }
+        __syncwarp();
+        if (TF32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            sts128(slab + lane * 128 + ((i ^ (lane & 7)) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          __syncwarp();
+          const int pieces = nc / 4, rows_per = 32 / pieces, pc = lane % pieces;
+          for (int r = lane / pieces; r < 32; r += rows_per) {
+            const int l = pix[lq * 32 + r];
+            if (l < 0) continue;
+            const float4 tv = lds128(slab + r * 128 + ((pc ^ (r & 7)) << 4));
+            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + ((int64_t)b * L + l) * p.out_rs + c + pc * 4) = tv;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 hv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hv[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+            const uint4 u = *reinterpret_cast<uint4*>(hv);
+            sts128(slab + lane * 128 + ((i ^ (lane & 7)) << 4), make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)));
+          }
+          __syncwarp();
+          const int pieces = nc / 8, rows_per = 32 / pieces, pc = lane % pieces;
+          for (int r = lane / pieces; r < 32; r += rows_per) {
+            const int l = pix[lq * 32 + r];
+            if (l < 0) continue;
+            const float4 tv = lds128(slab + r * 128 + ((pc ^ (r & 7)) << 4));
+            *reinterpret_cast<float4*>(static_cast<__nv_bfloat16*>(p.out) + ((int64_t)b * L + l) * p.out_rs + c + pc * 8) = tv;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(b_tempty + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+static size_t gp_smem_bytes(int D, int C, int esize) {
+  const int kblocks = D * esize / 128;
+  const size_t w = ((size_t)kblocks * C * 128 + 1023) & ~(size_t)1023;
+  const size_t y = (size_t)(D / 32) * GP_BLOCK;
+  const size_t a16 = esize == 2 ? (size_t)kblocks * GP_BLOCK : 0;
+  return w + y + a16 + GP_EPI_WARPS * 4096 + 128 + 2 * GP_TILE * 4 + 2 * GP_PT * 4 + 1024 /* alignment slack */;
+}
+
+bool gate_proj_tc_supported(int D, int C, int K, int dtype) {
+  if (dtype != SS2D_F32 && dtype != SS2D_BF16) return false;
+  if (D <= 0 || (D % 64) != 0 || C < 16 || C > 256 || (C & 15) || K < 1 || K > SS2D_MAX_GROUP_DIRS) return false;
+  return gp_smem_bytes(D, C, dtype == SS2D_F32 ? 4 : 2) <= 227 * 1024;
+}
+
+// Returns an ss2d_status; *cerr receives the CUDA error behind SS2D_ERR_CUDA.
+int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw, const float* lnb, float eps, const void* z,
+                        int64_t z_rs, int z_act, const void* W, int64_t ldw, const float* bias, void* out, int64_t out_rs,
+                        void* g_out, int64_t g_rs, float* mean_rstd, int batch, int D, int L, int H, int Wd, int C, int dtype,
+                        cudaStream_t stream, cudaError_t* cerr) {
+  *cerr = cudaSuccess;
+  if (!ys || !W || !out) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || L <= 0 || H <= 0 || Wd <= 0 || (int64_t)H * Wd != L) return SS2D_ERR_BAD_SHAPE;
+  if (!gate_proj_tc_supported(D, C, K, dtype)) return SS2D_ERR_UNSUPPORTED;
+  const int esize = dtype == SS2D_F32 ? 4 : 2;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(out) || ((out_rs * esize) & 15) || (z && (!al16(z) || ((z_rs * esize) & 15))) || (g_out && (!al16(g_out) || ((g_rs * esize) & 15))) ||
+      (lnw && !al16(lnw)) || (lnb && !al16(lnb)))
+    return SS2D_ERR_ALIGNMENT;
+  GpParams p;
+  memset(&p, 0, sizeof(p));
+  p.ys = ys; p.K = K; p.tmask = tmask; p.ys_bs = (int64_t)K * D * L; p.lnw = lnw; p.lnb = lnb; p.eps = eps;
+  p.z = z; p.z_rs = z_rs; p.z_act = z_act; p.out = out; p.out_rs = out_rs; p.g_out = g_out; p.g_rs = g_rs; p.mean_rstd = mean_rstd;
+  p.bias = bias; p.batch = batch; p.D = D; p.L = L; p.H = H; p.W = Wd; p.C = C;
+  p.tiles_w = (Wd + GP_TW - 1) / GP_TW;
+  p.tiles_per_batch = p.tiles_w * ((H + GP_TH - 1) / GP_TH);
+  p.n_tiles = batch * p.tiles_per_batch;
+  p.kb32 = D / 32;
+  p.kblocks = D * esize / 128;
+  p.acc_stride = C <= 16 ? 16 : C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
+  TMap wmap;
+  if (!tc_make_map(&wmap, W, esize, D, C, ldw, C)) return SS2D_ERR_ALIGNMENT;
+  const size_t smem = gp_smem_bytes(D, C, esize);
+  auto kern = dtype == SS2D_F32 ? gate_proj_tc_kernel<true> : gate_proj_tc_kernel<false>;
+  static PerDeviceOnce once32, once16;
+  cudaError_t e = func_attr_once(dtype == SS2D_F32 ? once32 : once16, reinterpret_cast<const void*>(kern),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { *cerr = e; return SS2D_ERR_CUDA; }
+  int grid = sm_count_current_device();
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<grid, GP_THREADS, smem, stream>>>(p, wmap);
+  *cerr = cudaGetLastError();
+  return *cerr == cudaSuccess ? SS2D_OK : SS2D_ERR_CUDA;
+}
+
+}  // namespace ss2d

@@ -203,6 +203,61 @@ class _OutGate(torch.autograd.Function):
                 None, None, None, None, None, None)
 
 
+class _OutGateProj(torch.autograd.Function):
+    """out = out_proj(LayerNorm(merge_K(ys)) * SiLU(z)) in ONE tcgen05 kernel (ops.gate_proj_fwd; ss2d.py:486-518): the gated
+    tensor is built in shared memory in the tensor core's operand layout and only written out (g) when a backward will need it.
+    Backward: dG = dout W (library GEMM), then ops.out_gate_bwd as for _OutGate; dW from g."""
+
+    @staticmethod
+    def forward(ctx, ys, ln_w, ln_b, z, W, bias, eps, H, Wd, tplanes):
+        Bn, G, P, D, L = ys.shape
+        K = G * P
+        tmask = 0
+        for k in range(K):
+            if (tplanes >> (k % P)) & 1:
+                tmask |= 1 << k
+        zc, Wc = _tc_operands(z, W)
+        need_bwd = any(ctx.needs_input_grad)
+        out, stats, g = ops.gate_proj_fwd(ys.view(Bn, K, D, L), ln_w, ln_b, zc, True, eps, Wc, bias, (H, Wd), tmask, need_bwd)
+        ctx.meta = (H, Wd, tmask, tplanes, bias is not None, z.dtype, W.dtype)
+        ctx.save_for_backward(ys, ln_w, ln_b, zc, stats, g, Wc)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ys, ln_w, ln_b, zc, stats, g, Wc = ctx.saved_tensors
+        H, Wd, tmask, tplanes, has_bias, z_dtype, W_dtype = ctx.meta
+        Bn, G, P, D, L = ys.shape
+        C = Wc.shape[0]
+        d2 = dout.reshape(Bn * L, C).to(Wc.dtype)
+        dG = torch.matmul(d2, Wc).view(Bn, L, D)
+        dz = torch.empty_like(zc)
+        two = P == 2 and tplanes == 0b10 and G * P > 1
+        dy, dlw, dlb = ops.out_gate_bwd(ys.view(Bn, G * P, D, L), ln_w, ln_b, zc, True, dG, stats, dz, (H, Wd), tmask, two_planes=two)
+        if two:
+            dys = dy.unsqueeze(1).expand(Bn, G, P, D, L)
+        elif G * P == 1:
+            dys = dy.view(Bn, 1, 1, D, L)
+        else:
+            planes = [dy.view(Bn, D, H, Wd).transpose(2, 3).reshape(Bn, D, L) if (tplanes >> j) & 1 else dy for j in range(P)]
+            base = planes[0].unsqueeze(1) if P == 1 else torch.stack(planes, dim=1)
+            dys = base.unsqueeze(1).expand(Bn, G, P, D, L)
+        dW = _wgrad_rows(d2.contiguous(), g.reshape(Bn * L, D)).to(W_dtype) if ctx.needs_input_grad[4] else None
+        db = d2.float().sum(dim=0) if has_bias and ctx.needs_input_grad[5] else None
+        return dys, dlw, dlb, dz.to(z_dtype), dW, db, None, None, None, None
+
+
+def out_gate_proj_ok(ys, z, W) -> bool:
+    """Eligibility of the fused epilogue + out_proj kernel: a gate is present, the operand dtype is allowed on the tensor cores
+    (_tc_dtype_ok) and the shape fits (ops.gate_proj_supported; the backward goes through out_gate_bwd: D <= its limit)."""
+    if z is None or not _tc_dtype_ok(z):
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else z.dtype
+    Bn, G, P, D, L = ys.shape
+    return (ys.dtype == torch.float32 and ops.gate_proj_supported(D, W.shape[0], G * P, dt) and W.shape[1] == D
+            and D <= ops.out_gate_max_D(backward=True))
+
+
 class _GroupGate(torch.autograd.Function):
     """The epilogues of the four single-direction SS2Ds of a GroupMambaLayer in one launch (ops.group_gate_fwd/bwd):
     per group out_norm LayerNorm(D) + SiLU(z) gate (ss2d.py:498, 515-517), un-transposition of the column-major planes,

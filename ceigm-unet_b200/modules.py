@@ -121,10 +121,11 @@ class SS2D(nn.Module, mamba_init):
             return 2, (tflag[0], tflag[1]), kdirs
         return None
 
-    def forward_core(self, x: torch.Tensor, z, dirs, planes_u=None):
+    def forward_core(self, x: torch.Tensor, z, dirs, planes_u=None, out_proj=None):
         """x: (B, D, H, W) activated conv output; z: (B, H, W, D) raw gate view or None -> (B, H, W, D).
         planes_u: (B, 2 D, L) = [x | x transposed] already written by the convolution kernel (Fn.dwconv3_silu_planes); x is
-        then only consulted for its shape."""
+        then only consulted for its shape. out_proj = (weight, bias): the output projection (ss2d.py:518) is applied as well —
+        inside the epilogue kernel when eligible (Fn._OutGateProj) — and (B, H, W, d_model) is returned."""
         Bn, D, H, W = x.shape
         K, _, R = self.dt_projs_weight.shape
         N = self.A_logs.shape[1]
@@ -190,11 +191,17 @@ class SS2D(nn.Module, mamba_init):
                              self.out_norm.eps).to(x.dtype)
             if zz is not None:
                 y = y * F.silu(zz)
-            return y.view(Bn, H, W, D)
+            y = y.view(Bn, H, W, D)
+            return y if out_proj is None else Fn.linear_tc(y, out_proj[0], out_proj[1])
         tplanes = sum(1 << j for j, t in enumerate(tflags) if t)
+        if out_proj is not None and Fn.out_gate_proj_ok(ys, zz, out_proj[0]):
+            # merge + out_norm + gate + out_proj in one tensor-core kernel: the gated tensor stays in shared memory
+            out = Fn._OutGateProj.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, out_proj[0], out_proj[1],
+                                        self.out_norm.eps, H, W, tplanes)
+            return out.view(Bn, H, W, -1)
         y = Fn._OutGate.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, True,
-                              self.out_norm.eps, x.dtype, H, W, tplanes)
-        return y.view(Bn, H, W, D)
+                              self.out_norm.eps, x.dtype, H, W, tplanes).view(Bn, H, W, D)
+        return y if out_proj is None else Fn.linear_tc(y, out_proj[0], out_proj[1])
 
     def forward(self, x: torch.Tensor, CrossScan=None, CrossMerge=None, **kwargs):
         if CrossScan is None and CrossMerge is None:
@@ -225,8 +232,8 @@ class SS2D(nn.Module, mamba_init):
             if cv is not None:
                 xi = Fn.dwconv3(xi, cv)                           # :512 (reduction-shaped parameter gradient)
             xi = self.act(xi)                                     # :513
-        y = self.forward_core(xi, z, dirs, planes_u)              # :514-517 (scan, merge, out_norm, gate)
-        return self.dropout(Fn.linear_tc(y, self.out_proj.weight, self.out_proj.bias))    # :518 (tensor cores when eligible)
+        y = self.forward_core(xi, z, dirs, planes_u, (self.out_proj.weight, self.out_proj.bias))    # :514-518
+        return self.dropout(y)
 
 
 class GroupMambaLayer(nn.Module):

@@ -413,6 +413,32 @@ def dwconv3_act_planes_bwd(x: torch.Tensor, weight: torch.Tensor, bias, du: torc
     return dpre
 
 
+def gate_proj_supported(D: int, C: int, K: int, dtype: torch.dtype) -> bool:
+    return dtype in (torch.float32, torch.bfloat16) and bool(_lib.lib().ss2d_gate_proj_supported(int(D), int(C), int(K), _DT[dtype]))
+
+
+def gate_proj_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, W, bias, hw, tmask: int, want_g: bool):
+    """out (B, L, C) = out_proj(LayerNorm(merge_K(ys)) * SiLU(z)) in one kernel (ss2d.py:486-518).
+    ys (B, K, D, L) fp32; z (B, L, D) rows (uniformly strided view) of W's dtype; W (C, D).
+    -> (out, stats (B, L, 2) fp32, g (B, L, D) gated tensor or None)."""
+    Bn, K, D, L = ys.shape
+    C = W.shape[0]
+    dt = W.dtype
+    _require(ys.is_cuda and ys.dtype == torch.float32 and ys.is_contiguous(), "gate_proj: ys must be a contiguous fp32 CUDA tensor")
+    _require(W.stride(1) == 1 and (z is None or z.dtype == dt), "gate_proj: z must have W's dtype")
+    out = torch.empty((Bn, L, C), dtype=dt, device=ys.device)
+    stats = torch.empty((Bn, L, 2), dtype=torch.float32, device=ys.device)
+    g = torch.empty((Bn, L, D), dtype=dt, device=ys.device) if want_g else None
+    zrs = _row_stride(z, Bn, L) if z is not None else 0
+    b32 = None if bias is None else bias.float().contiguous()
+    with torch.cuda.device(ys.device):
+        rc = _lib.lib().ss2d_gate_proj_fwd(_ptr(ys), K, ctypes.c_uint32(tmask), _ptr(ln_w), _ptr(ln_b), ctypes.c_float(eps), _ptr(z), zrs,
+                                           1 if z_act else 0, _ptr(W), W.stride(0), _ptr(b32), _ptr(out), C, _ptr(g), D, _ptr(stats),
+                                           Bn, D, L, int(hw[0]), int(hw[1]), C, _DT[dt], _stream(ys.device))
+    _lib.check(rc, "ss2d_gate_proj_fwd")
+    return out, stats, g
+
+
 # ---- tensor-core projections (tcgen05): out = A W^T (+ bias) with split / permuted epilogues ---------------
 def linear_tc_supported(n_cols: int, K: int, dtype: torch.dtype) -> bool:
     return dtype in (torch.float32, torch.bfloat16) and bool(_lib.lib().ss2d_linear_tc_supported(int(n_cols), int(K), _DT[dtype]))

@@ -277,6 +277,23 @@ int ss2d_linear_tc(const void* A, int64_t lda, const void* W, int64_t ldw, const
                    int32_t dtype, int32_t n_parts, const ss2d_linear_part* parts, ss2d_stream_t stream);
 int32_t ss2d_linear_tc_supported(int32_t n_cols, int32_t K, int32_t dtype);
 
+/* ---- fused epilogue WITH the output projection (north-star property 5) -----------------------------------
+ * out = out_proj( LayerNorm_D( merge_K(ys) ) * SiLU(z) ) in one kernel: ss2d_out_gate_fwd followed by nn.Linear(D, C)
+ * (model/gm/ss2d.py:486-498, 506-508, 515-518) without the gated tensor's round trip through HBM. The producer warps build
+ * the 128-pixel x D operand tile in shared memory in the tensor core's layout, tcgen05.mma multiplies it with the resident
+ * weight (TF32 math for SS2D_F32, bf16 for SS2D_BF16; fp32 accumulation in tensor memory).
+ * ys: fp32 (batch, K, D, L); bit k of transposed_mask: plane k is in the pixel order of the transposed image.
+ * z: rows of z_row_stride elements (batch * L rows, D columns), dtype `dtype`, or NULL; z_act != 0: SiLU(z).
+ * W: (C, D) rows ldw elements apart, `dtype`; bias: (C) fp32 or NULL. out: (batch * L, C) rows out_row_stride apart, `dtype`.
+ * g_out: optional (batch * L, D) rows: the gated tensor (what out_proj's weight gradient needs); mean_rstd: optional
+ * (batch * L, 2) fp32 for ss2d_out_gate_bwd. D % 64 == 0, C % 16 == 0, C <= 256, operand tile + weight within shared memory
+ * (ss2d_gate_proj_supported); all row pointers / strides 16-byte aligned. */
+int ss2d_gate_proj_fwd(const float* ys, int32_t K, uint32_t transposed_mask, const float* ln_weight, const float* ln_bias, float eps,
+                       const void* z, int64_t z_row_stride, int32_t z_act, const void* W, int64_t ldw, const float* bias, void* out,
+                       int64_t out_row_stride, void* g_out, int64_t g_row_stride, float* mean_rstd, int32_t batch, int32_t D,
+                       int32_t L, int32_t H, int32_t Wd, int32_t C, int32_t dtype, ss2d_stream_t stream);
+int32_t ss2d_gate_proj_supported(int32_t D, int32_t C, int32_t K, int32_t dtype);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* ss2d_strerror(int status);
 const char* ss2d_last_cuda_error(void);   /* thread-local text of the last SS2D_ERR_CUDA */

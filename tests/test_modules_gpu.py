@@ -315,10 +315,13 @@ def test_grouped_layer_equals_the_four_separate_ss2ds(C, H):
 
 
 def _tc_calls(monkeypatch):
+    """Counts the launches of the two tcgen05 kernels: in_proj (ops.linear_tc) and the fused epilogue + out_proj
+    (ops.gate_proj_fwd)."""
     from ceigm_unet_b200 import ops
     calls = []
-    real = ops.linear_tc
-    monkeypatch.setattr(ops, "linear_tc", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    real_l, real_g = ops.linear_tc, ops.gate_proj_fwd
+    monkeypatch.setattr(ops, "linear_tc", lambda *a, **k: (calls.append("linear_tc"), real_l(*a, **k))[1])
+    monkeypatch.setattr(ops, "gate_proj_fwd", lambda *a, **k: (calls.append("gate_proj"), real_g(*a, **k))[1])
     return calls
 
 
@@ -344,7 +347,7 @@ def test_ss2d_tensor_core_projections_tf32_vs_fp32(monkeypatch):
             y.backward(dy)
             res[tf32] = (y.detach().clone(), xg.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
             if tf32:
-                assert len(calls) == 2, "in_proj and out_proj must both run on the tensor-core kernel"
+                assert calls == ["linear_tc", "gate_proj"], "in_proj and the epilogue + out_proj must run on the tensor-core kernels"
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
     (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
@@ -371,7 +374,7 @@ def test_ss2d_tensor_core_projections_bf16_autocast(monkeypatch):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y16 = m(x)
     y16.backward(dy.to(y16.dtype))
-    assert len(calls) == 2 and y16.dtype == torch.bfloat16
+    assert calls == ["linear_tc", "gate_proj"] and y16.dtype == torch.bfloat16
     assert rel_err(y16.float(), ref[0].cpu().numpy()) < 2e-2
     assert rel_err(x.grad, ref[1].cpu().numpy()) < 2e-2
     for n, p in m.named_parameters():
