@@ -12,10 +12,11 @@
 // (256 threads) PRODUCE the A tile; warps 12-15 are the epilogue. A tile is an 8 (h) x 16 (w) pixel patch, so that planes in
 // natural pixel order are read in 64-byte runs and planes in transposed order (column-major directions run as row-major scans of
 // the transposed image) in 32-byte runs. Per tile the producers
-//   A. sum the natural-order planes:   lanes along w, a thread owns (pixel, 4 channels) -> one conflict-free 16-byte store into
-//      the fp32 tile, which already has the tensor core's layout (pixel m = row, channels = K);
-//   B. add the transposed-order planes: lanes along h (a different pixel <-> lane map), read-modify-write of the tile;
-//      (the pixel numbering m(h, w) = 16 h + ((w + h) & 15) makes both maps hit 8 distinct swizzle slots per quarter warp)
+//   A. sum the K planes: warp 0 streams them as TMA boxes of 16 channels x 8 x 16 pixels (4-D tensor maps over the natural and
+//      over the transposed images: both orientations arrive as dense tiles, zero-filled outside the image) through a ring of
+//      8 KB slots; a producer thread owns (pixel, 2 channel quads) of a box and accumulates it into the fp32 tile, which
+//      already has the tensor core's layout (pixel m = row, channels = K; the pixel numbering m(h, w) = 16 h + ((w + h) & 15)
+//      makes the 16-byte stores of a quarter warp hit 8 distinct swizzle slots) — no thread ever waits on a global load;
 //   C. two-pass LayerNorm statistics per pixel (two threads per pixel, halves combined through shared memory);
 //   D. normalise, affine, multiply by SiLU(z), round (TF32: in place; bf16: into a second, bf16 tile), optionally store G.
 // Handshakes: `ready` (producers -> MMA), `afree` (tcgen05.commit -> producers: the tile may be overwritten), tmem_full /
@@ -32,6 +33,10 @@ constexpr int GP_PROD0 = 4, GP_PROD_WARPS = 8, GP_EPI0 = 12, GP_EPI_WARPS = 4;
 constexpr int GP_PT = 32 * GP_PROD_WARPS;     // producer threads
 constexpr int GP_TILE = 128, GP_TH = 8, GP_TW = 16;
 constexpr int GP_BLOCK = GP_TILE * 128;       // one K block of an operand tile: 128 rows x 128 bytes
+constexpr int GP_CB = 16;                     // channels per plane box
+constexpr int GP_SLOT = GP_CB * GP_TILE * 4;  // 8 KB
+constexpr int GP_MAX_SLOTS = 4;
+struct GpMaps { TMap w, nat, tr; };
 
 struct GpParams {
   const float* ys;            // (batch, K, D, L) fp32
@@ -55,8 +60,40 @@ struct GpParams {
   int kb32;                   // D / 32: K blocks of the fp32 tile
   int kblocks;                // K blocks of the MMA operands (D * esize / 128)
   int acc_stride;
+  int slots;                  // plane-box ring depth
 };
 
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void tma_load_4d32(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 4-D fp32 tensor map with an explicit box, no swizzle, zero fill: the K direction planes as (inner, outer, channel, batch x K)
+static bool gp_make_map4(TMap* out, const void* base, const long long* dims, const long long* strides_elems, const int* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    if (i > 0) {
+      gstr[i - 1] = (cuuint64_t)strides_elems[i] * 4;
+      if (gstr[i - 1] == 0 || (gstr[i - 1] & 15)) return false;
+    }
+  }
+  if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 __device__ __forceinline__ void gp_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GP_PT) : "memory"); }
 // byte offset of channels [4 cq, 4 cq + 4) of pixel row m in the fp32 tile (K-major, 128-byte swizzle)
 __device__ __forceinline__ uint32_t gp_y_off(int m, int cq) { return (uint32_t)(cq >> 3) * GP_BLOCK + m * 128 + (((cq & 7) ^ (m & 7)) << 4); }
@@ -64,7 +101,7 @@ __device__ __forceinline__ float gp_silu(float x) { return __fdividef(x, 1.f + e
 __device__ __forceinline__ float gp_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 template <bool TF32>
-__global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpParams p, const __grid_constant__ TMap wmap) {
+__global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpParams p, const __grid_constant__ GpMaps maps) {
   extern __shared__ __align__(16) unsigned char gp_smem_raw[];
   const uint32_t sm = (smem_u32(gp_smem_raw) + 1023u) & ~1023u;
   unsigned char* smp = gp_smem_raw + (sm - smem_u32(gp_smem_raw));
@@ -74,11 +111,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   const uint32_t a_y = sm + ((w_bytes + 1023u) & ~1023u);            // fp32 tile: kb32 blocks
   const uint32_t a_a16 = a_y + (uint32_t)p.kb32 * GP_BLOCK;           // bf16 operand tile (bf16 variant only)
   const uint32_t a_slabs = a_a16 + (TF32 ? 0u : (uint32_t)p.kblocks * GP_BLOCK);
-  const uint32_t a_misc = a_slabs + GP_EPI_WARPS * 4096u;
+  const uint32_t a_stage = a_slabs + GP_EPI_WARPS * 4096u;              // [slots][16 channels][128 pixels] fp32 plane boxes
+  const uint32_t a_misc = a_stage + (uint32_t)p.slots * GP_SLOT;
   // misc: barriers + tmem pointer (128 B) | pixel tables 2 x 128 ints | statistics partials 2 x 256 floats
   const uint32_t b_w = a_misc, b_ready = a_misc + 8, b_afree = a_misc + 16, b_tfull = a_misc + 24, b_tempty = a_misc + 40, a_tptr = a_misc + 56;
   const uint32_t b_wready = a_misc + 64;                                // TF32: W rounded in place by the producers
-  int* s_pix = reinterpret_cast<int*>(smp + (a_misc - sm) + 128);       // [2][128]
+  const uint32_t b_full = a_misc + 72, b_empty = b_full + 8 * GP_MAX_SLOTS;    // plane-box ring (ends at + 136)
+  int* s_pix = reinterpret_cast<int*>(smp + (a_misc - sm) + 192);       // [2][128]
   float* s_part = reinterpret_cast<float*>(s_pix + 2 * GP_TILE);       // [2][256]
   const uint32_t tmem_cols = 2u * p.acc_stride;
 
@@ -87,6 +126,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_ready), "r"(GP_PROD_WARPS));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_afree));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_wready), "r"(GP_PROD_WARPS));
+    for (int s2 = 0; s2 < p.slots; ++s2) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_full + 8 * s2));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_empty + 8 * s2), "r"(GP_PROD_WARPS));
+    }
     for (int a = 0; a < 2; ++a) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b_tfull + 8 * a));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b_tempty + 8 * a), "r"(GP_EPI_WARPS));
@@ -107,12 +150,27 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   const int64_t plane = (int64_t)D * L;
 
   if (warp == 0) {
-    // ================================ W: one TMA load per K block ================================
+    // ================================ TMA: W once, then the plane boxes of every tile ================================
     if (lane == 0) {
-      tma_prefetch_desc(&wmap);
+      tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.nat); tma_prefetch_desc(&maps.tr);
       const int kb_elems = TF32 ? 32 : 64;
       tc_mbar_expect(b_w, w_bytes);
-      for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(a_w + (uint32_t)kb * p.C * 128u, &wmap, kb * kb_elems, 0, b_w);
+      for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(a_w + (uint32_t)kb * p.C * 128u, &maps.w, kb * kb_elems, 0, b_w);
+      int rit = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
+        const int th = tib / p.tiles_w, tw = tib - th * p.tiles_w;
+        const int h0 = th * GP_TH, w0 = tw * GP_TW;
+        for (int cb = 0; cb < D / GP_CB; ++cb) {
+          for (int k = 0; k < p.K; ++k, ++rit) {
+            const int s2 = rit % p.slots;
+            tc_mbar_wait(b_empty + 8 * s2, ((rit / p.slots) & 1) ^ 1);
+            tc_mbar_expect(b_full + 8 * s2, GP_SLOT);
+            if ((p.tmask >> k) & 1u) tma_load_4d32(a_stage + (uint32_t)s2 * GP_SLOT, &maps.tr, h0, w0, cb * GP_CB, b * p.K + k, b_full + 8 * s2);
+            else tma_load_4d32(a_stage + (uint32_t)s2 * GP_SLOT, &maps.nat, w0, h0, cb * GP_CB, b * p.K + k, b_full + 8 * s2);
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -141,7 +199,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   } else if (warp >= GP_PROD0 && warp < GP_EPI0) {
     // ================================ producers ================================
     const int pt = threadIdx.x - 32 * GP_PROD0, pw = pt >> 5;
-    const bool any_t = p.tmask != 0u;
+    int rit = 0;
     if (TF32) {      // the tensor core truncates fp32 containers: round the resident weight to nearest TF32 once
       tc_mbar_wait(b_w, 0);
       for (uint32_t o = (uint32_t)pt * 16u; o < w_bytes; o += GP_PT * 16u) {
@@ -165,77 +223,31 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
         const int h = h0 + hh, w = w0 + ww;
         pix[pt] = (h < H && w < W) ? h * W + w : -1;
       }
-      const float* ysb = p.ys + (int64_t)b * p.ys_bs;
-      // ---- A / B: one pass per plane, UNR channel quads (4 UNR independent loads) in flight per thread. Natural-order planes:
-      //      warp = patch row hh, lanes 0-15 / 16-31 = two channel-quad streams along w. Transposed-order planes: lanes = 8 h x 4 w
-      //      (32-byte runs along h), warp = w quad + channel-quad stream. The first pass stores, the others read-modify-write
-      //      (same thread, same elements within a kind; a named barrier separates the two kinds).
-      constexpr int UNR = 12;
-      bool first = true;
+      // ---- A: accumulate the K planes from the TMA ring. natural box [c][hh][ww], transposed box [c][ww][hh] ----
       {
-        const int hh = pw, ww = lane & 15;
-        const int h = h0 + hh, w = w0 + ww;
-        const bool ok = h < H && w < W;
-        const int m = hh * 16 + ((ww + hh) & 15);
-        const int nq = D / 8;                               // quads of this thread's stream: cq = (lane >> 4) + 2 i
-        for (int k = 0; k < p.K; ++k) {
-          if ((p.tmask >> k) & 1u) continue;
-          const float* src = ysb + k * plane + (int64_t)h * W + w;
-          for (int i0 = 0; i0 < nq; i0 += UNR) {
-            float4 v[UNR];
+        const int m_hh = (pt & (GP_TILE - 1)) >> 4, m_ww = pt & 15;
+        const int mrow = m_hh * 16 + ((m_ww + m_hh) & 15);
+        const int qb = (pt >> 7) * 2;                       // this thread's two channel quads of a 16-channel box
+        const uint32_t off_n = (uint32_t)(m_hh * 16 + m_ww) * 4u, off_t = (uint32_t)(m_ww * 8 + m_hh) * 4u;
+        for (int cb = 0; cb < D / GP_CB; ++cb) {
+          for (int k = 0; k < p.K; ++k, ++rit) {
+            const int s2 = rit % p.slots;
+            tc_mbar_wait(b_full + 8 * s2, (rit / p.slots) & 1);
+            const uint32_t st = a_stage + (uint32_t)s2 * GP_SLOT + (((p.tmask >> k) & 1u) ? off_t : off_n);
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-              const int cq = (lane >> 4) + 2 * (i0 + u);
-              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok && i0 + u < nq) {
-                const float* q = src + (int64_t)(4 * cq) * L;
-                v[u] = make_float4(__ldg(q), __ldg(q + L), __ldg(q + 2 * (int64_t)L), __ldg(q + 3 * (int64_t)L));
-              }
+            for (int j = 0; j < 2; ++j) {
+              const int q = qb + j;
+              float4 v = make_float4(lds32(st + (4 * q) * 512), lds32(st + (4 * q + 1) * 512), lds32(st + (4 * q + 2) * 512), lds32(st + (4 * q + 3) * 512));
+              const uint32_t o = a_y + gp_y_off(mrow, cb * 4 + q);
+              if (k > 0) { const float4 t4 = lds128(o); v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w; }
+              sts128(o, v);
             }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-              if (i0 + u >= nq) break;
-              const uint32_t o = a_y + gp_y_off(m, (lane >> 4) + 2 * (i0 + u));
-              if (!first) { const float4 t4 = lds128(o); v[u].x += t4.x; v[u].y += t4.y; v[u].z += t4.z; v[u].w += t4.w; }
-              sts128(o, v[u]);
-            }
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(b_empty + 8 * s2);
           }
-          first = false;
         }
       }
       gp_bar_sync();
-      if (any_t) {
-        const int hh = lane & 7, ww = 4 * (pw & 3) + (lane >> 3);
-        const int h = h0 + hh, w = w0 + ww;
-        const bool ok = h < H && w < W;
-        const int m = hh * 16 + ((ww + hh) & 15);
-        const int nq = D / 8;                               // cq = (pw >> 2) + 2 i
-        for (int k = 0; k < p.K; ++k) {
-          if (!((p.tmask >> k) & 1u)) continue;
-          const float* src = ysb + k * plane + (int64_t)w * H + h;
-          for (int i0 = 0; i0 < nq; i0 += UNR) {
-            float4 v[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-              const int cq = (pw >> 2) + 2 * (i0 + u);
-              v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok && i0 + u < nq) {
-                const float* q = src + (int64_t)(4 * cq) * L;
-                v[u] = make_float4(__ldg(q), __ldg(q + L), __ldg(q + 2 * (int64_t)L), __ldg(q + 3 * (int64_t)L));
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-              if (i0 + u >= nq) break;
-              const uint32_t o = a_y + gp_y_off(m, (pw >> 2) + 2 * (i0 + u));
-              if (!first) { const float4 t4 = lds128(o); v[u].x += t4.x; v[u].y += t4.y; v[u].z += t4.z; v[u].w += t4.w; }
-              sts128(o, v[u]);
-            }
-          }
-          first = false;
-        }
-        gp_bar_sync();
-      }
       // ---- C: LayerNorm statistics, two threads per pixel (channel halves), two passes ----
       const int m = pt & (GP_TILE - 1), hf = pt >> 7;
       const int cq0 = hf * (D / 8), cq1 = cq0 + D / 8;
@@ -381,12 +393,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   }
 }
 
+static int gp_slots(int esize) { return esize == 4 ? 4 : 2; }
 static size_t gp_smem_bytes(int D, int C, int esize) {
   const int kblocks = D * esize / 128;
   const size_t w = ((size_t)kblocks * C * 128 + 1023) & ~(size_t)1023;
   const size_t y = (size_t)(D / 32) * GP_BLOCK;
   const size_t a16 = esize == 2 ? (size_t)kblocks * GP_BLOCK : 0;
-  return w + y + a16 + GP_EPI_WARPS * 4096 + 128 + 2 * GP_TILE * 4 + 2 * GP_PT * 4 + 1024 /* alignment slack */;
+  return w + y + a16 + GP_EPI_WARPS * 4096 + (size_t)gp_slots(esize) * GP_SLOT + 192 + 2 * GP_TILE * 4 + 2 * GP_PT * 4 + 1024 /* alignment slack */;
 }
 
 bool gate_proj_tc_supported(int D, int C, int K, int dtype) {
@@ -420,8 +433,17 @@ int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw
   p.kb32 = D / 32;
   p.kblocks = D * esize / 128;
   p.acc_stride = C <= 16 ? 16 : C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
-  TMap wmap;
-  if (!tc_make_map(&wmap, W, esize, D, C, ldw, C)) return SS2D_ERR_ALIGNMENT;
+  p.slots = gp_slots(esize);
+  GpMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (!tc_make_map(&maps.w, W, esize, D, C, ldw, C)) return SS2D_ERR_ALIGNMENT;
+  {   // planes as images: natural (W inner) and transposed (H inner); box = 16 x 8 (resp. 8 x 16) pixels x 16 channels
+    const long long bk = (long long)batch * K;
+    const long long dn[4] = {Wd, H, D, bk}, sn[4] = {1, Wd, L, (long long)D * L};
+    const long long dt[4] = {H, Wd, D, bk}, st[4] = {1, H, L, (long long)D * L};
+    const int bn[4] = {GP_TW, GP_TH, GP_CB, 1}, bt[4] = {GP_TH, GP_TW, GP_CB, 1};
+    if (!gp_make_map4(&maps.nat, ys, dn, sn, bn) || !gp_make_map4(&maps.tr, ys, dt, st, bt)) return SS2D_ERR_UNSUPPORTED;
+  }
   const size_t smem = gp_smem_bytes(D, C, esize);
   auto kern = dtype == SS2D_F32 ? gate_proj_tc_kernel<true> : gate_proj_tc_kernel<false>;
   static PerDeviceOnce once32, once16;
@@ -430,7 +452,7 @@ int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw
   if (e != cudaSuccess) { *cerr = e; return SS2D_ERR_CUDA; }
   int grid = sm_count_current_device();
   if (grid > p.n_tiles) grid = p.n_tiles;
-  kern<<<grid, GP_THREADS, smem, stream>>>(p, wmap);
+  kern<<<grid, GP_THREADS, smem, stream>>>(p, maps);
   *cerr = cudaGetLastError();
   return *cerr == cudaSuccess ? SS2D_OK : SS2D_ERR_CUDA;
 }

@@ -247,7 +247,7 @@ class _OutGateProj(torch.autograd.Function):
         return dys, dlw, dlb, dz.to(z_dtype), dW, db, None, None, None, None
 
 
-def out_gate_proj_ok(ys, z, W) -> bool:
+def out_gate_proj_ok(ys, z, W, H, Wd) -> bool:
     """Eligibility of the fused epilogue + out_proj kernel: a gate is present, the operand dtype is allowed on the tensor cores
     (_tc_dtype_ok) and the shape fits (ops.gate_proj_supported; the backward goes through out_gate_bwd: D <= its limit)."""
     if z is None or not _tc_dtype_ok(z):
@@ -255,6 +255,7 @@ def out_gate_proj_ok(ys, z, W) -> bool:
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else z.dtype
     Bn, G, P, D, L = ys.shape
     return (ys.dtype == torch.float32 and ops.gate_proj_supported(D, W.shape[0], G * P, dt) and W.shape[1] == D
+            and H % 4 == 0 and Wd % 4 == 0              # the planes are read as TMA boxes: 16-byte aligned image rows
             and D <= ops.out_gate_max_D(backward=True))
 
 

@@ -194,7 +194,7 @@ class SS2D(nn.Module, mamba_init):
             y = y.view(Bn, H, W, D)
             return y if out_proj is None else Fn.linear_tc(y, out_proj[0], out_proj[1])
         tplanes = sum(1 << j for j, t in enumerate(tflags) if t)
-        if out_proj is not None and Fn.out_gate_proj_ok(ys, zz, out_proj[0]):
+        if out_proj is not None and Fn.out_gate_proj_ok(ys, zz, out_proj[0], H, W):
             # merge + out_norm + gate + out_proj in one tensor-core kernel: the gated tensor stays in shared memory
             out = Fn._OutGateProj.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, out_proj[0], out_proj[1],
                                         self.out_norm.eps, H, W, tplanes)
