@@ -35,7 +35,7 @@ constexpr int GP_TILE = 128, GP_TH = 8, GP_TW = 16;
 constexpr int GP_BLOCK = GP_TILE * 128;       // one K block of an operand tile: 128 rows x 128 bytes
 constexpr int GP_CB = 16;                     // channels per plane box
 constexpr int GP_SLOT = GP_CB * GP_TILE * 4;  // 8 KB
-constexpr int GP_MAX_SLOTS = 4;
+constexpr int GP_MAX_SLOTS = 16;
 struct GpMaps { TMap w, nat, tr; };
 
 struct GpParams {
@@ -108,16 +108,16 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_bytes = (uint32_t)p.kblocks * p.C * 128u;
   const uint32_t a_w = sm;
-  const uint32_t a_y = sm + ((w_bytes + 1023u) & ~1023u);            // fp32 tile: kb32 blocks
+  const uint32_t a_stage = sm;                                        // plane-box ring: ALIASES the weight (see the TMA warp)
+  const uint32_t a_y = sm + (uint32_t)p.slots * GP_SLOT;               // fp32 tile: kb32 blocks
   const uint32_t a_a16 = a_y + (uint32_t)p.kb32 * GP_BLOCK;           // bf16 operand tile (bf16 variant only)
   const uint32_t a_slabs = a_a16 + (TF32 ? 0u : (uint32_t)p.kblocks * GP_BLOCK);
-  const uint32_t a_stage = a_slabs + GP_EPI_WARPS * 4096u;              // [slots][16 channels][128 pixels] fp32 plane boxes
-  const uint32_t a_misc = a_stage + (uint32_t)p.slots * GP_SLOT;
+  const uint32_t a_misc = a_slabs + GP_EPI_WARPS * 4096u;
   // misc: barriers + tmem pointer (128 B) | pixel tables 2 x 128 ints | statistics partials 2 x 256 floats
   const uint32_t b_w = a_misc, b_ready = a_misc + 8, b_afree = a_misc + 16, b_tfull = a_misc + 24, b_tempty = a_misc + 40, a_tptr = a_misc + 56;
   const uint32_t b_wready = a_misc + 64;                                // TF32: W rounded in place by the producers
-  const uint32_t b_full = a_misc + 72, b_empty = b_full + 8 * GP_MAX_SLOTS;    // plane-box ring (ends at + 136)
-  int* s_pix = reinterpret_cast<int*>(smp + (a_misc - sm) + 192);       // [2][128]
+  const uint32_t b_full = a_misc + 72, b_empty = b_full + 8 * GP_MAX_SLOTS;    // plane-box ring (ends at + 328)
+  int* s_pix = reinterpret_cast<int*>(smp + (a_misc - sm) + 384);       // [2][128]
   float* s_part = reinterpret_cast<float*>(s_pix + 2 * GP_TILE);       // [2][256]
   const uint32_t tmem_cols = 2u * p.acc_stride;
 
@@ -150,17 +150,20 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   const int64_t plane = (int64_t)D * L;
 
   if (warp == 0) {
-    // ================================ TMA: W once, then the plane boxes of every tile ================================
+    // ================================ TMA: per tile the plane boxes, then the weight ================================
+    // The ring and the weight share one region of shared memory: the planes of a tile stream through it while the producers
+    // accumulate them (13 slots = 104 KB in flight next to a 72 KB weight), and once the last box has been consumed the weight
+    // is loaded over it (72 KB from L2, hidden behind the statistics / gate passes) for this tile's MMAs; the next tile's boxes
+    // wait for those MMAs (`afree`).
     if (lane == 0) {
       tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.nat); tma_prefetch_desc(&maps.tr);
       const int kb_elems = TF32 ? 32 : 64;
-      tc_mbar_expect(b_w, w_bytes);
-      for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(a_w + (uint32_t)kb * p.C * 128u, &maps.w, kb * kb_elems, 0, b_w);
-      int rit = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      int rit = 0, it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
         const int th = tib / p.tiles_w, tw = tib - th * p.tiles_w;
         const int h0 = th * GP_TH, w0 = tw * GP_TW;
+        tc_mbar_wait(b_afree, (it & 1) ^ 1);                      // MMAs of tile it - 1 have read the weight
         for (int cb = 0; cb < D / GP_CB; ++cb) {
           for (int k = 0; k < p.K; ++k, ++rit) {
             const int s2 = rit % p.slots;
@@ -170,6 +173,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
             else tma_load_4d32(a_stage + (uint32_t)s2 * GP_SLOT, &maps.nat, w0, h0, cb * GP_CB, b * p.K + k, b_full + 8 * s2);
           }
         }
+        for (int u = rit > p.slots ? rit - p.slots : 0; u < rit; ++u)       // every box of this tile has been consumed
+          tc_mbar_wait(b_empty + 8 * (u % p.slots), (u / p.slots) & 1);
+        tc_mbar_expect(b_w, w_bytes);
+        for (int kb = 0; kb < p.kblocks; ++kb) tma_load_2d(a_w + (uint32_t)kb * p.C * 128u, &maps.w, kb * kb_elems, 0, b_w);
       }
     }
   } else if (warp == 1) {
@@ -178,12 +185,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
       const uint32_t fmt = TF32 ? 2u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(GP_TILE >> 4) << 24);
       const uint32_t a_op = TF32 ? a_y : a_a16;
-      tc_mbar_wait(TF32 ? b_wready : b_w, 0);
       int it = 0;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const int acc = it & 1;
         tc_mbar_wait(b_tempty + 8 * acc, ((it >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator stage
         tc_mbar_wait(b_ready, it & 1);                               // the producers have finished the operand tile
+        tc_mbar_wait(TF32 ? b_wready : b_w, it & 1);                 // this tile's copy of the weight is in place (and rounded)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -200,16 +207,6 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
     // ================================ producers ================================
     const int pt = threadIdx.x - 32 * GP_PROD0, pw = pt >> 5;
     int rit = 0;
-    if (TF32) {      // the tensor core truncates fp32 containers: round the resident weight to nearest TF32 once
-      tc_mbar_wait(b_w, 0);
-      for (uint32_t o = (uint32_t)pt * 16u; o < w_bytes; o += GP_PT * 16u) {
-        const float4 v = lds128(a_w + o);
-        sts128(a_w + o, make_float4(gp_rna(v.x), gp_rna(v.y), gp_rna(v.z), gp_rna(v.w)));
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(b_wready);
-    }
     int it = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
       const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
@@ -324,9 +321,16 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
           }
         }
       }
+      if (TF32) {      // the tensor core truncates fp32 containers: round this tile's copy of the weight to nearest TF32
+        tc_mbar_wait(b_w, it & 1);
+        for (uint32_t o = (uint32_t)pt * 16u; o < w_bytes; o += GP_PT * 16u) {
+          const float4 v = lds128(a_w + o);
+          sts128(a_w + o, make_float4(gp_rna(v.x), gp_rna(v.y), gp_rna(v.z), gp_rna(v.w)));
+        }
+      }
       fence_proxy_async();           // generic-proxy writes before the tensor core's async-proxy reads
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(b_ready);
+      if (lane == 0) { tc_mbar_arrive(b_ready); if (TF32) tc_mbar_arrive(b_wready); }
     }
   } else if (warp >= GP_EPI0) {
     // ================================ epilogue ================================
@@ -393,13 +397,20 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   }
 }
 
-static int gp_slots(int esize) { return esize == 4 ? 4 : 2; }
+// ring slots: the weight's region plus 32 KB (fp32) / 16 KB (bf16) of extra staging
+static int gp_slots(int D, int C, int esize) {
+  const size_t w = ((size_t)(D * esize / 128) * C * 128 + 1023) & ~(size_t)1023;
+  int s = (int)((w + (esize == 4 ? 32768 : 16384)) / GP_SLOT);
+  return s > GP_MAX_SLOTS ? GP_MAX_SLOTS : s;
+}
 static size_t gp_smem_bytes(int D, int C, int esize) {
   const int kblocks = D * esize / 128;
   const size_t w = ((size_t)kblocks * C * 128 + 1023) & ~(size_t)1023;
   const size_t y = (size_t)(D / 32) * GP_BLOCK;
   const size_t a16 = esize == 2 ? (size_t)kblocks * GP_BLOCK : 0;
-  return w + y + a16 + GP_EPI_WARPS * 4096 + (size_t)gp_slots(esize) * GP_SLOT + 192 + 2 * GP_TILE * 4 + 2 * GP_PT * 4 + 1024 /* alignment slack */;
+  size_t ring = (size_t)gp_slots(D, C, esize) * GP_SLOT;
+  if (ring < w) ring = w;
+  return ring + y + a16 + GP_EPI_WARPS * 4096 + 384 + 2 * GP_TILE * 4 + 2 * GP_PT * 4 + 1024 /* alignment slack */;
 }
 
 bool gate_proj_tc_supported(int D, int C, int K, int dtype) {
@@ -433,7 +444,7 @@ int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw
   p.kb32 = D / 32;
   p.kblocks = D * esize / 128;
   p.acc_stride = C <= 16 ? 16 : C <= 32 ? 32 : C <= 64 ? 64 : C <= 128 ? 128 : 256;
-  p.slots = gp_slots(esize);
+  p.slots = gp_slots(D, C, esize);
   GpMaps maps;
   memset(&maps, 0, sizeof(maps));
   if (!tc_make_map(&maps.w, W, esize, D, C, ldw, C)) return SS2D_ERR_ALIGNMENT;

@@ -106,6 +106,11 @@ class SS2D(nn.Module, mamba_init):
         self.A_logs = self.A_log_init(d_state, d_inner, copies=k_group, merge=True)                # (K*D, N)
         self.Ds = self.D_init(d_inner, copies=k_group, merge=True)                                 # (K*D)
 
+    # True: merge + out_norm + gate + out_proj as ONE tcgen05 kernel (csrc/gate_proj_tc.cu, Fn._OutGateProj) when eligible.
+    # Off by default: at the north-star shape that kernel takes 178 us against 146 + 19 us for the epilogue kernel followed by
+    # the tensor-core out_proj — its 96 KB operand tile allows one CTA per SM and its phases run back to back.
+    fuse_out_proj = False
+
     # -- forward_corev2 (ss2d.py:349-500) as ONE fused pipeline ------------------------------------
     @staticmethod
     def _plan(dirs):
@@ -194,7 +199,7 @@ class SS2D(nn.Module, mamba_init):
             y = y.view(Bn, H, W, D)
             return y if out_proj is None else Fn.linear_tc(y, out_proj[0], out_proj[1])
         tplanes = sum(1 << j for j, t in enumerate(tflags) if t)
-        if out_proj is not None and Fn.out_gate_proj_ok(ys, zz, out_proj[0], H, W):
+        if out_proj is not None and self.fuse_out_proj and Fn.out_gate_proj_ok(ys, zz, out_proj[0], H, W):
             # merge + out_norm + gate + out_proj in one tensor-core kernel: the gated tensor stays in shared memory
             out = Fn._OutGateProj.apply(ys, self.out_norm.weight.float(), self.out_norm.bias.float(), zz, out_proj[0], out_proj[1],
                                         self.out_norm.eps, H, W, tplanes)

@@ -347,7 +347,7 @@ def test_ss2d_tensor_core_projections_tf32_vs_fp32(monkeypatch):
             y.backward(dy)
             res[tf32] = (y.detach().clone(), xg.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
             if tf32:
-                assert calls == ["linear_tc", "gate_proj"], "in_proj and the epilogue + out_proj must run on the tensor-core kernels"
+                assert calls == ["linear_tc", "linear_tc"], "in_proj and out_proj must both run on the tensor-core kernel"
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
     (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
@@ -374,7 +374,7 @@ def test_ss2d_tensor_core_projections_bf16_autocast(monkeypatch):
     with torch.autocast("cuda", dtype=torch.bfloat16):
         y16 = m(x)
     y16.backward(dy.to(y16.dtype))
-    assert calls == ["linear_tc", "gate_proj"] and y16.dtype == torch.bfloat16
+    assert calls == ["linear_tc", "linear_tc"] and y16.dtype == torch.bfloat16
     assert rel_err(y16.float(), ref[0].cpu().numpy()) < 2e-2
     assert rel_err(x.grad, ref[1].cpu().numpy()) < 2e-2
     for n, p in m.named_parameters():
@@ -412,3 +412,38 @@ def test_ss2d_tensor_core_path_cuda_graphs_match_eager():
     assert rel_err(gx1, gx2.cpu().numpy()) < 1e-4
     for a, b in zip(gp1, gp2):
         assert rel_err(a, b.cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_ss2d_fused_epilogue_and_out_proj_kernel(monkeypatch, mode):
+    """SS2D.fuse_out_proj = True: merge + out_norm + gate + out_proj (ss2d.py:486-518) in ONE tcgen05 kernel
+    (csrc/gate_proj_tc.cu) — output and every gradient against the same module on the two-kernel path."""
+    import ceigm_unet_b200 as P
+    torch.manual_seed(5)
+    m = P.SS2D(d_model=96, d_state=16, ssm_ratio=2.0, k_group=4).cuda()
+    x = torch.randn(2, 28, 28, 96, device="cuda")
+    dy = torch.randn(2, 28, 28, 96, device="cuda")
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    res = {}
+    try:
+        for fused in (False, True):
+            m.fuse_out_proj = fused
+            calls = _tc_calls(monkeypatch) if fused else []
+            m.zero_grad(set_to_none=True)
+            xg = x.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+                y = m(xg)
+            y.backward(dy.to(y.dtype))
+            res[fused] = (y.detach().float().clone(), xg.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters()})
+            if fused:
+                assert calls == ["linear_tc", "gate_proj"]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+        m.fuse_out_proj = False
+    tol = 1e-3 if mode == "tf32" else 2e-2
+    (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
+    assert rel_err(y1, y0.cpu().numpy()) < tol
+    assert rel_err(dx1, dx0.cpu().numpy()) < tol
+    for n in g0:
+        assert rel_err(g1[n].float(), g0[n].float().cpu().numpy()) < 2 * tol, n
