@@ -17,8 +17,9 @@
 //      8 KB slots; a producer thread owns (pixel, 2 channel quads) of a box and accumulates it into the fp32 tile, which
 //      already has the tensor core's layout (pixel m = row, channels = K; the pixel numbering m(h, w) = 16 h + ((w + h) & 15)
 //      makes the 16-byte stores of a quarter warp hit 8 distinct swizzle slots) — no thread ever waits on a global load;
-//   C. two-pass LayerNorm statistics per pixel (two threads per pixel, halves combined through shared memory);
-//   D. normalise, affine, multiply by SiLU(z), round (TF32: in place; bf16: into a second, bf16 tile), optionally store G.
+//   C + D. a warp then owns 16 pixel rows with its lanes along the channels: two-pass LayerNorm statistics by butterflies,
+//      normalise, affine, multiply by SiLU(z) (z and the optional G rows are read / written as whole contiguous rows), round
+//      (TF32: in place; bf16: into a second, bf16 tile).
 // Handshakes: `ready` (producers -> MMA), `afree` (tcgen05.commit -> producers: the tile may be overwritten), tmem_full /
 // tmem_empty per accumulator stage (MMA <-> epilogue; the producers also wait for tmem_empty before they reuse the pixel table
 // of that stage). The only CTA-wide barrier is in the prologue; the producers synchronise among themselves with a named barrier.
@@ -100,7 +101,7 @@ __device__ __forceinline__ uint32_t gp_y_off(int m, int cq) { return (uint32_t)(
 __device__ __forceinline__ float gp_silu(float x) { return __fdividef(x, 1.f + ex2f(-x * kLog2e)); }
 __device__ __forceinline__ float gp_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
-template <bool TF32>
+template <bool TF32, bool HAS_Z, bool HAS_G>
 __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpParams p, const __grid_constant__ GpMaps maps) {
   extern __shared__ __align__(16) unsigned char gp_smem_raw[];
   const uint32_t sm = (smem_u32(gp_smem_raw) + 1023u) & ~1023u;
@@ -118,7 +119,6 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   const uint32_t b_wready = a_misc + 64;                                // TF32: W rounded in place by the producers
   const uint32_t b_full = a_misc + 72, b_empty = b_full + 8 * GP_MAX_SLOTS;    // plane-box ring (ends at + 328)
   int* s_pix = reinterpret_cast<int*>(smp + (a_misc - sm) + 384);       // [2][128]
-  float* s_part = reinterpret_cast<float*>(s_pix + 2 * GP_TILE);       // [2][256]
   const uint32_t tmem_cols = 2u * p.acc_stride;
 
   if (threadIdx.x == 0) {
@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(a_tptr));
 
   const int D = p.D, L = p.L, H = p.H, W = p.W;
-  const int64_t plane = (int64_t)D * L;
 
   if (warp == 0) {
     // ================================ TMA: per tile the plane boxes, then the weight ================================
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
     if (lane == 0) {
       tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.nat); tma_prefetch_desc(&maps.tr);
       const int kb_elems = TF32 ? 32 : 64;
-      int rit = 0, it = 0;
+      int rit = 0, it = 0, s2 = 0, ph = 0;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
         const int th = tib / p.tiles_w, tw = tib - th * p.tiles_w;
@@ -166,11 +165,11 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
         tc_mbar_wait(b_afree, (it & 1) ^ 1);                      // MMAs of tile it - 1 have read the weight
         for (int cb = 0; cb < D / GP_CB; ++cb) {
           for (int k = 0; k < p.K; ++k, ++rit) {
-            const int s2 = rit % p.slots;
-            tc_mbar_wait(b_empty + 8 * s2, ((rit / p.slots) & 1) ^ 1);
+            tc_mbar_wait(b_empty + 8 * s2, ph ^ 1);
             tc_mbar_expect(b_full + 8 * s2, GP_SLOT);
             if ((p.tmask >> k) & 1u) tma_load_4d32(a_stage + (uint32_t)s2 * GP_SLOT, &maps.tr, h0, w0, cb * GP_CB, b * p.K + k, b_full + 8 * s2);
             else tma_load_4d32(a_stage + (uint32_t)s2 * GP_SLOT, &maps.nat, w0, h0, cb * GP_CB, b * p.K + k, b_full + 8 * s2);
+            if (++s2 == p.slots) { s2 = 0; ph ^= 1; }
           }
         }
         for (int u = rit > p.slots ? rit - p.slots : 0; u < rit; ++u)       // every box of this tile has been consumed
@@ -206,7 +205,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   } else if (warp >= GP_PROD0 && warp < GP_EPI0) {
     // ================================ producers ================================
     const int pt = threadIdx.x - 32 * GP_PROD0, pw = pt >> 5;
-    int rit = 0;
+    int s2 = 0, ph = 0;          // ring slot and phase, carried across tiles (no division in the box loop)
     int it = 0;
     for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
       const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
@@ -227,9 +226,8 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
         const int qb = (pt >> 7) * 2;                       // this thread's two channel quads of a 16-channel box
         const uint32_t off_n = (uint32_t)(m_hh * 16 + m_ww) * 4u, off_t = (uint32_t)(m_ww * 8 + m_hh) * 4u;
         for (int cb = 0; cb < D / GP_CB; ++cb) {
-          for (int k = 0; k < p.K; ++k, ++rit) {
-            const int s2 = rit % p.slots;
-            tc_mbar_wait(b_full + 8 * s2, (rit / p.slots) & 1);
+          for (int k = 0; k < p.K; ++k) {
+            tc_mbar_wait(b_full + 8 * s2, ph);
             const uint32_t st = a_stage + (uint32_t)s2 * GP_SLOT + (((p.tmask >> k) & 1u) ? off_t : off_n);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -241,83 +239,97 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
             }
             __syncwarp();
             if (lane == 0) tc_mbar_arrive(b_empty + 8 * s2);
+            if (++s2 == p.slots) { s2 = 0; ph ^= 1; }
           }
         }
       }
       gp_bar_sync();
-      // ---- C: LayerNorm statistics, two threads per pixel (channel halves), two passes ----
-      const int m = pt & (GP_TILE - 1), hf = pt >> 7;
-      const int cq0 = hf * (D / 8), cq1 = cq0 + D / 8;
-      const int l = pix[m];
-      {
-        float s = 0.f;
-        for (int cq = cq0; cq < cq1; ++cq) { const float4 v = lds128(a_y + gp_y_off(m, cq)); s += (v.x + v.y) + (v.z + v.w); }
-        s_part[pt] = s;
-      }
-      gp_bar_sync();
-      const float mean = (s_part[m] + s_part[m + GP_TILE]) / D;
-      {
-        float q = 0.f;
-        for (int cq = cq0; cq < cq1; ++cq) {
-          const float4 v = lds128(a_y + gp_y_off(m, cq));
-          const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
-          q = fmaf(a0, a0, q); q = fmaf(a1, a1, q); q = fmaf(a2, a2, q); q = fmaf(a3, a3, q);
-        }
-        s_part[GP_PT + pt] = q;
-      }
-      gp_bar_sync();
-      const float rstd = rsqrtf((s_part[GP_PT + m] + s_part[GP_PT + m + GP_TILE]) / D + p.eps);
-      const int64_t row = (int64_t)b * L + (l >= 0 ? l : 0);
-      if (hf == 0 && l >= 0 && p.mean_rstd) { p.mean_rstd[row * 2] = mean; p.mean_rstd[row * 2 + 1] = rstd; }
-      // ---- D: normalise, affine, gate, round into the operand tile (ZU gate quads requested before they are used) ----
-      constexpr int ZU = 8;
-      for (int c0 = cq0; c0 < cq1; c0 += ZU) {
-        float zq[ZU][4];
-        if (p.z && l >= 0) {
+      // ---- C + D: a warp owns 16 pixel rows; its lanes run along the channels (quads lane and lane + 32), so the gate z and the
+      //      optional G rows are read / written as whole contiguous rows, the LayerNorm statistics are two butterfly sums, and
+      //      nothing crosses warps. RU rows in flight per step: their z quads are requested before the statistics are computed.
+      constexpr int RU = 4;
+      const int nq = D / 4;
+      const bool has2 = lane + 32 < nq;                   // D <= 256: at most two quads per lane
+      for (int r0 = 0; r0 < 16; r0 += RU) {
+        float4 y0[RU], y1[RU], z0[RU], z1[RU];
+        int lrow[RU];
 #pragma unroll
-          for (int u = 0; u < ZU; ++u) {
-            const int cq = c0 + u;
-            if (cq >= cq1) break;
+        for (int u = 0; u < RU; ++u) {
+          const int mrow = pw * 16 + r0 + u;
+          lrow[u] = pix[mrow];
+          y0[u] = lane < nq ? lds128(a_y + gp_y_off(mrow, lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          y1[u] = has2 ? lds128(a_y + gp_y_off(mrow, lane + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          z0[u] = z1[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (HAS_Z && lrow[u] >= 0) {
+            const int64_t row = (int64_t)b * L + lrow[u];
             if (TF32) {
-              const float4 zv = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.z) + row * p.z_rs) + cq);
-              zq[u][0] = zv.x; zq[u][1] = zv.y; zq[u][2] = zv.z; zq[u][3] = zv.w;
+              const float4* zr = reinterpret_cast<const float4*>(static_cast<const float*>(p.z) + row * p.z_rs);
+              if (lane < nq) z0[u] = __ldg(zr + lane);
+              if (has2) z1[u] = __ldg(zr + lane + 32);
             } else {
-              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.z) + row * p.z_rs) + cq);
-              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-              const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-              zq[u][0] = a.x; zq[u][1] = a.y; zq[u][2] = c.x; zq[u][3] = c.y;
+              const uint2* zr = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.z) + row * p.z_rs);
+              if (lane < nq) {
+                const uint2 raw = __ldg(zr + lane);
+                const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                z0[u] = make_float4(a2.x, a2.y, c2.x, c2.y);
+              }
+              if (has2) {
+                const uint2 raw = __ldg(zr + lane + 32);
+                const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                z1[u] = make_float4(a2.x, a2.y, c2.x, c2.y);
+              }
             }
           }
         }
 #pragma unroll
-        for (int u = 0; u < ZU; ++u) {
-          const int cq = c0 + u;
-          if (cq >= cq1) break;
-          const float4 v = lds128(a_y + gp_y_off(m, cq));
-          float g[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
-          if (p.lnw) {
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(p.lnw) + cq);
-            const float4 bv = p.lnb ? __ldg(reinterpret_cast<const float4*>(p.lnb) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-            g[0] = fmaf(g[0], wv.x, bv.x); g[1] = fmaf(g[1], wv.y, bv.y); g[2] = fmaf(g[2], wv.z, bv.z); g[3] = fmaf(g[3], wv.w, bv.w);
-          }
-          if (l < 0) { g[0] = g[1] = g[2] = g[3] = 0.f; }
-          if (p.z && l >= 0) {
+        for (int u = 0; u < RU; ++u) {
+          const int mrow = pw * 16 + r0 + u;
+          const int l = lrow[u];
+          float sm1 = ((y0[u].x + y0[u].y) + (y0[u].z + y0[u].w)) + ((y1[u].x + y1[u].y) + (y1[u].z + y1[u].w));
 #pragma unroll
-            for (int i = 0; i < 4; ++i) g[i] *= p.z_act ? gp_silu(zq[u][i]) : zq[u][i];
-          }
-          if (TF32) {
-            if (p.g_out && l >= 0)
-              *(reinterpret_cast<float4*>(static_cast<float*>(p.g_out) + row * p.g_rs) + cq) = make_float4(g[0], g[1], g[2], g[3]);
-            sts128(a_y + gp_y_off(m, cq), make_float4(gp_rna(g[0]), gp_rna(g[1]), gp_rna(g[2]), gp_rna(g[3])));
-          } else {
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(g[0], g[1]), hi = __floats2bfloat162_rn(g[2], g[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-            if (p.g_out && l >= 0) *(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.g_out) + row * p.g_rs) + cq) = pk;
-            // bf16 operand tile: 64 channels per 128-byte row, 16-byte chunk = 8 channels = two quads
-            const uint32_t o = (uint32_t)(cq >> 4) * GP_BLOCK + m * 128 + ((((cq >> 1) & 7) ^ (m & 7)) << 4) + ((cq & 1) << 3);
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_a16 + o), "r"(pk.x), "r"(pk.y) : "memory");
+          for (int o = 16; o >= 1; o >>= 1) sm1 += __shfl_xor_sync(0xffffffffu, sm1, o);
+          const float mean = sm1 / D;
+          float q = 0.f;
+          if (lane < nq) { const float a0 = y0[u].x - mean, a1 = y0[u].y - mean, a2 = y0[u].z - mean, a3 = y0[u].w - mean; q = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, a3 * a3))); }
+          if (has2) { const float a0 = y1[u].x - mean, a1 = y1[u].y - mean, a2 = y1[u].z - mean, a3 = y1[u].w - mean; q += fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, a3 * a3))); }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          const float rstd = rsqrtf(q / D + p.eps);
+          const int64_t row = (int64_t)b * L + (l >= 0 ? l : 0);
+          if (lane == 0 && l >= 0 && p.mean_rstd) { p.mean_rstd[row * 2] = mean; p.mean_rstd[row * 2 + 1] = rstd; }
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const int cq = lane + 32 * hq;
+            if (hq == 0 ? lane >= nq : !has2) continue;
+            const float4 v = hq == 0 ? y0[u] : y1[u];
+            const float4 zz = hq == 0 ? z0[u] : z1[u];
+            float g[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
+            if (p.lnw) {
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(p.lnw) + cq);
+              const float4 bv = p.lnb ? __ldg(reinterpret_cast<const float4*>(p.lnb) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+              g[0] = fmaf(g[0], wv.x, bv.x); g[1] = fmaf(g[1], wv.y, bv.y); g[2] = fmaf(g[2], wv.z, bv.z); g[3] = fmaf(g[3], wv.w, bv.w);
+            }
+            if (l < 0) { g[0] = g[1] = g[2] = g[3] = 0.f; }
+            if (HAS_Z && l >= 0) {
+              g[0] *= p.z_act ? gp_silu(zz.x) : zz.x; g[1] *= p.z_act ? gp_silu(zz.y) : zz.y;
+              g[2] *= p.z_act ? gp_silu(zz.z) : zz.z; g[3] *= p.z_act ? gp_silu(zz.w) : zz.w;
+            }
+            if (TF32) {
+              if (HAS_G && l >= 0)
+                *(reinterpret_cast<float4*>(static_cast<float*>(p.g_out) + row * p.g_rs) + cq) = make_float4(g[0], g[1], g[2], g[3]);
+              sts128(a_y + gp_y_off(mrow, cq), make_float4(gp_rna(g[0]), gp_rna(g[1]), gp_rna(g[2]), gp_rna(g[3])));
+            } else {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(g[0], g[1]), hi = __floats2bfloat162_rn(g[2], g[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+              if (HAS_G && l >= 0) *(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.g_out) + row * p.g_rs) + cq) = pk;
+              // bf16 operand tile: 64 channels per 128-byte row, 16-byte chunk = 8 channels = two quads
+              const uint32_t o2 = (uint32_t)(cq >> 4) * GP_BLOCK + mrow * 128 + ((((cq >> 1) & 7) ^ (mrow & 7)) << 4) + ((cq & 1) << 3);
+              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_a16 + o2), "r"(pk.x), "r"(pk.y) : "memory");
+            }
           }
         }
       }
@@ -415,7 +427,7 @@ static size_t gp_smem_bytes(int D, int C, int esize) {
 
 bool gate_proj_tc_supported(int D, int C, int K, int dtype) {
   if (dtype != SS2D_F32 && dtype != SS2D_BF16) return false;
-  if (D <= 0 || (D % 64) != 0 || C < 16 || C > 256 || (C & 15) || K < 1 || K > SS2D_MAX_GROUP_DIRS) return false;
+  if (D <= 0 || (D % 64) != 0 || D > 256 || C < 16 || C > 256 || (C & 15) || K < 1 || K > SS2D_MAX_GROUP_DIRS) return false;
   return gp_smem_bytes(D, C, dtype == SS2D_F32 ? 4 : 2) <= 227 * 1024;
 }
 
@@ -456,10 +468,15 @@ int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw
     if (!gp_make_map4(&maps.nat, ys, dn, sn, bn) || !gp_make_map4(&maps.tr, ys, dt, st, bt)) return SS2D_ERR_UNSUPPORTED;
   }
   const size_t smem = gp_smem_bytes(D, C, esize);
-  auto kern = dtype == SS2D_F32 ? gate_proj_tc_kernel<true> : gate_proj_tc_kernel<false>;
-  static PerDeviceOnce once32, once16;
-  cudaError_t e = func_attr_once(dtype == SS2D_F32 ? once32 : once16, reinterpret_cast<const void*>(kern),
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  using KernT = void (*)(const GpParams, const GpMaps);
+  static const KernT kerns[8] = {gate_proj_tc_kernel<false, false, false>, gate_proj_tc_kernel<false, false, true>,
+                                 gate_proj_tc_kernel<false, true, false>,  gate_proj_tc_kernel<false, true, true>,
+                                 gate_proj_tc_kernel<true, false, false>,  gate_proj_tc_kernel<true, false, true>,
+                                 gate_proj_tc_kernel<true, true, false>,   gate_proj_tc_kernel<true, true, true>};
+  const int ki = (dtype == SS2D_F32 ? 4 : 0) + (z ? 2 : 0) + (g_out ? 1 : 0);
+  KernT kern = kerns[ki];
+  static PerDeviceOnce once[8];
+  cudaError_t e = func_attr_once(once[ki], reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) { *cerr = e; return SS2D_ERR_CUDA; }
   int grid = sm_count_current_device();
   if (grid > p.n_tiles) grid = p.n_tiles;

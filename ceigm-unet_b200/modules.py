@@ -107,7 +107,7 @@ class SS2D(nn.Module, mamba_init):
         self.Ds = self.D_init(d_inner, copies=k_group, merge=True)                                 # (K*D)
 
     # True: merge + out_norm + gate + out_proj as ONE tcgen05 kernel (csrc/gate_proj_tc.cu, Fn._OutGateProj) when eligible.
-    # Off by default: at the north-star shape that kernel takes 178 us against 146 + 19 us for the epilogue kernel followed by
+    # Off by default: at the north-star shape that kernel takes 170 us against 146 + 19 us for the epilogue kernel followed by
     # the tensor-core out_proj — its 96 KB operand tile allows one CTA per SM and its phases run back to back.
     fuse_out_proj = False
 
