@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   const uint32_t a_stage = sm;                                        // plane-box ring: ALIASES the weight (see the TMA warp)
   const uint32_t a_y = sm + (uint32_t)p.slots * GP_SLOT;               // fp32 tile: kb32 blocks
   const uint32_t a_a16 = a_y + (uint32_t)p.kb32 * GP_BLOCK;           // bf16 operand tile (bf16 variant only)
-  const uint32_t a_slabs = a_a16 + (TF32 ? 0u : (uint32_t)p.kblocks * GP_BLOCK);
+  const uint32_t a_slabs = a_a16 + ((TF32 || p.C == 0) ? 0u : (uint32_t)p.kblocks * GP_BLOCK);
   const uint32_t a_misc = a_slabs + GP_EPI_WARPS * 4096u;
   // misc: barriers + tmem pointer (128 B) | pixel tables 2 x 128 ints | statistics partials 2 x 256 floats
   const uint32_t b_w = a_misc, b_ready = a_misc + 8, b_afree = a_misc + 16, b_tfull = a_misc + 24, b_tempty = a_misc + 40, a_tptr = a_misc + 56;
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(a_tptr));
 
   const int D = p.D, L = p.L, H = p.H, W = p.W;
+  const bool proj = p.C > 0;          // C == 0: epilogue only (merge + LayerNorm + gate -> G rows), no weight, no MMA
 
   if (warp == 0) {
     // ================================ TMA: per tile the plane boxes, then the weight ================================
@@ -155,14 +156,15 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
     // is loaded over it (72 KB from L2, hidden behind the statistics / gate passes) for this tile's MMAs; the next tile's boxes
     // wait for those MMAs (`afree`).
     if (lane == 0) {
-      tma_prefetch_desc(&maps.w); tma_prefetch_desc(&maps.nat); tma_prefetch_desc(&maps.tr);
+      if (proj) tma_prefetch_desc(&maps.w);
+      tma_prefetch_desc(&maps.nat); tma_prefetch_desc(&maps.tr);
       const int kb_elems = TF32 ? 32 : 64;
       int rit = 0, it = 0, s2 = 0, ph = 0;
       for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
         const int b = t / p.tiles_per_batch, tib = t - b * p.tiles_per_batch;
         const int th = tib / p.tiles_w, tw = tib - th * p.tiles_w;
         const int h0 = th * GP_TH, w0 = tw * GP_TW;
-        tc_mbar_wait(b_afree, (it & 1) ^ 1);                      // MMAs of tile it - 1 have read the weight
+        if (proj) tc_mbar_wait(b_afree, (it & 1) ^ 1);            // MMAs of tile it - 1 have read the weight
         for (int cb = 0; cb < D / GP_CB; ++cb) {
           for (int k = 0; k < p.K; ++k, ++rit) {
             tc_mbar_wait(b_empty + 8 * s2, ph ^ 1);
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
             if (++s2 == p.slots) { s2 = 0; ph ^= 1; }
           }
         }
+        if (!proj) continue;                                      // epilogue only: the boxes of the next tile follow at once
         for (int u = rit > p.slots ? rit - p.slots : 0; u < rit; ++u)       // every box of this tile has been consumed
           tc_mbar_wait(b_empty + 8 * (u % p.slots), (u / p.slots) & 1);
         tc_mbar_expect(b_w, w_bytes);
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    if (lane == 0 && proj) {
       const uint32_t fmt = TF32 ? 2u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(GP_TILE >> 4) << 24);
       const uint32_t a_op = TF32 ? a_y : a_a16;
@@ -212,8 +215,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
       const int th = tib / p.tiles_w, tw = tib - th * p.tiles_w;
       const int h0 = th * GP_TH, w0 = tw * GP_TW;
       int* pix = s_pix + (it & 1) * GP_TILE;
-      tc_mbar_wait(b_tempty + 8 * (it & 1), ((it >> 1) & 1) ^ 1);    // epilogue of tile it - 2 done: its pixel table is free
-      tc_mbar_wait(b_afree, (it & 1) ^ 1);                           // MMAs of tile it - 1 have read the operand tile
+      if (proj) {
+        tc_mbar_wait(b_tempty + 8 * (it & 1), ((it >> 1) & 1) ^ 1);  // epilogue of tile it - 2 done: its pixel table is free
+        tc_mbar_wait(b_afree, (it & 1) ^ 1);                         // MMAs of tile it - 1 have read the operand tile
+      } else {
+        gp_bar_sync();                                               // every producer has left the previous tile
+      }
       if (pt < GP_TILE) {
         const int hh = pt >> 4, ww = ((pt & 15) - hh) & 15;
         const int h = h0 + hh, w = w0 + ww;
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
             if (TF32) {
               if (HAS_G && l >= 0)
                 *(reinterpret_cast<float4*>(static_cast<float*>(p.g_out) + row * p.g_rs) + cq) = make_float4(g[0], g[1], g[2], g[3]);
-              sts128(a_y + gp_y_off(mrow, cq), make_float4(gp_rna(g[0]), gp_rna(g[1]), gp_rna(g[2]), gp_rna(g[3])));
+              if (proj) sts128(a_y + gp_y_off(mrow, cq), make_float4(gp_rna(g[0]), gp_rna(g[1]), gp_rna(g[2]), gp_rna(g[3])));
             } else {
               const __nv_bfloat162 lo = __floats2bfloat162_rn(g[0], g[1]), hi = __floats2bfloat162_rn(g[2], g[3]);
               uint2 pk;
@@ -328,11 +335,12 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
               if (HAS_G && l >= 0) *(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.g_out) + row * p.g_rs) + cq) = pk;
               // bf16 operand tile: 64 channels per 128-byte row, 16-byte chunk = 8 channels = two quads
               const uint32_t o2 = (uint32_t)(cq >> 4) * GP_BLOCK + mrow * 128 + ((((cq >> 1) & 7) ^ (mrow & 7)) << 4) + ((cq & 1) << 3);
-              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_a16 + o2), "r"(pk.x), "r"(pk.y) : "memory");
+              if (proj) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_a16 + o2), "r"(pk.x), "r"(pk.y) : "memory");
             }
           }
         }
       }
+      if (!proj) continue;
       if (TF32) {      // the tensor core truncates fp32 containers: round this tile's copy of the weight to nearest TF32
         tc_mbar_wait(b_w, it & 1);
         for (uint32_t o = (uint32_t)pt * 16u; o < w_bytes; o += GP_PT * 16u) {
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
       __syncwarp();
       if (lane == 0) { tc_mbar_arrive(b_ready); if (TF32) tc_mbar_arrive(b_wready); }
     }
-  } else if (warp >= GP_EPI0) {
+  } else if (warp >= GP_EPI0 && proj) {
     // ================================ epilogue ================================
     const int lq = warp & 3;                    // TMEM lanes 32 lq ... (warp id % 4)
     const uint32_t slab = a_slabs + (uint32_t)(warp - GP_EPI0) * 4096u;
@@ -411,6 +419,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
 
 // ring slots: the weight's region plus 32 KB (fp32) / 16 KB (bf16) of extra staging
 static int gp_slots(int D, int C, int esize) {
+  if (C == 0) return 12;
   const size_t w = ((size_t)(D * esize / 128) * C * 128 + 1023) & ~(size_t)1023;
   int s = (int)((w + (esize == 4 ? 32768 : 16384)) / GP_SLOT);
   return s > GP_MAX_SLOTS ? GP_MAX_SLOTS : s;
@@ -419,7 +428,7 @@ static size_t gp_smem_bytes(int D, int C, int esize) {
   const int kblocks = D * esize / 128;
   const size_t w = ((size_t)kblocks * C * 128 + 1023) & ~(size_t)1023;
   const size_t y = (size_t)(D / 32) * GP_BLOCK;
-  const size_t a16 = esize == 2 ? (size_t)kblocks * GP_BLOCK : 0;
+  const size_t a16 = (esize == 2 && C > 0) ? (size_t)kblocks * GP_BLOCK : 0;
   size_t ring = (size_t)gp_slots(D, C, esize) * GP_SLOT;
   if (ring < w) ring = w;
   return ring + y + a16 + GP_EPI_WARPS * 4096 + 384 + 2 * GP_TILE * 4 + 2 * GP_PT * 4 + 1024 /* alignment slack */;
@@ -427,7 +436,8 @@ static size_t gp_smem_bytes(int D, int C, int esize) {
 
 bool gate_proj_tc_supported(int D, int C, int K, int dtype) {
   if (dtype != SS2D_F32 && dtype != SS2D_BF16) return false;
-  if (D <= 0 || (D % 64) != 0 || D > 256 || C < 16 || C > 256 || (C & 15) || K < 1 || K > SS2D_MAX_GROUP_DIRS) return false;
+  if (D <= 0 || (D % 64) != 0 || D > 256 || K < 1 || K > SS2D_MAX_GROUP_DIRS) return false;
+  if (C != 0 && (C < 16 || C > 256 || (C & 15))) return false;        // C == 0: epilogue only
   return gp_smem_bytes(D, C, dtype == SS2D_F32 ? 4 : 2) <= 227 * 1024;
 }
 
@@ -437,12 +447,12 @@ int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw
                         void* g_out, int64_t g_rs, float* mean_rstd, int batch, int D, int L, int H, int Wd, int C, int dtype,
                         cudaStream_t stream, cudaError_t* cerr) {
   *cerr = cudaSuccess;
-  if (!ys || !W || !out) return SS2D_ERR_NULL_POINTER;
+  if (!ys || (C > 0 && (!W || !out)) || (C == 0 && !g_out)) return SS2D_ERR_NULL_POINTER;
   if (batch <= 0 || L <= 0 || H <= 0 || Wd <= 0 || (int64_t)H * Wd != L) return SS2D_ERR_BAD_SHAPE;
   if (!gate_proj_tc_supported(D, C, K, dtype)) return SS2D_ERR_UNSUPPORTED;
   const int esize = dtype == SS2D_F32 ? 4 : 2;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (!al16(out) || ((out_rs * esize) & 15) || (z && (!al16(z) || ((z_rs * esize) & 15))) || (g_out && (!al16(g_out) || ((g_rs * esize) & 15))) ||
+  if ((C > 0 && (!al16(out) || ((out_rs * esize) & 15))) || (z && (!al16(z) || ((z_rs * esize) & 15))) || (g_out && (!al16(g_out) || ((g_rs * esize) & 15))) ||
       (lnw && !al16(lnw)) || (lnb && !al16(lnb)))
     return SS2D_ERR_ALIGNMENT;
   GpParams p;
@@ -459,7 +469,7 @@ int gate_proj_tc_launch(const float* ys, int K, unsigned tmask, const float* lnw
   p.slots = gp_slots(D, C, esize);
   GpMaps maps;
   memset(&maps, 0, sizeof(maps));
-  if (!tc_make_map(&maps.w, W, esize, D, C, ldw, C)) return SS2D_ERR_ALIGNMENT;
+  if (C > 0 && !tc_make_map(&maps.w, W, esize, D, C, ldw, C)) return SS2D_ERR_ALIGNMENT;
   {   // planes as images: natural (W inner) and transposed (H inner); box = 16 x 8 (resp. 8 x 16) pixels x 16 channels
     const long long bk = (long long)batch * K;
     const long long dn[4] = {Wd, H, D, bk}, sn[4] = {1, Wd, L, (long long)D * L};
