@@ -287,7 +287,10 @@ int32_t ss2d_linear_tc_supported(int32_t n_cols, int32_t K, int32_t dtype);
  * W: (C, D) rows ldw elements apart, `dtype`; bias: (C) fp32 or NULL. out: (batch * L, C) rows out_row_stride apart, `dtype`.
  * g_out: optional (batch * L, D) rows: the gated tensor (what out_proj's weight gradient needs); mean_rstd: optional
  * (batch * L, 2) fp32 for ss2d_out_gate_bwd. D % 64 == 0, C % 16 == 0, C <= 256, operand tile + weight within shared memory
- * (ss2d_gate_proj_supported); all row pointers / strides 16-byte aligned. */
+ * (ss2d_gate_proj_supported); H % 4 == 0 and Wd % 4 == 0 (the planes are read as TMA boxes); all row pointers / strides
+ * 16-byte aligned.
+ * C == 0 (W = NULL, out = NULL): epilogue only — the kernel stops after the gate and g_out (required) receives what
+ * ss2d_out_gate_fwd would write; the TMA-fed alternative to that kernel for 4-aligned images. */
 int ss2d_gate_proj_fwd(const float* ys, int32_t K, uint32_t transposed_mask, const float* ln_weight, const float* ln_bias, float eps,
                        const void* z, int64_t z_row_stride, int32_t z_act, const void* W, int64_t ldw, const float* bias, void* out,
                        int64_t out_row_stride, void* g_out, int64_t g_row_stride, float* mean_rstd, int32_t batch, int32_t D,
