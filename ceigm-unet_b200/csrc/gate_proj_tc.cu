@@ -275,18 +275,10 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
               if (has2) z1[u] = __ldg(zr + lane + 32);
             } else {
               const uint2* zr = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.z) + row * p.z_rs);
-              if (lane < nq) {
-                const uint2 raw = __ldg(zr + lane);
-                const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-                const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-                z0[u] = make_float4(a2.x, a2.y, c2.x, c2.y);
-              }
-              if (has2) {
-                const uint2 raw = __ldg(zr + lane + 32);
-                const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-                const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-                z1[u] = make_float4(a2.x, a2.y, c2.x, c2.y);
-              }
+              // keep the raw 16-bit pairs in the registers (converted where they are used): converting here would wait for
+              // each load before the next one is issued
+              if (lane < nq) { const uint2 raw = __ldg(zr + lane); z0[u].x = __uint_as_float(raw.x); z0[u].y = __uint_as_float(raw.y); }
+              if (has2) { const uint2 raw = __ldg(zr + lane + 32); z1[u].x = __uint_as_float(raw.x); z1[u].y = __uint_as_float(raw.y); }
             }
           }
         }
@@ -311,7 +303,13 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gate_proj_tc_kernel(const GpPar
             const int cq = lane + 32 * hq;
             if (hq == 0 ? lane >= nq : !has2) continue;
             const float4 v = hq == 0 ? y0[u] : y1[u];
-            const float4 zz = hq == 0 ? z0[u] : z1[u];
+            float4 zz = hq == 0 ? z0[u] : z1[u];
+            if (!TF32 && HAS_Z && l >= 0) {
+              const uint32_t r0 = __float_as_uint(zz.x), r1 = __float_as_uint(zz.y);
+              const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r0));
+              const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r1));
+              zz = make_float4(a2.x, a2.y, c2.x, c2.y);
+            }
             float g[4] = {(v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd};
             if (p.lnw) {
               const float4 wv = __ldg(reinterpret_cast<const float4*>(p.lnw) + cq);

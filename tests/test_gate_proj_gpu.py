@@ -91,17 +91,7 @@ def test_epilogue_only_mode_serves_out_gate_fwd(shape, dtype):
     lnb = 0.1 * torch.randn(D, device="cuda", generator=g)
     z = torch.randn(Bn, L, D, device="cuda", generator=g).to(dtype)
     assert ops.gate_proj_supported(D, 0, K, dtype)
-    out, stats = ops.out_gate_fwd(ys, lnw, lnb, z, True, 1e-5, dtype, (H, Wd), tmask)      # fp32: TMA-fed kernel; bf16: tiled kernel
-    if dtype == torch.bfloat16:       # the C = 0 mode itself also serves bf16 rows (not routed: it measured slower there)
-        out = torch.empty_like(out)
-        import ctypes
-        from ceigm_unet_b200 import _lib
-        rc = _lib.lib().ss2d_gate_proj_fwd(ctypes.c_void_p(ys.data_ptr()), K, ctypes.c_uint32(tmask), ctypes.c_void_p(lnw.data_ptr()),
-                                           ctypes.c_void_p(lnb.data_ptr()), ctypes.c_float(1e-5), ctypes.c_void_p(z.data_ptr()), D, 1, None, 0, None,
-                                           None, 0, ctypes.c_void_p(out.data_ptr()), D, ctypes.c_void_p(stats.data_ptr()), Bn, D, L, H, Wd, 0,
-                                           _lib.SS2D_BF16, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0
-        torch.cuda.synchronize()
+    out, stats = ops.out_gate_fwd(ys, lnw, lnb, z, True, 1e-5, dtype, (H, Wd), tmask)
     planes = [ys[:, k].double().view(Bn, D, Wd, H).transpose(2, 3).reshape(Bn, D, L) if (tmask >> k) & 1 else ys[:, k].double() for k in range(K)]
     y = sum(planes)
     ref = F.layer_norm(y.transpose(1, 2), (D,), lnw.double(), lnb.double(), 1e-5) * F.silu(z.double())
