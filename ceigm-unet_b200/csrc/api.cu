@@ -12,6 +12,7 @@
 
 namespace ss2d {
 cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
+bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err);
 cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_bwd_finalize(const ScanParams& p, float* dA, float* dD, float* dbias, cudaStream_t stream);
 cudaError_t scan_par_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
@@ -199,7 +200,7 @@ int ss2d_scan_fwd(const ss2d_scan_desc* d, const void* u, const void* delta, con
     cudaError_t e;
     if (use_par(p)) {      // d_state = 1: lean fp32 kernels (scan_n1.cu) when eligible, else the generic parallel-along-L ones
       if (!scan_n1_fwd_try(p, static_cast<cudaStream_t>(stream), &e)) e = scan_par_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
-    } else {
+    } else if (!scan_fwdr_try(p, static_cast<cudaStream_t>(stream), &e)) {     // lane-owns-row fast path (scan_fwdr.cu)
       e = scan_fwd_dispatch(p, static_cast<cudaStream_t>(stream));
     }
     if (e != cudaSuccess) return cuda_fail(e);

@@ -25,9 +25,9 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // fp32 tensor with innermost extent dims[0] (stride 4 bytes) and `rank` dimensions; strides in ELEMENTS for dims 1..;
-// box = (kTileL, box1, 1, ...) with 128-byte swizzle. Returns false when the tensor cannot be described.
+// box = (kTileL, box1, 1, ...) with 128-byte swizzle (or dense rows when swizzle = false). Returns false when the tensor cannot be described.
 inline bool make_tmap(TMap* out, const void* base, int rank, const long long* dims, const long long* strides_elems,
-                      int box1) {
+                      int box1, bool swizzle = true) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t gdim[5];
@@ -48,7 +48,7 @@ inline bool make_tmap(TMap* out, const void* base, int rank, const long long* di
   static_assert(sizeof(TMap) == sizeof(CUtensorMap), "TMap must mirror CUtensorMap");
   CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                   const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
