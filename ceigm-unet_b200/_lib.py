@@ -24,7 +24,7 @@ EXPORTS = [
     "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_out_gate_fwd", "ss2d_out_gate_bwd",
     "ss2d_out_gate_bwd_partials", "ss2d_group_gate_fwd", "ss2d_group_gate_bwd", "ss2d_out_gate_max_width", "ss2d_wgrad_ts", "ss2d_wgrad_ts_workspace_bytes",
     "ss2d_layernorm_fwd", "ss2d_layernorm_bwd", "ss2d_layernorm_bwd_partials",
-    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_dwconv3_act", "ss2d_dwconv3_act_planes", "ss2d_gate_proj_fwd", "ss2d_gate_proj_supported", "ss2d_linear_tc", "ss2d_linear_tc_supported", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count",
+    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_dwconv3_act", "ss2d_dwconv3_act_planes", "ss2d_gate_proj_fwd", "ss2d_gate_proj_supported", "ss2d_linear_tc", "ss2d_linear_tc_supported", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count", "ss2d_test_force_path",
 ]
 
 
@@ -141,6 +141,8 @@ def lib() -> ctypes.CDLL:
     L.ss2d_version.restype = ctypes.c_char_p
     L.ss2d_launch_count.argtypes = [ctypes.c_int]
     L.ss2d_launch_count.restype = ctypes.c_int64
+    L.ss2d_test_force_path.argtypes = [ctypes.c_int32]
+    L.ss2d_test_force_path.restype = ctypes.c_int32
     _lib = L
     return L
 
@@ -152,6 +154,13 @@ def check(rc: int, what: str) -> None:
         if rc == -7:
             msg += ": " + L.ss2d_last_cuda_error().decode()
         raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def test_force_path(policy: int) -> None:
+    """TEST HOOK (include/ss2d_b200.h: ss2d_test_force_path): 0 automatic, 1 / 2 lane-owns-row forward (32 / 16-row warps), 3 the 8-row-warp forward."""
+    rc = lib().ss2d_test_force_path(int(policy))
+    if rc != 0:
+        raise RuntimeError("ss2d_test_force_path(%d) -> %d" % (policy, rc))
 
 
 def launch_count(reset: bool = False) -> int:

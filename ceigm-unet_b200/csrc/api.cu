@@ -79,6 +79,8 @@ int linear_tc_launch(const void* A, int64_t lda, const void* W, int64_t ldw, con
 thread_local char g_cuda_err[256] = "";
 // process-wide: the autograd engine launches the backward kernels from its own per-device threads
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_path_policy{0};
+int scan_path_policy() { return g_path_policy.load(std::memory_order_relaxed); }
 
 static int cuda_fail(cudaError_t e) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -540,6 +542,11 @@ const char* ss2d_last_cuda_error(void) { return g_cuda_err; }
 const char* ss2d_version(void) { return "ss2d_b200 0.1.0 sm_100a"; }
 int64_t ss2d_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
+}
+int32_t ss2d_test_force_path(int32_t policy) {
+  if (policy < 0 || policy > 3) return SS2D_ERR_BAD_SHAPE;
+  g_path_policy.store(policy, std::memory_order_relaxed);
+  return SS2D_OK;
 }
 
 }  // extern "C"

@@ -260,6 +260,8 @@ static cudaError_t launch_fwdr(const ScanParams& p, const FwdrMaps& maps, cudaSt
   return cudaGetLastError();
 }
 
+int scan_path_policy();     // api.cu
+
 // Returns true when the fast path took the call (*err holds the launch status).
 bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   if (!p.tma_ok || p.N <= 4 || p.N > 16 || p.accum || p.io_dtype != SS2D_F32 || p.out_dtype != SS2D_F32) return false;
@@ -276,12 +278,9 @@ bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   const long long wb2 = (long long)((p.dpg + 15) / 16) * p.G * p.batch;
   if (wb2 >= 0x7fffffffLL) return false;
   const long long need = (long long)sm_count_current_device() * 4 * 2 * 9 / 10;
-#ifdef FR_FORCE_R
-  const bool r1 = FR_FORCE_R == 1;
-#else
-  if (wb2 < need) return false;
-  const bool r1 = wb1 >= need;
-#endif
+  const int policy = scan_path_policy();      // 0 unless a parity test forces a path (ss2d_test_force_path)
+  if (policy == 3 || (policy == 0 && wb2 < need)) return false;
+  const bool r1 = policy == 0 ? wb1 >= need : policy == 1;
   FwdrMaps maps;
   if (r1) {
     if (!fwdr_maps<1>(p, &maps)) return false;

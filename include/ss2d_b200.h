@@ -303,6 +303,12 @@ const char* ss2d_last_cuda_error(void);   /* thread-local text of the last SS2D_
 const char* ss2d_version(void);           /* "ss2d_b200 <semver> sm_100a" */
 /* number of this library's kernel launches issued by the calling thread since the last reset */
 int64_t ss2d_launch_count(int reset);
+/* TEST HOOK, not part of the operator interface. The forward kernel of a d_state 5..16 call is picked by how many warps
+ * the call gives the machine (csrc/scan_fwdr.cu); parity tests use this to run a small case through a kernel that only
+ * large calls would select. policy 0: automatic (the default, the only value a product caller ever needs); 1: lane-owns-row
+ * forward with 32-row warps; 2: the same with 16-row warps; 3: the 8-row-warp forward (scan_fwd.cu).
+ * Process-wide; returns SS2D_OK or SS2D_ERR_BAD_SHAPE. */
+int32_t ss2d_test_force_path(int32_t policy);
 
 #ifdef __cplusplus
 }

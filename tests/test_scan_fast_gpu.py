@@ -1,5 +1,8 @@
-"""GPU parity tests aimed at the fast backward path (csrc/scan_bwd2.cu: fp32, TMA-stageable, 8 < d_state <= 16, SCAN
-layout or directions 1 / 3) and the forward that feeds it its checkpoints: idle warps, ragged channel counts, padded
+"""GPU parity tests aimed at the fast paths of the north-star regime (fp32, TMA-stageable, 8 < d_state <= 16, SCAN
+layout or directions 1 / 3) — the backward csrc/scan_bwd2.cu and the forwards that feed it its checkpoints: csrc/scan_fwd.cu
+(8-row warps) and the lane-owns-row kernel csrc/scan_fwdr.cu, which only large calls select by themselves, so every case
+runs once per forward kernel through the test hook ss2d_test_force_path (policy 1: 32-row warps, 2: 16-row warps,
+3: 8-row warps): idle warps, ragged channel counts, padded
 state counts, sequence tails, reversed traversal with a tail (negative TMA start coordinate), input shared between
 the groups (u_dim_modulo). Checked through the C ABI (ops.ScanProblem) against the C/f64 oracle; for direction 3 the
 oracle sees the flipped sequences (CrossScan_3 / CrossMerge_3, model/gm/csms6s.py:133-168).
@@ -12,6 +15,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 NAMES = ["du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias"]
+
+
+@pytest.fixture(params=[1, 2, 3], ids=lambda p: "path%d" % p, autouse=True)
+def forced_path(request):
+    from ceigm_unet_b200 import _lib
+    _lib.test_force_path(request.param)
+    yield request.param
+    _lib.test_force_path(0)
 
 
 def _flip_groups(x, per_group, flip):
