@@ -5,7 +5,7 @@ Layers:
       `fwd` / `bwd` functions; `install_dropin()` registers them in sys.modules so that the reference's own
       `model/gm/csms6s.py` picks them up unchanged.
   b2  functional.py — SelectiveScanCore/Oflex, CrossScan[_k], CrossMerge[_k] autograd Functions.
-  b3  modules.py — SS2D, GroupMambaLayer with the reference's state_dict.
+  b3  modules.py — SS2D, GroupMambaLayer (and the FFNs next to them: PVT2FFN, custom_ffn) with the reference's state_dict.
 Underneath: ops.py -> _lib.py (ctypes) -> libss2d_b200.so (csrc/*.cu, C ABI in include/ss2d_b200.h).
 There is no CPU or PyTorch fallback: without the built library every operator raises RuntimeError.
 """
@@ -13,7 +13,7 @@ from . import _lib, dist, functional, modules, ops                 # noqa: F401
 from ._lib import build, launch_count, version                    # noqa: F401
 from .functional import (CrossMerge, CrossMerge_1, CrossMerge_2, CrossMerge_3, CrossMerge_4, CrossScan,   # noqa: F401
                          CrossScan_1, CrossScan_2, CrossScan_3, CrossScan_4, SelectiveScanCore, SelectiveScanOflex)
-from .modules import SS2D, GroupMambaLayer, mamba_init             # noqa: F401
+from .modules import SS2D, GroupMambaLayer, PVT2FFN, custom_ffn, mamba_init             # noqa: F401
 
 
 def graphed(module, sample_args, num_warmup_iters: int = 3):

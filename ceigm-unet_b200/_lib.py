@@ -24,7 +24,7 @@ EXPORTS = [
     "ss2d_cross_scan", "ss2d_cross_merge", "ss2d_out_gate_fwd", "ss2d_out_gate_bwd",
     "ss2d_out_gate_bwd_partials", "ss2d_group_gate_fwd", "ss2d_group_gate_bwd", "ss2d_out_gate_max_width", "ss2d_wgrad_ts", "ss2d_wgrad_ts_workspace_bytes",
     "ss2d_layernorm_fwd", "ss2d_layernorm_bwd", "ss2d_layernorm_bwd_partials",
-    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_dwconv3_act", "ss2d_dwconv3_act_planes", "ss2d_gate_proj_fwd", "ss2d_gate_proj_supported", "ss2d_linear_tc", "ss2d_linear_tc_supported", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count", "ss2d_test_force_path",
+    "ss2d_dwconv3_wgrad", "ss2d_dwconv3_wgrad_workspace_bytes", "ss2d_dwconv3_act", "ss2d_dwconv3_act_planes", "ss2d_gate_proj_fwd", "ss2d_gate_proj_supported", "ss2d_linear_tc", "ss2d_linear_tc_supported", "ss2d_strerror", "ss2d_last_cuda_error", "ss2d_version", "ss2d_launch_count", "ss2d_test_force_path", "ss2d_dwnhwc_stencil", "ss2d_dwnhwc_wgrad", "ss2d_dwnhwc_wgrad_workspace_bytes",
 ]
 
 
@@ -135,6 +135,13 @@ def lib() -> ctypes.CDLL:
     L.ss2d_linear_tc.restype = ctypes.c_int
     L.ss2d_linear_tc_supported.argtypes = [i32, i32, i32]
     L.ss2d_linear_tc_supported.restype = i32
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    L.ss2d_dwnhwc_stencil.argtypes = [vp, vp, vp, i32, ip, ip, pp, pp, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.ss2d_dwnhwc_stencil.restype = ctypes.c_int
+    L.ss2d_dwnhwc_wgrad.argtypes = [vp, vp, i32, i32, i32, fp, fp, i32, i32, i32, i32, i32, vp, sz, vp]
+    L.ss2d_dwnhwc_wgrad.restype = ctypes.c_int
+    L.ss2d_dwnhwc_wgrad_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+    L.ss2d_dwnhwc_wgrad_workspace_bytes.restype = sz
     L.ss2d_strerror.argtypes = [ctypes.c_int]
     L.ss2d_strerror.restype = ctypes.c_char_p
     L.ss2d_last_cuda_error.restype = ctypes.c_char_p

@@ -13,6 +13,13 @@
 namespace ss2d {
 cudaError_t scan_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
 bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err);
+constexpr int kDwnMaxSeg = 4;
+struct DwnSegs { int nseg; int cbeg[kDwnMaxSeg + 1]; int k[kDwnMaxSeg]; const float* w[kDwnMaxSeg]; const float* b[kDwnMaxSeg]; };
+cudaError_t dwnhwc_stencil_launch(const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B, int H,
+                                  int W, int C, int dt, cudaStream_t stream);
+int dwnhwc_wgrad_slabs(int B, int H, int W, int nc);
+cudaError_t dwnhwc_wgrad_launch(const void* x, const void* g, int c0, int nc, int K, float* dW, float* db, int B, int H, int W,
+                                int C, int dt, float* part, cudaStream_t stream);
 cudaError_t scan_bwd_dispatch(const ScanParams& p, cudaStream_t stream);
 cudaError_t scan_bwd_finalize(const ScanParams& p, float* dA, float* dD, float* dbias, cudaStream_t stream);
 cudaError_t scan_par_fwd_dispatch(const ScanParams& p, cudaStream_t stream);
@@ -472,6 +479,57 @@ int ss2d_dwconv3_act(int32_t mode, const void* x, const float* weight, const flo
   cudaError_t e = dwconv3_fused_launch(mode, x, weight, bias, dy, y, batch, C, H, W, dtype, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e);
   ++g_launches;
+  return SS2D_OK;
+}
+
+int ss2d_dwnhwc_stencil(const void* x, const void* aux, void* y, int32_t nseg, const int32_t* cbeg, const int32_t* ksize,
+                        const float* const* weight, const float* const* bias, int32_t flip, int32_t epi, int32_t batch,
+                        int32_t H, int32_t W, int32_t C, int32_t dtype, ss2d_stream_t stream) {
+  if (!x || !y || !cbeg || !ksize || !weight || (epi == 3 && !aux)) return SS2D_ERR_NULL_POINTER;
+  if (epi < 0 || epi > 3) return SS2D_ERR_UNSUPPORTED;
+  if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || nseg < 1 || nseg > kDwnMaxSeg || (int64_t)batch * H * W >= (1ll << 31))
+    return SS2D_ERR_BAD_SHAPE;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  DwnSegs sg;
+  memset(&sg, 0, sizeof(sg));
+  sg.nseg = nseg;
+  if (cbeg[0] != 0 || cbeg[nseg] != C) return SS2D_ERR_BAD_SHAPE;
+  for (int s = 0; s < nseg; ++s) {
+    if (cbeg[s + 1] <= cbeg[s]) return SS2D_ERR_BAD_SHAPE;
+    if (ksize[s] != 0 && ksize[s] != 1 && ksize[s] != 3 && ksize[s] != 5 && ksize[s] != 7) return SS2D_ERR_UNSUPPORTED;
+    if (ksize[s] > 1 && !weight[s]) return SS2D_ERR_NULL_POINTER;
+    sg.cbeg[s] = cbeg[s]; sg.k[s] = ksize[s]; sg.w[s] = weight[s]; sg.b[s] = bias ? bias[s] : nullptr;
+    if (!aligned(sg.w[s], 4) || !aligned(sg.b[s], 4)) return SS2D_ERR_ALIGNMENT;
+  }
+  sg.cbeg[nseg] = C;
+  const size_t va = 2 * esize(dtype);      // channel pairs move as one access when every segment starts on an even channel
+  if (!aligned(x, va) || !aligned(y, va) || (aux && !aligned(aux, va))) return SS2D_ERR_ALIGNMENT;
+  cudaError_t e = dwnhwc_stencil_launch(x, aux, y, sg, flip != 0, epi, batch, H, W, C, dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  ++g_launches;
+  return SS2D_OK;
+}
+
+size_t ss2d_dwnhwc_wgrad_workspace_bytes(int32_t batch, int32_t H, int32_t W, int32_t channels, int32_t ksize) {
+  if (batch <= 0 || H <= 0 || W <= 0 || channels <= 0 || (ksize != 3 && ksize != 5 && ksize != 7)) return 0;
+  return (size_t)dwnhwc_wgrad_slabs(batch, H, W, channels) * channels * (ksize * ksize + 1) * sizeof(float);
+}
+
+int ss2d_dwnhwc_wgrad(const void* x, const void* g, int32_t c0, int32_t c1, int32_t ksize, float* dweight, float* dbias,
+                      int32_t batch, int32_t H, int32_t W, int32_t C, int32_t dtype, void* workspace, size_t workspace_bytes,
+                      ss2d_stream_t stream) {
+  if (!x || !g || !dweight) return SS2D_ERR_NULL_POINTER;
+  if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || c0 < 0 || c1 <= c0 || c1 > C || (int64_t)batch * H * W >= (1ll << 31))
+    return SS2D_ERR_BAD_SHAPE;
+  if (ksize != 3 && ksize != 5 && ksize != 7) return SS2D_ERR_UNSUPPORTED;
+  if (!dtype_ok(dtype)) return SS2D_ERR_BAD_DTYPE;
+  if (!aligned(x, esize(dtype)) || !aligned(g, esize(dtype)) || !aligned(dweight, 4) || !aligned(dbias, 4)) return SS2D_ERR_ALIGNMENT;
+  if (!workspace || workspace_bytes < ss2d_dwnhwc_wgrad_workspace_bytes(batch, H, W, c1 - c0, ksize) || !aligned(workspace, 4))
+    return SS2D_ERR_WORKSPACE;
+  cudaError_t e = dwnhwc_wgrad_launch(x, g, c0, c1 - c0, ksize, dweight, dbias, batch, H, W, C, dtype,
+                                      static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e);
+  g_launches += 2;
   return SS2D_OK;
 }
 

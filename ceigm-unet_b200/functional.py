@@ -672,3 +672,71 @@ def dwconv3(x, conv: "torch.nn.Conv2d"):
           conv.dilation == (1, 1) and conv.groups == conv.in_channels == conv.out_channels and conv.padding_mode == "zeros" and
           x.shape[0] * x.shape[2] * x.shape[3] >= _TS_MIN_ROWS)
     return _DWConv3.apply(x, conv.weight, conv.bias) if ok else conv(x)
+
+
+class _FFNDepthwise(torch.autograd.Function):
+    """The depthwise stack between fc1 and fc2 of PVT2FFN / custom_ffn on the channels-last token tensor (csrc/ffn_dw.cu):
+        y1  = GELU(dw3x3(h) + b)                                                   groupmamba.py:76-78, custom_mlp.py:363-364
+        out = y1 + cat(y1_id, dw3x3(y1_3), dw5x5(y1_5), dw7x7(y1_7))   (custom_ffn)  custom_mlp.py:323-336
+    h: (B, L, C) contiguous, hw = (H, W). ms = None (PVT2FFN) or the six multi-scale tensors (w3, b3, w5, b5, w7, b7).
+    Two launches forward (one without the multi-scale block); backward: the data gradient is three stencil launches
+    (multi-scale transposed + residual; GELU' on the recomputed pre-activation; 3x3 transposed), the parameter gradients
+    one reduction per convolution. Saved: h and y1 — what the reference's autograd keeps is h, the pre-activation, y1, the
+    three splits and their outputs."""
+
+    @staticmethod
+    @_custom_fwd
+    def forward(ctx, h, hw, w3, b3, *ms):
+        C = h.shape[-1]
+        h = h.contiguous()
+        y1 = ops.dwnhwc_stencil(h, hw, [(C, 3, w3, b3)], epi=ops.EPI_GELU)
+        ctx.hw, ctx.has_ms = hw, len(ms) > 0
+        if ctx.has_ms:
+            gc = ms[0].shape[0]
+            ctx.gc = gc
+            segs = [(C - 3 * gc, 1, None, None), (C - 2 * gc, 3, ms[0], ms[1]), (C - gc, 5, ms[2], ms[3]), (C, 7, ms[4], ms[5])]
+            out = ops.dwnhwc_stencil(y1, hw, segs, epi=ops.EPI_RESIDUAL)
+            ctx.save_for_backward(h, y1, w3, b3, *ms)
+        else:
+            out = y1
+            ctx.save_for_backward(h, w3, b3)
+        return out
+
+    @staticmethod
+    @_custom_bwd
+    def backward(ctx, dout):
+        hw = ctx.hw
+        dout = dout.contiguous()
+        if ctx.has_ms:
+            h, y1, w3, b3, *ms = ctx.saved_tensors
+        else:
+            h, w3, b3 = ctx.saved_tensors
+            ms = []
+        C = h.shape[-1]
+        if dout.dtype != h.dtype:
+            dout = dout.to(h.dtype)
+        grads_ms = []
+        if ctx.has_ms:
+            gc = ctx.gc
+            segs = [(C - 3 * gc, 1, None, None), (C - 2 * gc, 3, ms[0], None), (C - gc, 5, ms[2], None), (C, 7, ms[4], None)]
+            dy1 = ops.dwnhwc_stencil(dout, hw, segs, flip=True, epi=ops.EPI_RESIDUAL)
+            for i, k in enumerate((3, 5, 7)):
+                c0 = C - (3 - i) * gc
+                dW, db = ops.dwnhwc_wgrad(y1, dout, hw, c0, c0 + gc, k, True)
+                grads_ms += [dW.to(ms[2 * i].dtype), db.to(ms[2 * i + 1].dtype)]
+        else:
+            dy1 = dout
+        dz = ops.dwnhwc_stencil(h, hw, [(C, 3, w3, b3)], epi=ops.EPI_DGELU_MUL, aux=dy1)
+        dh = ops.dwnhwc_stencil(dz, hw, [(C, 3, w3, None)], flip=True, epi=ops.EPI_NONE) if ctx.needs_input_grad[0] else None
+        dW3, db3 = ops.dwnhwc_wgrad(h, dz, hw, 0, C, 3, True)
+        return (dh, None, dW3.to(w3.dtype), db3.to(b3.dtype), *grads_ms)
+
+
+def ffn_depthwise(h, hw, conv3: "torch.nn.Conv2d", ms_convs=None):
+    """h (B, L, C) -> the input of fc2. conv3: the DWConv's nn.Conv2d; ms_convs: (dwconv_3x3, dwconv_5x5, dwconv_7x7) or None."""
+    _need_cuda(h, "ffn_depthwise")
+    ms = []
+    if ms_convs is not None:
+        for m in ms_convs:
+            ms += [m.weight, m.bias]
+    return _FFNDepthwise.apply(h, hw, conv3.weight, conv3.bias, *ms)

@@ -335,3 +335,78 @@ class GroupMambaLayer(nn.Module):
         xm = xm.view(Bn, L, C) * aff.unsqueeze(1)                               # :154
         xm = Fn.layer_norm_rows(xm, self.norm.weight, self.norm.bias, self.norm.eps)   # :156 (same LayerNorm, shared weights)
         return Fn.linear_ts(xm, self.proj.weight, self.proj.bias)               # :157
+
+
+# ---- the GroupMamba FFNs: same constructors, sub-module names and initialisation as the reference, the
+#      depthwise stack between the two linear layers on this package's channels-last kernels ----
+def _ffn_init_weights(m):
+    """PVT2FFN._init_weights / custom_ffn._init_weights (groupmamba.py:63-76, custom_mlp.py:349-361)."""
+    if isinstance(m, nn.Linear):
+        nn.init.trunc_normal_(m.weight, std=.02)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+    elif isinstance(m, nn.LayerNorm):
+        nn.init.constant_(m.bias, 0)
+        nn.init.constant_(m.weight, 1.0)
+    elif isinstance(m, nn.Conv2d):
+        fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+        fan_out //= m.groups
+        m.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+        if m.bias is not None:
+            m.bias.data.zero_()
+
+
+class DWConv(nn.Module):
+    """Parameter holder of the reference's DWConv (groupmamba.py:446-455): `dwconv` = depthwise 3 x 3 with bias."""
+
+    def __init__(self, dim=768):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+
+class InceptionDWConv2d_MultiScale(nn.Module):
+    """Parameter holder of custom_mlp.py:313-336: identity | 3 x 3 | 5 x 5 | 7 x 7 depthwise branches on channel segments."""
+
+    def __init__(self, in_channels, kernel_sizes=(1, 3, 5), branch_ratio=0.125):
+        super().__init__()
+        gc = int(in_channels * branch_ratio)
+        self.dwconv_3x3 = nn.Conv2d(gc, gc, kernel_size=3, padding=1, groups=gc)
+        self.dwconv_5x5 = nn.Conv2d(gc, gc, kernel_size=5, padding=2, groups=gc)
+        self.dwconv_7x7 = nn.Conv2d(gc, gc, kernel_size=7, padding=3, groups=gc)
+        self.split_indexes = (in_channels - 3 * gc, gc, gc, gc)
+
+
+class PVT2FFN(nn.Module):
+    """fc1 -> depthwise 3 x 3 -> GELU -> fc2 (groupmamba.py:54-83); forward(x (B, L, C), H, W)."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.dwconv = DWConv(hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, in_features)
+        self.apply(_ffn_init_weights)
+
+    def forward(self, x, H, W):
+        h = self.fc1(x)
+        y = Fn.ffn_depthwise(h, (H, W), self.dwconv.dwconv)
+        return self.fc2(y)
+
+
+class custom_ffn(nn.Module):
+    """fc1 -> depthwise 3 x 3 -> GELU -> multi-scale depthwise residual -> fc2 (custom_mlp.py:338-368)."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.dwconv = DWConv(hidden_features)
+        self.act = nn.GELU()
+        self.custom = InceptionDWConv2d_MultiScale(hidden_features, [])
+        self.fc2 = nn.Linear(hidden_features, in_features)
+        self.apply(_ffn_init_weights)
+
+    def forward(self, x, H, W):
+        h = self.fc1(x)
+        c = self.custom
+        y = Fn.ffn_depthwise(h, (H, W), self.dwconv.dwconv, (c.dwconv_3x3, c.dwconv_5x5, c.dwconv_7x7))
+        return self.fc2(y)

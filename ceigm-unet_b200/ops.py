@@ -545,3 +545,56 @@ def dwconv3_wgrad(x: torch.Tensor, dy: torch.Tensor, want_bias: bool):
                                   _stream(x.device))
     _lib.check(rc, "ss2d_dwconv3_wgrad")
     return dW, db
+
+
+# ---- depthwise stack of the GroupMamba FFNs on channels-last tensors (csrc/ffn_dw.cu) -------------------------------
+EPI_NONE, EPI_GELU, EPI_RESIDUAL, EPI_DGELU_MUL = 0, 1, 2, 3
+
+
+def dwnhwc_stencil(x: torch.Tensor, hw, segments, *, flip: bool = False, epi: int = EPI_NONE, aux=None) -> torch.Tensor:
+    """y = epi(bias + depthwise conv(x)) on the (B, H, W, C) image behind a contiguous (B, L, C) token tensor.
+    segments: [(c_end, ksize, weight (c, 1, k, k) or None, bias (c) or None), ...] in channel order (ksize 0: no taps)."""
+    _require(x.is_cuda and x.dtype in _DT and x.is_contiguous() and x.dim() == 3, "dwnhwc_stencil: contiguous CUDA (B, L, C) tensor")
+    Bn, L, C = x.shape
+    H, W = int(hw[0]), int(hw[1])
+    _require(H * W == L, "dwnhwc_stencil: H * W must equal the token count")
+    _require(aux is None or (aux.shape == x.shape and aux.dtype == x.dtype and aux.is_contiguous()), "dwnhwc_stencil: aux must match x")
+    n = len(segments)
+    _require(1 <= n <= 4 and segments[-1][0] == C, "dwnhwc_stencil: 1..4 channel segments covering C")
+    cbeg = (ctypes.c_int32 * (n + 1))(0, *[int(sg[0]) for sg in segments])
+    ks = (ctypes.c_int32 * n)(*[int(sg[1]) for sg in segments])
+    keep = []                      # fp32 contiguous copies stay alive until the launch is enqueued
+    wp, bp = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)()
+    for i, (_, k, w, b) in enumerate(segments):
+        w32 = None if w is None else w.detach().float().contiguous()
+        b32 = None if b is None else b.detach().float().contiguous()
+        keep += [w32, b32]
+        wp[i] = None if w32 is None else w32.data_ptr()
+        bp[i] = None if b32 is None else b32.data_ptr()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ss2d_dwnhwc_stencil(_ptr(x), _ptr(aux), _ptr(y), n, cbeg, ks, wp, bp, 1 if flip else 0, int(epi), Bn, H, W, C,
+                                            _DT[x.dtype], _stream(x.device))
+    _lib.check(rc, "ss2d_dwnhwc_stencil")
+    return y
+
+
+def dwnhwc_wgrad(x: torch.Tensor, g: torch.Tensor, hw, c0: int, c1: int, ksize: int, want_bias: bool = True):
+    """Weight / bias gradient of the depthwise segment [c0, c1): -> dweight (c1 - c0, 1, k, k) fp32, dbias (c1 - c0) or None."""
+    _require(x.is_cuda and x.dtype in _DT and x.is_contiguous() and x.dim() == 3 and g.shape == x.shape and g.dtype == x.dtype
+             and g.is_contiguous(), "dwnhwc_wgrad: contiguous CUDA (B, L, C) tensors of one dtype")
+    Bn, L, C = x.shape
+    H, W = int(hw[0]), int(hw[1])
+    _require(H * W == L, "dwnhwc_wgrad: H * W must equal the token count")
+    Lb = _lib.lib()
+    nc = c1 - c0
+    ws_bytes = int(Lb.ss2d_dwnhwc_wgrad_workspace_bytes(Bn, H, W, nc, ksize))
+    _require(ws_bytes > 0, "dwnhwc_wgrad: unsupported segment")
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=x.device)
+    dW = torch.empty((nc, 1, ksize, ksize), dtype=torch.float32, device=x.device)
+    db = torch.empty((nc,), dtype=torch.float32, device=x.device) if want_bias else None
+    with torch.cuda.device(x.device):
+        rc = Lb.ss2d_dwnhwc_wgrad(_ptr(x), _ptr(g), c0, c1, ksize, _ptr(dW), _ptr(db), Bn, H, W, C, _DT[x.dtype], _ptr(ws),
+                                  ctypes.c_size_t(ws_bytes), _stream(x.device))
+    _lib.check(rc, "ss2d_dwnhwc_wgrad")
+    return dW, db

@@ -7,7 +7,9 @@ No reference file is edited. What the harness does instead (SURVEY.md Appendix A
     reference imports in try/except at model/gm/csms6s.py:209-220 — level-1 drop-in: every scan goes through libss2d_b200.so;
   * `model.EMCAD22nn = model.EMCAD22n` (model/__init__.py:9 binds EMCAD22n, :29 reads EMCAD22nn -> NameError);
   * level 2 (`fused=True`): `model.gm.groupmamba.GroupMambaLayer` is rebound to `ceigm_unet_b200.GroupMambaLayer` before the
-    model is built (Block_mamba looks the name up at construction, groupmamba.py:203) — same state_dict, fused kernels.
+    model is built (Block_mamba looks the name up at construction, groupmamba.py:203) — same state_dict, fused kernels;
+    likewise `PVT2FFN` (groupmamba.py:204) and the decoder's `custom_ffn` (custom_module.py:51) -> the channels-last
+    depthwise-stack kernels (csrc/ffn_dw.cu).
 
 `scan="cpu_ref"` is for the CHECKER side of tests and the CPU baseline of bench.py only: SelectiveScanCore is rebound to the
 oracle's restatement of the reference's PyTorch scan (the reference has no CPU scan, csms6s.py:352).
@@ -85,6 +87,10 @@ def load_reference(scan: str = "dropin", fused: bool = False):
     if fused:
         import ceigm_unet_b200 as pkg
         gmb.GroupMambaLayer = pkg.GroupMambaLayer
+        # the FFNs next to the SS2D branch: Block_mamba reads PVT2FFN from groupmamba's globals
+        # (groupmamba.py:204), the decoder's `cm` passes custom_module's `custom_ffn` (custom_module.py:51)
+        gmb.PVT2FFN = pkg.PVT2FFN
+        importlib.import_module("model.gm.custom_module").custom_ffn = pkg.custom_ffn
     return model
 
 

@@ -203,6 +203,27 @@ int ss2d_dwconv3_wgrad(const float* x, const float* dy, float* dweight, float* d
                        int32_t W, void* workspace, size_t workspace_bytes, ss2d_stream_t stream);
 size_t ss2d_dwconv3_wgrad_workspace_bytes(int32_t batch, int32_t C, int32_t H, int32_t W);
 
+/* ---- the depthwise stack of the GroupMamba FFNs on channels-last tensors -----------------
+ * PVT2FFN (model/gm/groupmamba.py:54-83: fc1 -> DWConv 3x3 -> GELU -> fc2; DWConv = :446-455) and custom_ffn
+ * (model/gm/custom_mlp.py:338-368: ... -> GELU -> InceptionDWConv2d_MultiScale (:313-336) -> fc2) between the two
+ * linear layers. The (B, L, C) token tensor is read as the (batch, H, W, C) channels-last image it is: no NCHW copies.
+ *   y = epi(bias[c] + sum_(i,j) weight[c][i][j] * x[b, h+i-P, w+j-P, c]),  zero padding P = k / 2,
+ * with the kernel size chosen per channel SEGMENT: channels [cbeg[s], cbeg[s+1]) use ksize[s] in {0, 1, 3, 5, 7}
+ * (0: no taps, acc = 0; 1: identity, acc = x, no weight — the untouched channels of the multi-scale block), weight[s] = (channels, 1, k, k) fp32 as nn.Conv2d(groups=channels).weight, bias[s] (fp32) or NULL.
+ * nseg <= 4, cbeg[0] = 0, cbeg[nseg] = C. flip = 1 correlates with the flipped kernel (the transposed convolution:
+ * data gradient). epi 0: y = acc; 1: y = GELU(acc) (exact erf, nn.GELU()); 2: y = x + acc (the multi-scale residual);
+ * 3: y = aux * GELU'(acc) (gradient of the pre-activation, recomputed from x). x, aux, y: `dtype`, contiguous. */
+int ss2d_dwnhwc_stencil(const void* x, const void* aux, void* y, int32_t nseg, const int32_t* cbeg, const int32_t* ksize,
+                        const float* const* weight, const float* const* bias, int32_t flip, int32_t epi, int32_t batch,
+                        int32_t H, int32_t W, int32_t C, int32_t dtype, ss2d_stream_t stream);
+/* Weight / bias gradient of one segment [c0, c1) with kernel size ksize in {3, 5, 7}:
+ * dweight[c][i][j] = sum_(b,h,w) g[b,h,w,c] x[b,h+i-P,w+j-P,c] ((c1 - c0, 1, k, k) fp32), dbias[c] = sum g (fp32 or NULL).
+ * x, g: (batch, H, W, C) of `dtype`. Fully overwritten, deterministic. workspace: ss2d_dwnhwc_wgrad_workspace_bytes. */
+int ss2d_dwnhwc_wgrad(const void* x, const void* g, int32_t c0, int32_t c1, int32_t ksize, float* dweight, float* dbias,
+                      int32_t batch, int32_t H, int32_t W, int32_t C, int32_t dtype, void* workspace, size_t workspace_bytes,
+                      ss2d_stream_t stream);
+size_t ss2d_dwnhwc_wgrad_workspace_bytes(int32_t batch, int32_t H, int32_t W, int32_t channels, int32_t ksize);
+
 /* ---- depthwise 3 x 3 convolution fused with SiLU: forward and input gradient -------------------------------
  * nn.Conv2d(D, D, groups=D, kernel_size=3, padding=1) followed by SiLU (model/gm/ss2d.py:512-513) as one pass.
  * x, dy, y: (batch, C, H, W) contiguous tensors of `dtype`; weight: (C, 1, 3, 3) fp32; bias: (C) fp32 or NULL.

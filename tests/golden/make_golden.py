@@ -8,6 +8,7 @@ Reference entry points exercised:
   model/gm/ss2d.py:521-556                                SS2D (k_group=1, d_state=1)
   model/vmamba/vmamba.py:992                              SS2D (k_group=4, d_state=16, forward_type v2)
   model/gm/groupmamba.py:85-159                           GroupMambaLayer
+  model/gm/groupmamba.py:54-83, custom_mlp.py:313-368     PVT2FFN, custom_ffn (+ their initialisation under a fixed seed)
 """
 from __future__ import annotations
 
@@ -177,6 +178,28 @@ def gen_init(gm, vm):
     print("init_seed1234", len(rec), "arrays")
 
 
+def gen_ffn(gm):
+    """The feed-forward blocks next to the SS2D branch, non-square maps on purpose."""
+    torch.manual_seed(11)
+    m = gm["groupmamba"].PVT2FFN(16, 64)
+    init = {"init." + k: _np(v).copy() for k, v in m.state_dict().items()}
+    _perturb(m, 12)
+    x = torch.randn(2, 30, 16, generator=torch.Generator().manual_seed(13))
+    rec = _module_record(m, x, lambda t: m(t, 6, 5))
+    rec.update(init)
+    np.savez_compressed(os.path.join(HERE, "ffn_pvt2.npz"), **rec)
+    print("ffn_pvt2", rec["y"].shape)
+    torch.manual_seed(14)
+    m = gm["custom_mlp"].custom_ffn(12, 48)              # gc = 6: segments 30 | 6 | 6 | 6
+    init = {"init." + k: _np(v).copy() for k, v in m.state_dict().items()}
+    _perturb(m, 15)
+    x = torch.randn(2, 56, 12, generator=torch.Generator().manual_seed(16))
+    rec = _module_record(m, x, lambda t: m(t, 8, 7))
+    rec.update(init)
+    np.savez_compressed(os.path.join(HERE, "ffn_custom.npz"), **rec)
+    print("ffn_custom", rec["y"].shape)
+
+
 if __name__ == "__main__":
     if not RL.available():
         raise SystemExit("reference tree not present: golden vectors can only be regenerated in the build container")
@@ -188,3 +211,4 @@ if __name__ == "__main__":
     gen_ss2d_vm(vm)
     gen_group_layer(gm)
     gen_init(gm, vm)
+    gen_ffn(gm)

@@ -1,0 +1,126 @@
+"""GPU parity of the FFN depthwise stack (csrc/ffn_dw.cu): ceigm_unet_b200.PVT2FFN / custom_ffn against
+(1) outputs and gradients recorded from the UNMODIFIED reference modules (tests/golden/ffn_*.npz) and (2) the oracle
+restatement (oracle/ffn_ref.py, fp32 on the CPU) at the live stage shapes of the 224^2 model — hidden 512 @ 56^2 and
+1392 @ 14^2 (whose 174-channel multi-scale segments start on even, not 4-aligned, channels) and an odd-channel case for
+the scalar path; the kernels are also checked alone through the C ABI (ops.dwnhwc_stencil / dwnhwc_wgrad) against
+torch's conv2d. Tolerances (BASELINE.json north_star): rel <= 1e-3 fp32 (2e-3 parameter gradients), <= 2e-2 under bf16 autocast;
+rel = max |got - ref| / max |ref| per tensor."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_err(got, ref):
+    got = got.detach().double().cpu().numpy()
+    ref = ref.detach().double().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("name,ctor,hw", [("ffn_pvt2.npz", "PVT2FFN", (6, 5)), ("ffn_custom.npz", "custom_ffn", (8, 7))])
+def test_ffn_vs_reference_golden(name, ctor, hw):
+    import ceigm_unet_b200 as pkg
+    g = _load(name)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    mod = getattr(pkg, ctor)(sd["fc1.weight"].shape[1], sd["fc1.weight"].shape[0])
+    missing, unexpected = mod.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    mod = mod.cuda()
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    y = mod(x, *hw)
+    assert rel_err(y, g["y"]) < 1e-3
+    (y * torch.from_numpy(g["dy"]).cuda()).sum().backward()
+    assert rel_err(x.grad, g["dx"]) < 1e-3
+    for n, p in mod.named_parameters():
+        assert rel_err(p.grad, g["grad." + n]) < 2e-3, n
+
+
+def _oracle_case(ctor, C, hidden, H, W, B, amp):
+    import ceigm_unet_b200 as pkg
+    from oracle import ffn_ref
+    torch.manual_seed(5)
+    mod = getattr(pkg, ctor)(C, hidden)
+    gen = torch.Generator().manual_seed(6)
+    with torch.no_grad():                                   # away from the zero biases / tiny weights of the initialisation
+        for p in mod.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    x = torch.randn(B, H * W, C, generator=gen)
+    dy = torch.randn(B, H * W, C, generator=gen)
+    pr = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref = (ffn_ref.pvt2_ffn if ctor == "PVT2FFN" else ffn_ref.custom_ffn)(xr, pr, H, W)
+    (ref * dy).sum().backward()
+    mod = mod.cuda()
+    xg = x.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        y = mod(xg, H, W)
+    (y.float() * dy.cuda()).sum().backward()
+    tol = 2e-2 if amp else 1e-3
+    assert rel_err(y.float(), ref) < tol
+    assert rel_err(xg.grad, xr.grad) < tol
+    for n, p in mod.named_parameters():
+        assert rel_err(p.grad, pr[n].grad) < 2 * tol, n
+
+
+@pytest.mark.parametrize("ctor", ["PVT2FFN", "custom_ffn"])
+@pytest.mark.parametrize("C,hidden,H,W", [(64, 512, 56, 56), (348, 1392, 14, 14), (9, 45, 7, 9)])
+def test_ffn_vs_oracle_live_shapes(ctor, C, hidden, H, W):
+    _oracle_case(ctor, C, hidden, H, W, 2, False)
+
+
+@pytest.mark.parametrize("ctor", ["PVT2FFN", "custom_ffn"])
+def test_ffn_bf16_autocast(ctor):
+    _oracle_case(ctor, 128, 1024, 28, 28, 2, True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_stencil_and_wgrad_kernels_vs_conv2d(dtype, k):
+    """One segment with kernel size k between two untouched ones, through the C ABI: forward, flipped (transposed) pass and
+    the parameter gradients against F.conv2d / autograd on the NCHW view."""
+    from ceigm_unet_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(k)
+    B, H, W, C, c0, c1 = 3, 11, 9, 20, 6, 14
+    x = torch.randn(B, H * W, C, device="cuda", generator=gen).to(dtype)
+    g = torch.randn(B, H * W, C, device="cuda", generator=gen).to(dtype)
+    w = torch.randn(c1 - c0, 1, k, k, device="cuda", generator=gen)
+    b = torch.randn(c1 - c0, device="cuda", generator=gen)
+    segs = [(c0, 0, None, None), (c1, k, w, b), (C, 0, None, None)]
+    y = ops.dwnhwc_stencil(x, (H, W), segs, epi=ops.EPI_NONE)
+    img = x.float().transpose(1, 2).reshape(B, C, H, W)[:, c0:c1].clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv2d(img, wr, br, padding=k // 2, groups=c1 - c0)
+    tol = 1e-3 if dtype == torch.float32 else 2e-2
+    got = y.float().transpose(1, 2).reshape(B, C, H, W)
+    assert rel_err(got[:, c0:c1], ref) < tol
+    assert float(got[:, :c0].abs().max()) == 0.0 and float(got[:, c1:].abs().max()) == 0.0
+    gi = g.float().transpose(1, 2).reshape(B, C, H, W)[:, c0:c1]
+    ref.backward(gi)
+    dx = ops.dwnhwc_stencil(g, (H, W), [(c0, 0, None, None), (c1, k, w, None), (C, 0, None, None)], flip=True, epi=ops.EPI_NONE)
+    assert rel_err(dx.float().transpose(1, 2).reshape(B, C, H, W)[:, c0:c1], img.grad) < tol
+    dW, db = ops.dwnhwc_wgrad(x, g, (H, W), c0, c1, k)
+    assert rel_err(dW, wr.grad) < tol and rel_err(db, br.grad) < tol
+
+
+def test_stencil_rejects_bad_arguments():
+    from ceigm_unet_b200 import ops
+    x = torch.randn(1, 12, 8, device="cuda")
+    w = torch.randn(8, 1, 3, 3, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.dwnhwc_stencil(x, (3, 5), [(8, 3, w, None)])                 # H * W != L
+    with pytest.raises(RuntimeError):
+        ops.dwnhwc_stencil(x, (3, 4), [(8, 4, w, None)])                 # unsupported kernel size
+    with pytest.raises(RuntimeError):
+        ops.dwnhwc_stencil(x.cpu(), (3, 4), [(8, 3, w, None)])           # no CPU path

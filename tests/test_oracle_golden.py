@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import c_oracle, cross_scan, scan_analytic, ss2d_ref
+from oracle import c_oracle, cross_scan, ffn_ref, scan_analytic, ss2d_ref
 from oracle.selective_scan_ref import selective_scan_ref
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -128,6 +128,26 @@ def test_ss2d_vm_restatement():
 
 def test_group_layer_restatement():
     _module_case(os.path.join(GOLDEN, "group_mamba_layer.npz"), lambda x, p: ss2d_ref.group_layer(x, p, 6, 6))
+
+
+def test_ffn_restatements():
+    """oracle/ffn_ref.py vs the unmodified PVT2FFN / custom_ffn (outputs, input and parameter gradients)."""
+    _module_case(os.path.join(GOLDEN, "ffn_pvt2.npz"), lambda x, p: ffn_ref.pvt2_ffn(x, p, 6, 5))
+    _module_case(os.path.join(GOLDEN, "ffn_custom.npz"), lambda x, p: ffn_ref.custom_ffn(x, p, 8, 7))
+
+
+def test_ffn_modules_same_keys_and_init():
+    """ceigm_unet_b200.PVT2FFN / custom_ffn: the reference's state_dict keys and, under the same seed, bit-identical
+    parameters (constructor RNG order + _init_weights: groupmamba.py:55-76, custom_mlp.py:339-361)."""
+    import ceigm_unet_b200 as pkg
+    for name, ctor, seed in (("ffn_pvt2.npz", lambda: pkg.PVT2FFN(16, 64), 11), ("ffn_custom.npz", lambda: pkg.custom_ffn(12, 48), 14)):
+        g = load(os.path.join(GOLDEN, name))
+        torch.manual_seed(seed)
+        m = ctor()
+        sd = m.state_dict()
+        assert list(sd.keys()) == [k[5:] for k in g if k.startswith("init.")]
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), g["init." + k]), k
 
 
 def test_fast_scan_matches_ref():
