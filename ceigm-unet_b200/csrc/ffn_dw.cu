@@ -7,10 +7,24 @@
 // convolutions, a cat and an add. Here the token tensor IS the (B, H, W, C) channels-last image: one stencil kernel with
 // a per-channel-segment kernel size and a fused epilogue covers every forward and data-gradient pass
 //   epi 0: y = acc         1: y = gelu(acc)         2: y = x + acc (residual)         3: y = aux * gelu'(acc)
-// (acc = bias + sum over taps, or acc = x for an identity segment, k = 1; flip = 1 correlates with the flipped kernel = transposed convolution), and one
-// reduction kernel gives the weight / bias gradients of a segment. No transposed copy, no split / cat, GELU and the
-// residual never touch HBM on their own. HBM-bound: 2 (epi 0-2) or 3 (epi 3) tensor passes of s bytes per element.
-// Math in fp32 whatever the I/O type (fp32 / fp16 / bf16); exact-erf GELU as nn.GELU().
+// (acc = bias + sum over taps, or acc = x for an identity segment, k = 1; flip = 1 correlates with the flipped kernel =
+// transposed convolution), and one reduction kernel gives the weight / bias gradients of a segment. No transposed copy,
+// no split / cat, GELU and the residual never touch HBM on their own. HBM-bound: 2 (epi 0-2) or 3 (epi 3) tensor passes
+// of s bytes per element. Math in fp32 whatever the I/O type (fp32 / fp16 / bf16); erf-based GELU as nn.GELU() (gelu_phi).
+//
+// Machine mapping (second version; the first one — runtime dtype, 2 channels x 4 pixels of a row per thread, one image row
+// per CTA row — ran at 0.3 TB/s, slower than the reference composition):
+//   * a thread owns VEC consecutive channels (one 16-byte access in fp32, 8 bytes in 16-bit types; VEC drops to 2 / 1 when
+//     C or a segment boundary is not a multiple of 4) of DW_PY vertically adjacent pixels; a CTA = 16 channel lanes
+//     (16 VEC channels: whole 128 / 256-byte row pieces per pixel) x 16 pixel columns, so the horizontal neighbours of a
+//     thread are its neighbours' own centre columns (L1 hits) and the K - 1 halo rows are shared by the DW_PY outputs;
+//   * a CTA never straddles a segment: channel blocks are enumerated per segment, the kernel size is CTA-uniform and
+//     dispatched to a fully unrolled body; the block's weights are staged once in shared memory as [tap][channel]
+//     (3 x 3: copied on into registers; 5 x 5 / 7 x 7: one broadcast LDS.128 per tap and 4 VEC FMAs);
+//   * dtype, vector width and "has GELU" are template parameters; all loads of an input row are independent and issued
+//     before the FMAs that use them.
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -25,204 +39,464 @@ struct DwnSegs {
   const float* b[kDwnMaxSeg];      // (channels of the segment) fp32 or null
 };
 
-template <int VEC>
-__device__ __forceinline__ void ldv(const void* base, int64_t idx, int dt, float* v) {
-  if (VEC == 1) { v[0] = load1(base, idx, dt); return; }
-  if (dt == SS2D_F32) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + idx));
-    v[0] = t.x; v[1] = t.y;
+constexpr int DW_CL = 16;          // channel lanes of a CTA
+constexpr int DW_PL = 16;          // pixel lanes of a CTA (image columns in the stencil, flattened pixels in the reduction)
+constexpr int DW_PY = 4;           // vertically adjacent outputs per thread (stencil)
+constexpr int DW_THREADS = DW_CL * DW_PL;
+
+struct DwnPlan {
+  int blk0[kDwnMaxSeg + 1];        // first channel block of each segment (blk0[nseg] = number of blocks)
+  int nblk, tiles_w, tiles_h;
+};
+
+// ---- VEC consecutive channels as one access ----
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t raw);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t raw) { return __half22float2(*reinterpret_cast<const __half2*>(&raw)); }
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t raw) {
+  return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));      // bf16 -> fp32 is a shift
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void ldvec(const T* __restrict__ p, float (&v)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (VEC == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+      v[0] = t.x; v[1] = t.y;
+    } else {
+      v[0] = __ldg(reinterpret_cast<const float*>(p));
+    }
   } else {
-    const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint16_t*>(base) + idx));
-    const float2 t = dt == SS2D_F16 ? __half22float2(*reinterpret_cast<const __half2*>(&raw))
-                                    : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
-    v[0] = t.x; v[1] = t.y;
+    if constexpr (VEC == 4) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+      const float2 a = unpack2<T>(t.x), b = unpack2<T>(t.y);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else if constexpr (VEC == 2) {
+      const float2 a = unpack2<T>(__ldg(reinterpret_cast<const uint32_t*>(p)));
+      v[0] = a.x; v[1] = a.y;
+    } else {
+      const uint32_t raw = __ldg(reinterpret_cast<const uint16_t*>(p));
+      v[0] = unpack2<T>(raw).x;
+    }
   }
 }
-template <int VEC>
-__device__ __forceinline__ void stv(void* base, int64_t idx, int dt, const float* v) {
-  if (VEC == 1) { store1(base, idx, dt, v[0]); return; }
-  if (dt == SS2D_F32) {
-    *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + idx) = make_float2(v[0], v[1]);
-  } else if (dt == SS2D_F16) {
-    *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(base) + idx) = __floats2half2_rn(v[0], v[1]);
+template <typename T, int VEC>
+__device__ __forceinline__ void stvec(T* __restrict__ p, const float (&v)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    else *reinterpret_cast<float*>(p) = v[0];
   } else {
-    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = __floats2bfloat162_rn(v[0], v[1]);
+    if constexpr (VEC == 4) *reinterpret_cast<uint2*>(p) = make_uint2(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]));
+    else if constexpr (VEC == 2) *reinterpret_cast<uint32_t*>(p) = pack2<T>(v[0], v[1]);
+    else *reinterpret_cast<uint16_t*>(p) = static_cast<uint16_t>(pack2<T>(v[0], 0.f) & 0xffffu);
   }
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  return 0.5f * (1.f + erff(x * 0.70710678f)) + x * 0.3989422804f * __expf(-0.5f * x * x);
+// VEC channels as loaded (unconverted): what a software-pipelined loop keeps in flight
+template <typename T, int VEC>
+struct RawVec {
+  static constexpr int NW = (sizeof(T) * VEC + 3) / 4;
+  uint32_t r[NW];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) r[i] = 0u;
+  }
+  __device__ __forceinline__ void load(const T* __restrict__ p) {
+    if constexpr (sizeof(T) * VEC == 16) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+      r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else if constexpr (sizeof(T) * VEC == 8) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+      r[0] = t.x; r[1] = t.y;
+    } else if constexpr (sizeof(T) * VEC == 4) {
+      r[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    } else {
+      r[0] = __ldg(reinterpret_cast<const uint16_t*>(p));
+    }
+  }
+  __device__ __forceinline__ void get(float (&v)[VEC]) const {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) v[i] = __uint_as_float(r[i]);
+    } else if constexpr (VEC == 1) {
+      v[0] = unpack2<T>(r[0]).x;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC / 2; ++i) {
+        const float2 t = unpack2<T>(r[i]);
+        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+      }
+    }
+  }
+};
+
+// nn.GELU() = x Phi(x), Phi from erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z = |x| / sqrt(2)
+// (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 on erf — fp32 rounding level; no cancellation in the negative tail, where
+// 1 + erff(z) loses every digit). One MUFU.RCP + one MUFU.EX2 + 10 FMA-pipe instructions; erff() costs about three times that,
+// and exp(-z^2) = exp(-x^2 / 2) is also the density term of the derivative.
+template <bool GRAD>
+__device__ __forceinline__ float gelu_phi(float x, float aux) {
+  const float az = fabsf(x) * 0.70710678f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+  const float e = ex2f(-az * az * kLog2e);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float hc = 0.5f * t * poly * e;                       // Phi(-|x|)
+  const float phi = x < 0.f ? hc : 1.f - hc;
+  if (GRAD) return aux * fmaf(x * 0.3989422804f, e, phi);      // aux * d gelu / dx
+  return x * phi;
 }
 
-constexpr int kDwnPX = 4;      // consecutive pixels of an image row per thread: the K x K weights and the overlapping columns stay in registers
-
-// acc[px][v] += sum over taps for pixels w0 .. w0 + PX - 1 of image row (b, h), channels c .. c + VEC - 1
-template <int VEC, int K>
-__device__ __forceinline__ void dwn_taps(const void* __restrict__ x, const float* __restrict__ wp, int flip, int b, int h, int w0,
-                                         int c, int H, int W, int C, int dt, float (*acc)[VEC]) {
-  constexpr int P = K / 2;
-  float wr[VEC][K * K];
+// acc[py][v] += sum over taps for the DW_PY pixels (h0 + py, w), channels c .. c + VEC - 1.
+// xb: this thread's pointer to (row h0 - P, column w - P) of its image (dereferenced only where the image exists); every load
+// address is xb + (i * WC + j * C) with compile-time i, j and kernel-uniform WC = W * C, C — one 32-bit uniform offset per
+// load, no per-load 64-bit arithmetic. wts: K == 3: the segment's weights in global memory (read straight into registers:
+// no shared-memory hop, no barrier between a CTA's start and its loads); K > 3: this thread's column of the CTA's
+// [tap][CB] tile in shared memory (flip already applied).
+template <typename T, int VEC, int K>
+__device__ __forceinline__ void dwn_taps(const T* __restrict__ xb, const float* __restrict__ wts, int flip, int h0, int w, int H,
+                                         int W, int WC, int C, float (&acc)[DW_PY][VEC]) {
+  constexpr int P = K / 2, CB = DW_CL * VEC;
+  constexpr int NR = K == 3 ? 9 : 1;
+  float wr[NR][VEC];
+  if constexpr (K == 3) {
+    float wf[VEC * 9];                                           // [channel][tap], as stored
+    if (VEC == 4 && (reinterpret_cast<uintptr_t>(wts) & 15) == 0) {
 #pragma unroll
-  for (int v = 0; v < VEC; ++v)
+      for (int q = 0; q < (VEC * 9) / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wts) + q);
+        wf[4 * q] = t.x; wf[4 * q + 1] = t.y; wf[4 * q + 2] = t.z; wf[4 * q + 3] = t.w;
+      }
+    } else {
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) wr[v][t] = __ldg(wp + v * K * K + (flip ? K * K - 1 - t : t));
+      for (int q = 0; q < VEC * 9; ++q) wf[q] = __ldg(wts + q);
+    }
 #pragma unroll
-  for (int i = 0; i < K; ++i) {
-    const int hh = h + i - P;
-    if (hh < 0 || hh >= H) continue;
-    const int64_t rowoff = ((int64_t)(b * H + hh) * W) * C + c;
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int jj = 0; jj < kDwnPX + K - 1; ++jj) {
-      const int ww = w0 + jj - P;
-      float xv[VEC];
+      for (int v = 0; v < VEC; ++v) wr[t][v] = flip ? wf[v * 9 + 8 - t] : wf[v * 9 + t];
+  }
+  bool colok[K];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) xv[v] = 0.f;
-      if (ww >= 0 && ww < W) ldv<VEC>(x, rowoff + (int64_t)ww * C, dt, xv);
+  for (int j = 0; j < K; ++j) colok[j] = w + j - P >= 0 && w + j - P < W;
 #pragma unroll
-      for (int px = 0; px < kDwnPX; ++px) {
-        const int j = jj - px;
-        if (j >= 0 && j < K) {
+  for (int i = 0; i < DW_PY + K - 1; ++i) {
+    const int r = h0 + i - P;
+    if (r < 0 || r >= H) continue;                               // CTA-uniform
+    float xv[K][VEC];
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[px][v] = fmaf(wr[v][i * K + j], xv[v], acc[px][v]);
+    for (int j = 0; j < K; ++j) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) xv[j][v] = 0.f;
+      if (colok[j]) ldvec<T, VEC>(xb + (i * WC + j * C), xv[j]);
+    }
+#pragma unroll
+    for (int py = 0; py < DW_PY; ++py) {
+      const int ki = i - py;
+      if (ki < 0 || ki >= K) continue;                           // resolved at compile time
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if constexpr (K == 3) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[py][v] = fmaf(wr[ki * 3 + j][v], xv[j][v], acc[py][v]);
+        } else {
+          float wv[VEC];
+          if constexpr (VEC == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(wts + (ki * K + j) * CB);
+            wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+          } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) wv[v] = wts[(ki * K + j) * CB + v];
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[py][v] = fmaf(wv[v], xv[j][v], acc[py][v]);
         }
       }
     }
   }
 }
 
-// grid: x = (pixel quads of a row) x (channel vectors), channel vectors fastest (coalesced); y = image row (b, h)
-template <int VEC>
-__global__ void __launch_bounds__(256)
-dwnhwc_stencil_kernel(const void* __restrict__ x, const void* __restrict__ aux, void* __restrict__ y, const DwnSegs sg, int flip,
-                      int epi, int H, int W, int C, int dt) {
-  const unsigned CV = C / VEC;
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned wq = t / CV, cv = t - wq * CV;
-  const int w0 = (int)wq * kDwnPX;
-  if (w0 >= W) return;
-  const int h = blockIdx.y % H, b = blockIdx.y / H;
-  const int c = (int)cv * VEC;
-  // segment of this thread's channels (selects, not a dynamic index into the parameter block)
-  int k = sg.k[0], cb = 0;
+// grid: x = (image, row tile, column tile, channel block), channel block (segment-major) fastest: CTAs that run at the same
+// time consume whole pixel rows of C channels, not 128-byte slices 2 C bytes apart. 256 threads = 16 columns x 16 channel lanes.
+template <typename T, int VEC, bool GELU>
+__global__ void __launch_bounds__(DW_THREADS)
+dwnhwc_stencil_kernel(const T* __restrict__ x, const T* __restrict__ aux, T* __restrict__ y, const DwnSegs sg, const DwnPlan pl,
+                      int flip, int epi, int H, int W, int C) {
+  constexpr int CB = DW_CL * VEC;
+  __shared__ __align__(16) float s_w[49 * CB];
+  const int chl = threadIdx.x % DW_CL, pxl = threadIdx.x / DW_CL;
+  // segment and channel range of this CTA (selects, not a dynamic index into the parameter block)
+  const int by = blockIdx.x % pl.nblk;
+  int k = sg.k[0], cb = 0, ce = sg.cbeg[1], b0 = 0;
   const float* ws = sg.w[0];
   const float* bs = sg.b[0];
 #pragma unroll
   for (int i = 1; i < kDwnMaxSeg; ++i)
-    if (i < sg.nseg && c >= sg.cbeg[i]) { k = sg.k[i]; cb = sg.cbeg[i]; ws = sg.w[i]; bs = sg.b[i]; }
-  const int cl = c - cb;
-  float acc[kDwnPX][VEC];
+    if (i < sg.nseg && by >= pl.blk0[i]) { k = sg.k[i]; cb = sg.cbeg[i]; ce = sg.cbeg[i + 1]; b0 = pl.blk0[i]; ws = sg.w[i]; bs = sg.b[i]; }
+  const int cl0 = (by - b0) * CB;                    // first channel of the block inside its segment
+  const int nvalid = min(CB, ce - cb - cl0);         // channels of the block that exist
+  if (k > 3) {                                       // CTA-uniform: 5 x 5 / 7 x 7 weights go through shared memory
+    const int kk = k * k;
+    const float* wsrc = ws + (int64_t)cl0 * kk;
+    for (int idx = threadIdx.x; idx < nvalid * kk; idx += DW_THREADS) {
+      const int cc = idx / kk, t = idx - cc * kk;
+      s_w[(flip ? kk - 1 - t : t) * CB + cc] = __ldg(wsrc + idx);
+    }
+    __syncthreads();
+  }
+  unsigned bx = blockIdx.x / pl.nblk;
+  const int tw = bx % pl.tiles_w; bx /= pl.tiles_w;
+  const int th = bx % pl.tiles_h;
+  const int b = bx / pl.tiles_h;
+  const int w = tw * DW_PL + pxl, h0 = th * DW_PY;
+  const int cl = cl0 + chl * VEC;                    // first channel of this thread inside its segment
+  if (w >= W || chl * VEC >= nvalid) return;
+  const int WC = W * C;
+  const int64_t o00 = ((int64_t)(b * H + h0) * W + w) * C + cb + cl;     // element (b, h0, w, c)
+
+  float acc[DW_PY][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     const float bv = (k > 1 && bs) ? __ldg(bs + cl + v) : 0.f;
 #pragma unroll
-    for (int px = 0; px < kDwnPX; ++px) acc[px][v] = bv;
+    for (int py = 0; py < DW_PY; ++py) acc[py][v] = bv;
   }
-  const float* wp = ws + (int64_t)cl * k * k;
-  if (k == 3) dwn_taps<VEC, 3>(x, wp, flip, b, h, w0, c, H, W, C, dt, acc);
-  else if (k == 5) dwn_taps<VEC, 5>(x, wp, flip, b, h, w0, c, H, W, C, dt, acc);
-  else if (k == 7) dwn_taps<VEC, 7>(x, wp, flip, b, h, w0, c, H, W, C, dt, acc);
-  const int64_t o0 = ((int64_t)blockIdx.y * W + w0) * C + c;
+  if (k == 3) dwn_taps<T, VEC, 3>(x + o00 - (WC + C), ws + (int64_t)cl * 9, flip, h0, w, H, W, WC, C, acc);
+  else if (k == 5) dwn_taps<T, VEC, 5>(x + o00 - 2 * (WC + C), s_w + chl * VEC, flip, h0, w, H, W, WC, C, acc);
+  else if (k == 7) dwn_taps<T, VEC, 7>(x + o00 - 3 * (WC + C), s_w + chl * VEC, flip, h0, w, H, W, WC, C, acc);
+
+  const T* xo = x + o00;
+  const T* ao = aux + o00;
+  T* yo = y + o00;
 #pragma unroll
-  for (int px = 0; px < kDwnPX; ++px) {
-    if (w0 + px >= W) break;
-    const int64_t o = o0 + (int64_t)px * C;
+  for (int py = 0; py < DW_PY; ++py) {
+    if (h0 + py >= H) break;
     float out[VEC];
-    if (k == 1) {                  // identity segment: acc = x
-      ldv<VEC>(x, o, dt, out);
+    if (k == 1) ldvec<T, VEC>(xo + py * WC, acc[py]);       // identity segment: acc = x
+    if constexpr (GELU) {
+      if (epi == 1) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[px][v] = out[v];
-    }
-    if (epi == 0) {
+        for (int v = 0; v < VEC; ++v) out[v] = gelu_phi<false>(acc[py][v], 0.f);
+      } else {                                        // epi 3
+        float av[VEC];
+        ldvec<T, VEC>(ao + py * WC, av);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) out[v] = acc[px][v];
-    } else if (epi == 1) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) out[v] = gelu_erf(acc[px][v]);
-    } else if (epi == 2) {
-      float xc[VEC];
-      ldv<VEC>(x, o, dt, xc);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) out[v] = xc[v] + acc[px][v];
+        for (int v = 0; v < VEC; ++v) out[v] = gelu_phi<true>(acc[py][v], av[v]);
+      }
     } else {
-      float av[VEC];
-      ldv<VEC>(aux, o, dt, av);
+      if (epi == 2) {
+        float xc[VEC];
+        ldvec<T, VEC>(xo + py * WC, xc);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) out[v] = av[v] * gelu_erf_grad(acc[px][v]);
+        for (int v = 0; v < VEC; ++v) out[v] = xc[v] + acc[py][v];
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) out[v] = acc[py][v];
+      }
     }
-    stv<VEC>(y, o, dt, out);
+    stvec<T, VEC>(yo + py * WC, out);
   }
+}
+
+template <typename T, int VEC>
+static cudaError_t stencil_launch_t(const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B, int H,
+                                    int W, int C, cudaStream_t stream) {
+  constexpr int CB = DW_CL * VEC;
+  DwnPlan pl;
+  int nblk = 0;
+  for (int s = 0; s < kDwnMaxSeg + 1; ++s) pl.blk0[s] = 0;
+  for (int s = 0; s < sg.nseg; ++s) {
+    pl.blk0[s] = nblk;
+    nblk += (sg.cbeg[s + 1] - sg.cbeg[s] + CB - 1) / CB;
+  }
+  for (int s = sg.nseg; s < kDwnMaxSeg + 1; ++s) pl.blk0[s] = nblk;
+  pl.tiles_w = (W + DW_PL - 1) / DW_PL;
+  pl.tiles_h = (H + DW_PY - 1) / DW_PY;
+  pl.nblk = nblk;
+  const int64_t ctas = (int64_t)B * pl.tiles_w * pl.tiles_h * nblk;
+  if (ctas >= (1ll << 31) || (int64_t)W * C * (DW_PY + 8) >= (1ll << 31)) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)ctas);
+  const T* xs = static_cast<const T*>(x);
+  const T* as = static_cast<const T*>(aux);
+  T* ys = static_cast<T*>(y);
+  if (epi == 1 || epi == 3) dwnhwc_stencil_kernel<T, VEC, true><<<grid, DW_THREADS, 0, stream>>>(xs, as, ys, sg, pl, flip, epi, H, W, C);
+  else dwnhwc_stencil_kernel<T, VEC, false><<<grid, DW_THREADS, 0, stream>>>(xs, as, ys, sg, pl, flip, epi, H, W, C);
+  return cudaGetLastError();
+}
+
+static int dwn_vec(int C, const int* bounds, int nb, size_t esz, const void* p0, const void* p1, const void* p2) {
+  int vec = 4;
+  auto fits = [&](int v) {
+    if (C % v) return false;
+    for (int i = 0; i < nb; ++i) if (bounds[i] % v) return false;
+    const uintptr_t m = (uintptr_t)v * esz - 1;
+    return !((reinterpret_cast<uintptr_t>(p0) & m) || (reinterpret_cast<uintptr_t>(p1) & m) || (reinterpret_cast<uintptr_t>(p2) & m));
+  };
+  while (vec > 1 && !fits(vec)) vec >>= 1;
+  return vec;
+}
+
+template <typename T>
+static cudaError_t stencil_launch_v(int vec, const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B,
+                                    int H, int W, int C, cudaStream_t stream) {
+  if (vec == 4) return stencil_launch_t<T, 4>(x, aux, y, sg, flip, epi, B, H, W, C, stream);
+  if (vec == 2) return stencil_launch_t<T, 2>(x, aux, y, sg, flip, epi, B, H, W, C, stream);
+  return stencil_launch_t<T, 1>(x, aux, y, sg, flip, epi, B, H, W, C, stream);
 }
 
 cudaError_t dwnhwc_stencil_launch(const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B, int H,
                                   int W, int C, int dt, cudaStream_t stream) {
-  bool even = (C & 1) == 0;
-  for (int s = 0; s <= sg.nseg; ++s) even = even && (sg.cbeg[s] & 1) == 0;
-  const int vec = even ? 2 : 1;
-  const int64_t per_row = (int64_t)((W + kDwnPX - 1) / kDwnPX) * (C / vec);
-  const int64_t rows = (int64_t)B * H;
-  if (per_row >= (1ll << 31) || rows > 65535 * 32768ll) return cudaErrorInvalidValue;
-  // image rows on grid.y (<= 65535): very tall batches are walked in slices of rows
-  for (int64_t r0 = 0; r0 < rows; r0 += 65535 - 65535 % H) {
-    const int64_t nr = rows - r0 < 65535 - 65535 % H ? rows - r0 : 65535 - 65535 % H;
-    dim3 grid((unsigned)((per_row + 255) / 256), (unsigned)nr);
-    const size_t eb = (size_t)(dt == SS2D_F32 ? 4 : 2) * (size_t)r0 * W * C;
-    const char* xs = static_cast<const char*>(x) + eb;
-    const char* as = aux ? static_cast<const char*>(aux) + eb : nullptr;
-    char* ys = static_cast<char*>(y) + eb;
-    if (vec == 2) dwnhwc_stencil_kernel<2><<<grid, 256, 0, stream>>>(xs, as, ys, sg, flip, epi, H, W, C, dt);
-    else dwnhwc_stencil_kernel<1><<<grid, 256, 0, stream>>>(xs, as, ys, sg, flip, epi, H, W, C, dt);
-  }
-  return cudaGetLastError();
+  const int vec = dwn_vec(C, sg.cbeg, sg.nseg + 1, dt == SS2D_F32 ? 4 : 2, x, aux, y);
+  if (dt == SS2D_F32) return stencil_launch_v<float>(vec, x, aux, y, sg, flip, epi, B, H, W, C, stream);
+  if (dt == SS2D_F16) return stencil_launch_v<__half>(vec, x, aux, y, sg, flip, epi, B, H, W, C, stream);
+  return stencil_launch_v<__nv_bfloat16>(vec, x, aux, y, sg, flip, epi, B, H, W, C, stream);
 }
 
 // ---- weight / bias gradient of one segment: dW[c][i][j] = sum_(b,h,w) g[b,h,w,c] x[b,h+i-P,w+j-P,c], db[c] = sum g ----
-// CTA = 32 consecutive channels x 8 pixel lanes over one slab of pixels; K*K + 1 sums per thread in registers, folded
-// over the pixel lanes through shared memory; per-slab partials, fixed-order finalize (deterministic).
-template <int K>
-__global__ void __launch_bounds__(256)
-dwnhwc_wgrad_kernel(const void* __restrict__ x, const void* __restrict__ g, float* __restrict__ part, int c0, int nc, int B, int H,
-                    int W, int C, int dt, int slabs) {
-  constexpr int T = K * K + 1, P = K / 2;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int cl = blockIdx.x * 32 + tx;
+// CTA = 16 channel lanes (VEC channels each) x 16 pixel lanes; a pixel lane WALKS image rows left to right with the K x K
+// neighbourhood of x in a register window: one new column (K loads) and one g per pixel instead of K * K + 1 loads with
+// their address and border arithmetic (the first version: 290 instructions per pixel for 40 FMAs). The walk is unrolled
+// K-fold so that the window's column slots are compile-time (slot = column mod K), with no branch inside (borders and the
+// row's tail are load predicates), so the loads of the next pixels are issued ahead of the current pixel's FMAs.
+// The 16 lanes of a CTA walk 16 adjacent image rows in lockstep: the rows above / below are the neighbours' centre rows
+// (L1 hits). K * K + 1 sums per channel in registers, folded over the pixel lanes by one shuffle and a shared-memory
+// pass; per-slab partials, fixed-order finalize (deterministic).
+template <typename T, int K>
+constexpr int wgrad_ctas_per_sm() { return (K == 3 && sizeof(T) == 2) ? 2 : 1; }     // register budget: 128 / 255 per thread
+
+template <typename T, int VEC, int K>
+__global__ void __launch_bounds__(DW_THREADS, wgrad_ctas_per_sm<T, K>())
+dwnhwc_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ g, float* __restrict__ part, int c0, int nc, int rows, int H,
+                    int W, int C, int rpl) {
+  constexpr int NT = K * K + 1, P = K / 2, CB = DW_CL * VEC, TT = 10;
+  const int chl = threadIdx.x % DW_CL, pxl = threadIdx.x / DW_CL;
+  const int cl = blockIdx.x * CB + chl * VEC;
   const bool cok = cl < nc;
   const int c = c0 + (cok ? cl : 0);
-  const int64_t total = (int64_t)B * H * W;
-  const int64_t per = (total + slabs - 1) / slabs;
-  const int64_t p0 = (int64_t)blockIdx.y * per, p1 = p0 + per < total ? p0 + per : total;
-  float acc[T];
+  float acc[NT][VEC];
 #pragma unroll
-  for (int t = 0; t < T; ++t) acc[t] = 0.f;
-  for (int64_t p = p0 + ty; p < p1; p += 8) {
-    const unsigned pu = (unsigned)p;                         // B * H * W < 2^31 (checked by the host)
-    const unsigned pr = pu / (unsigned)W;
-    const int w = (int)(pu - pr * (unsigned)W), h = (int)(pr % (unsigned)H);
-    const float gv = load1(g, p * C + c, dt);
-    acc[K * K] += gv;
+  for (int t = 0; t < NT; ++t)
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      const int hh = h + i - P;
-      if (hh < 0 || hh >= H) continue;
+    for (int v = 0; v < VEC; ++v) acc[t][v] = 0.f;
+  if (cok) {
+    for (int k = 0; k < rpl; ++k) {
+      const int row = (blockIdx.y * rpl + k) * DW_PL + pxl;      // flattened (image, h)
+      if (row >= rows) break;
+      const int h = row % H;
+      const T* grow = g + (int64_t)row * W * C + c;
+      const T* xrow = x + (int64_t)row * W * C + c;
+      bool rv[K];
 #pragma unroll
-      for (int j = 0; j < K; ++j) {
-        const int ww = w + j - P;
-        if (ww < 0 || ww >= W) continue;
-        acc[i * K + j] = fmaf(gv, load1(x, (p + (int64_t)(i - P) * W + (j - P)) * C + c, dt), acc[i * K + j]);
+      for (int i = 0; i < K; ++i) rv[i] = h + i - P >= 0 && h + i - P < H;
+      float win[K][K][VEC];                                      // [kernel row][column slot], slot = column mod K
+#pragma unroll
+      for (int i = 0; i < K; ++i)
+#pragma unroll
+        for (int sl = 0; sl < K; ++sl)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) win[i][sl][v] = 0.f;
+      // One "body" = K consecutive pixels: per pixel one g and the new window column (K loads), kept RAW (unconverted) so
+      // that the next body's loads are in flight while the current body is multiplied. The walk starts one body before
+      // the row (g masked), which fills the window's first columns through the same path.
+      struct Step { RawVec<T, VEC> g, xn[K]; };
+      auto load_step = [&](int w, Step& st) {
+        const int cn = w + P;
+        st.g.zero();
+        if (w >= 0 && w < W) st.g.load(grow + (int64_t)w * C);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+          st.xn[i].zero();
+          if (rv[i] && cn >= 0 && cn < W) st.xn[i].load(xrow + ((int64_t)(i - P) * W + cn) * C);
+        }
+      };
+      auto compute_step = [&](const Step& st, auto S) {
+        constexpr int s = decltype(S)::value;
+        float gv[VEC];
+        st.g.get(gv);
+#pragma unroll
+        for (int i = 0; i < K; ++i) st.xn[i].get(win[i][(s + K - 1) % K]);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[K * K][v] += gv[v];
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[i * K + j][v] = fmaf(gv[v], win[i][(s + j) % K][v], acc[i * K + j][v]);
+      };
+      if constexpr (K == 3) {                                    // two bodies of three pixels in registers: ping-pong
+        Step ba[3], bb[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) load_step(-3 + s, ba[s]);
+        for (int w0 = -3; w0 < W; w0 += 6) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) load_step(w0 + 3 + s, bb[s]);
+          compute_step(ba[0], std::integral_constant<int, 0>{});
+          compute_step(ba[1], std::integral_constant<int, 1>{});
+          compute_step(ba[2], std::integral_constant<int, 2>{});
+#pragma unroll
+          for (int s = 0; s < 3; ++s) load_step(w0 + 6 + s, ba[s]);
+          compute_step(bb[0], std::integral_constant<int, 0>{});
+          compute_step(bb[1], std::integral_constant<int, 1>{});
+          compute_step(bb[2], std::integral_constant<int, 2>{});
+        }
+      } else {                                                   // the wider windows leave registers for one pixel's loads
+        for (int w0 = -K; w0 < W; w0 += K) {
+          Step st;
+          load_step(w0 + 0, st); compute_step(st, std::integral_constant<int, 0>{});
+          load_step(w0 + 1, st); compute_step(st, std::integral_constant<int, 1>{});
+          load_step(w0 + 2, st); compute_step(st, std::integral_constant<int, 2>{});
+          load_step(w0 + 3, st); compute_step(st, std::integral_constant<int, 3>{});
+          load_step(w0 + 4, st); compute_step(st, std::integral_constant<int, 4>{});
+          if constexpr (K == 7) {
+            load_step(w0 + 5, st); compute_step(st, std::integral_constant<int, 5>{});
+            load_step(w0 + 6, st); compute_step(st, std::integral_constant<int, 6>{});
+          }
+        }
       }
     }
   }
-  __shared__ float s_red[8][33];
-  float* dst = part + ((int64_t)blockIdx.y * nc + cl) * T;
+  // fold the 16 pixel lanes: lanes l and l ^ 16 of a warp are two pixel lanes of one channel lane
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    s_red[ty][tx] = acc[t];
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[t][v] += __shfl_xor_sync(0xffffffffu, acc[t][v], 16);
+  __shared__ float s_red[DW_THREADS / 32][TT][CB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t0 = 0; t0 < NT; t0 += TT) {
+    if (lane < 16) {
+#pragma unroll
+      for (int tt = 0; tt < TT; ++tt)
+        if (t0 + tt < NT) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s_red[warp][tt][chl * VEC + v] = acc[t0 + tt][v];
+        }
+    }
     __syncthreads();
-    if (ty == 0 && cok) {
-      float v = 0.f;
+    for (int idx = threadIdx.x; idx < TT * CB; idx += DW_THREADS) {
+      const int tt = idx / CB, cc = idx - tt * CB;
+      const int ch = blockIdx.x * CB + cc;
+      if (t0 + tt < NT && ch < nc) {
+        float s = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v += s_red[r][tx];
-      dst[t] = v;
+        for (int wi = 0; wi < DW_THREADS / 32; ++wi) s += s_red[wi][tt][cc];
+        part[((int64_t)blockIdx.y * nc + ch) * NT + t0 + tt] = s;
+      }
     }
     __syncthreads();
   }
@@ -239,23 +513,66 @@ __global__ void dwnhwc_wgrad_finalize_kernel(const float* __restrict__ part, flo
   else if (db) db[cl] = v;
 }
 
+// Row geometry of the reduction: 16-row groups (one image row per pixel lane), `rpl` groups per CTA, `slabs` CTAs along the
+// rows. The workspace query returns the upper bound (one group per CTA); the launch picks rpl against wave quantisation:
+// the smallest (waves x rpl) for the CTA slots of the instantiation, ties to the larger rpl (fewer partials).
+static int64_t dwn_row_groups(int B, int H) { return ((int64_t)B * H + DW_PL - 1) / DW_PL; }
 int dwnhwc_wgrad_slabs(int B, int H, int W, int nc) {
-  const int64_t total = (int64_t)B * H * W;
-  const int cblocks = (nc + 31) / 32;
-  int64_t slabs = ((int64_t)sm_count_current_device() * 8 + cblocks - 1) / cblocks;
-  const int64_t cap = total / 64 > 1 ? total / 64 : 1;
-  if (slabs > cap) slabs = cap;
-  if (slabs > 65535) slabs = 65535;
-  return (int)(slabs < 1 ? 1 : slabs);
+  (void)W; (void)nc;
+  const int64_t groups = dwn_row_groups(B, H);
+  return (int)(groups < 65535 ? groups : 65535);
+}
+static int dwn_pick_rpl(int64_t groups, int cblocks, int ctas_per_sm) {
+  const int64_t slots = (int64_t)sm_count_current_device() * ctas_per_sm;
+  const int rmin = (int)((groups + 65534) / 65535);
+  int best = rmin;
+  int64_t best_cost = -1;
+  for (int r = rmin; r < rmin + 8; ++r) {
+    const int64_t ctas = ((groups + r - 1) / r) * cblocks;
+    const int64_t cost = ((ctas + slots - 1) / slots) * r;
+    if (best_cost < 0 || cost <= best_cost) { best = r; best_cost = cost; }
+  }
+  return best;
+}
+
+template <typename T, int VEC, int K>
+static int wgrad_launch_k(const void* x, const void* g, float* part, int c0, int nc, int B, int H, int W, int C, cudaStream_t stream) {
+  constexpr int CB = DW_CL * VEC;
+  const int cblocks = (nc + CB - 1) / CB;
+  const int64_t groups = dwn_row_groups(B, H);
+  const int rpl = dwn_pick_rpl(groups, cblocks, wgrad_ctas_per_sm<T, K>());
+  const int slabs = (int)((groups + rpl - 1) / rpl);
+  dim3 grid(cblocks, slabs);
+  dwnhwc_wgrad_kernel<T, VEC, K><<<grid, DW_THREADS, 0, stream>>>(static_cast<const T*>(x), static_cast<const T*>(g), part, c0, nc,
+                                                                  B * H, H, W, C, rpl);
+  return slabs;
+}
+
+template <typename T>
+static int wgrad_launch_t(int vec, int K, const void* x, const void* g, float* part, int c0, int nc, int B, int H, int W, int C,
+                          cudaStream_t stream) {
+  // registers: (K * K + 1) * VEC sums + the K * K * VEC window per thread -> 4 channels for 3 x 3, 2 for 5 x 5 / 7 x 7
+  if (K == 3) {
+    if (vec == 4) return wgrad_launch_k<T, 4, 3>(x, g, part, c0, nc, B, H, W, C, stream);
+    if (vec == 2) return wgrad_launch_k<T, 2, 3>(x, g, part, c0, nc, B, H, W, C, stream);
+    return wgrad_launch_k<T, 1, 3>(x, g, part, c0, nc, B, H, W, C, stream);
+  }
+  if (K == 5) {
+    if (vec >= 2) return wgrad_launch_k<T, 2, 5>(x, g, part, c0, nc, B, H, W, C, stream);
+    return wgrad_launch_k<T, 1, 5>(x, g, part, c0, nc, B, H, W, C, stream);
+  }
+  if (vec >= 2) return wgrad_launch_k<T, 2, 7>(x, g, part, c0, nc, B, H, W, C, stream);
+  return wgrad_launch_k<T, 1, 7>(x, g, part, c0, nc, B, H, W, C, stream);
 }
 
 cudaError_t dwnhwc_wgrad_launch(const void* x, const void* g, int c0, int nc, int K, float* dW, float* db, int B, int H, int W,
                                 int C, int dt, float* part, cudaStream_t stream) {
-  const int slabs = dwnhwc_wgrad_slabs(B, H, W, nc);
-  dim3 grid((nc + 31) / 32, slabs);
-  if (K == 3) dwnhwc_wgrad_kernel<3><<<grid, 256, 0, stream>>>(x, g, part, c0, nc, B, H, W, C, dt, slabs);
-  else if (K == 5) dwnhwc_wgrad_kernel<5><<<grid, 256, 0, stream>>>(x, g, part, c0, nc, B, H, W, C, dt, slabs);
-  else dwnhwc_wgrad_kernel<7><<<grid, 256, 0, stream>>>(x, g, part, c0, nc, B, H, W, C, dt, slabs);
+  const int bounds[2] = {c0, c0 + nc};
+  const int vec = dwn_vec(C, bounds, 2, dt == SS2D_F32 ? 4 : 2, x, g, nullptr);
+  int slabs;
+  if (dt == SS2D_F32) slabs = wgrad_launch_t<float>(vec, K, x, g, part, c0, nc, B, H, W, C, stream);
+  else if (dt == SS2D_F16) slabs = wgrad_launch_t<__half>(vec, K, x, g, part, c0, nc, B, H, W, C, stream);
+  else slabs = wgrad_launch_t<__nv_bfloat16>(vec, K, x, g, part, c0, nc, B, H, W, C, stream);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int T = K * K + 1;
