@@ -287,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_extras:
         line["other_workloads"] = other_workloads(core, device, peak, exclude=args.workload)
         line["projections"] = projection_workloads(device, peak)
+        line["ffn_depthwise"] = ffn_workloads(device, peak)
     if not args.no_model:
         # every rank takes part (batch-sharded data parallel, gradient all-reduce on NCCL); rank 0 reports
         line["model"] = model_workloads(device, rank, world)
@@ -418,6 +419,74 @@ def projection_workloads(device, peak):
         out.append({"error": repr(e)[:300]})
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    return out
+
+
+def ffn_workloads(device, peak):
+    """The depthwise stack of the GroupMamba FFNs (csrc/ffn_dw.cu) at the stage-1 encoder shape of a 224^2
+    batch-24 step (hidden 512 @ 56 x 56, bf16 — the autocast training configuration): the module's forward + backward
+    between fc1 and fc2 (ceigm_unet_b200.functional.ffn_depthwise) next to the reference composition (transpose to NCHW,
+    F.conv2d depthwise, GELU, [split, three depthwise convs, cat, residual], transpose back: groupmamba.py:446-455, 76-78,
+    custom_mlp.py:323-336, 363-366); CUDA-graph replay, L2 flushed between replays. Algorithmic bytes per element of the
+    (B, L, C) tensor (s = 2): PVT2FFN forward 2 s, backward 3 s (GELU' on the recomputed pre-activation) + 2 s (transposed conv) + 2 s
+    (weight gradient) = 9 s; custom_ffn adds the multi-scale pass forward (2 s), its transposed pass (2 s) and three 1/8-width
+    reductions (0.75 s) = 13.75 s."""
+    import torch.nn.functional as F
+    import ceigm_unet_b200 as pkg
+    from ceigm_unet_b200 import functional as Fn
+    Bn, H, W, C = 24, 56, 56, 512
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out = []
+    try:
+        for name, ctor in (("PVT2FFN", pkg.PVT2FFN), ("custom_ffn", pkg.custom_ffn)):
+            torch.manual_seed(0)
+            mod = ctor(C // 8, C).to(device)
+            h = torch.randn(Bn, H * W, C, device=device).to(torch.bfloat16).requires_grad_(True)
+            dy = torch.randn(Bn, H * W, C, device=device).to(torch.bfloat16)
+            conv3 = mod.dwconv.dwconv
+            ms_convs = (mod.custom.dwconv_3x3, mod.custom.dwconv_5x5, mod.custom.dwconv_7x7) if name == "custom_ffn" else None
+            params = [p for m in ((conv3,) + (ms_convs or ())) for p in m.parameters()]
+
+            def ours():
+                y = Fn.ffn_depthwise(h, (H, W), conv3, ms_convs)
+                return torch.autograd.grad(y, [h] + params, dy)
+
+            def lib():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    img = h.transpose(1, 2).reshape(Bn, C, H, W)
+                    y = F.gelu(conv3(img))
+                    if ms_convs is not None:
+                        gc = ms_convs[0].weight.shape[0]
+                        a, b3, b5, b7 = torch.split(y, (C - 3 * gc, gc, gc, gc), dim=1)
+                        y = y + torch.cat((a, ms_convs[0](b3), ms_convs[1](b5), ms_convs[2](b7)), dim=1)
+                    y = y.flatten(2).transpose(1, 2)
+                return torch.autograd.grad(y, [h] + params, dy.to(y.dtype))
+
+            def timed(fn, iters=10):
+                g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+                with torch.cuda.stream(st):
+                    fn()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g, stream=st):
+                        fn()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(iters):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                return statistics.median(ts)
+
+            ms, ms_lib = timed(ours), timed(lib)
+            passes = 9.0 if name == "PVT2FFN" else 13.75      # tensor passes of one forward + backward (docstring)
+            nbytes = passes * 2 * h.numel()
+            out.append({"op": f"{name} depthwise stack fwd+bwd (hidden {C} @ {H}x{W}, batch {Bn})", "kernel": "dwnhwc_stencil_kernel / dwnhwc_wgrad_kernel",
+                        "dtype": "bf16", "ms": round(ms, 4), "alg_GBps": round(nbytes / ms / 1e6, 1),
+                        "frac_of_hbm_peak": round(nbytes / ms / 1e6 / peak, 4), "reference_composition_ms": round(ms_lib, 4),
+                        "speedup_vs_reference_composition": round(ms_lib / ms, 2)})
+    except Exception as e:      # noqa: BLE001
+        out.append({"error": repr(e)[:300]})
     return out
 
 
