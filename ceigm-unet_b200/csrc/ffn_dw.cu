@@ -30,6 +30,8 @@
 
 namespace ss2d {
 
+int scan_path_policy();     // api.cu (test hook)
+
 constexpr int kDwnMaxSeg = 4;
 struct DwnSegs {
   int nseg;
@@ -312,6 +314,161 @@ dwnhwc_stencil_kernel(const T* __restrict__ x, const T* __restrict__ aux, T* __r
   }
 }
 
+// ---- the 3 x 3 single-segment case (the DWConv of both FFNs: forward + GELU, GELU' pass, transposed pass) as a COLUMN WALKER ----
+// A thread owns 4 channels of one image column and walks `rs` rows down it: per output pixel 3 new loads (the row below:
+// columns w - 1, w, w + 1), the 3 x 3 x 4 neighbourhood in a register window (row slot = row mod 3, walk unrolled 3-fold), and
+// the loads of the next THREE rows in flight as raw vectors (ring slot = row mod 3) while the current row is multiplied —
+// the tiled kernel above issues one batch of 18 loads per short-lived CTA and waits for it (48 % issue utilisation,
+// long_scoreboard 5.9 stall cycles per issue; profiles/r2_ncu_ffn_dw.txt). For epi 3 the ring slot of x row r carries aux row r - 1.
+// grid.x = (image, row segment, column tile, channel block), channel block fastest.
+struct DwnWalk { int nblk, tiles_w, nrs, rs; };
+
+template <typename T>
+constexpr int walk_ctas_per_sm() { return sizeof(T) == 2 ? 2 : 1; }
+
+template <typename T, bool GELU>
+__global__ void __launch_bounds__(DW_THREADS, walk_ctas_per_sm<T>())
+dwnhwc_walk3_kernel(const T* __restrict__ x, const T* __restrict__ aux, T* __restrict__ y, const float* __restrict__ wgt,
+                    const float* __restrict__ bias, const DwnWalk wk, int flip, int epi, int H, int W, int C) {
+  constexpr int VEC = 4, CB = DW_CL * VEC;
+  using RV = RawVec<T, VEC>;
+  const int chl = threadIdx.x % DW_CL, pxl = threadIdx.x / DW_CL;
+  unsigned bx = blockIdx.x;
+  const int by = bx % wk.nblk; bx /= wk.nblk;
+  const int tw = bx % wk.tiles_w; bx /= wk.tiles_w;
+  const int rsi = bx % wk.nrs;
+  const int b = bx / wk.nrs;
+  const int c = by * CB + chl * VEC;
+  const int w = tw * DW_PL + pxl;
+  if (c >= C || w >= W) return;                                  // no barrier in this kernel
+  const int r0 = rsi * wk.rs, r1 = min(H, r0 + wk.rs);           // output rows [r0, r1)
+  const int WC = W * C;
+
+  float wr[9][VEC], bv[VEC];
+  {
+    const float* wts = wgt + (int64_t)c * 9;
+    float wf[VEC * 9];
+    if ((reinterpret_cast<uintptr_t>(wts) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < 9; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wts) + q);
+        wf[4 * q] = t.x; wf[4 * q + 1] = t.y; wf[4 * q + 2] = t.z; wf[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < VEC * 9; ++q) wf[q] = __ldg(wts + q);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) wr[t][v] = flip ? wf[v * 9 + 8 - t] : wf[v * 9 + t];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) bv[v] = bias ? __ldg(bias + c + v) : 0.f;
+  }
+  bool colok[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) colok[j] = w + j - 1 >= 0 && w + j - 1 < W;
+  const int64_t img = ((int64_t)b * H * W + w) * C + c;          // element (b, 0, w, c)
+  const T* xc = x + img - C;                                     // column w - 1 of row 0
+  const T* ac = aux + img;
+  T* yc = y + img;
+  const bool want_aux = GELU && epi == 3;
+
+  RV ring[3][3], ringa[3];
+  auto issue = [&](int r, RV (&dst)[3], RV& dsta) {              // x row r (columns w - 1 .. w + 1) and aux row r - 1
+    const bool rok = r >= 0 && r < H && r <= r1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dst[j].zero();
+      if (rok && colok[j]) dst[j].load(xc + (r * WC + j * C));
+    }
+    dsta.zero();
+    if (want_aux && r - 1 >= r0 && r - 1 < r1) dsta.load(ac + (r - 1) * WC);
+  };
+  float win[3][3][VEC];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) win[i][j][v] = 0.f;
+
+  const int hs = r0 - 2;                                         // the walk starts two rows early: they fill the window
+  issue(hs + 1, ring[1], ringa[1]);
+  issue(hs + 2, ring[2], ringa[2]);
+  issue(hs + 3, ring[0], ringa[0]);
+  auto step = [&](int h, auto S) {
+    constexpr int s = decltype(S)::value;                        // (h - hs) mod 3
+    constexpr int sn = (s + 1) % 3;                              // slot of row h + 1
+    float av[VEC];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ring[sn][j].get(win[sn][j]);
+    ringa[sn].get(av);
+    issue(h + 4, ring[sn], ringa[sn]);                           // consumed three steps from now
+    if (h >= r0 && h < r1) {                                     // CTA-uniform
+      float acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] = bv[v];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wr[i * 3 + j][v], win[(s + i + 2) % 3][j][v], acc[v]);
+      float out[VEC];
+      if constexpr (GELU) {
+        if (epi == 1) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) out[v] = gelu_phi<false>(acc[v], 0.f);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) out[v] = gelu_phi<true>(acc[v], av[v]);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) out[v] = epi == 2 ? win[s][1][v] + acc[v] : acc[v];
+      }
+      stvec<T, VEC>(yc + h * WC, out);
+    }
+  };
+  for (int h = hs; h < r1; h += 3) {
+    step(h, std::integral_constant<int, 0>{});
+    step(h + 1, std::integral_constant<int, 1>{});
+    step(h + 2, std::integral_constant<int, 2>{});
+  }
+}
+
+template <typename T>
+static cudaError_t walk3_launch(const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B, int H, int W,
+                                int C, cudaStream_t stream) {
+  constexpr int CB = DW_CL * 4;
+  DwnWalk wk;
+  wk.nblk = (C + CB - 1) / CB;
+  wk.tiles_w = (W + DW_PL - 1) / DW_PL;
+  // rows per walker against wave quantisation: every segment costs two window-filling steps
+  const int64_t slots = (int64_t)sm_count_current_device() * walk_ctas_per_sm<T>();
+  const int64_t base = (int64_t)B * wk.tiles_w * wk.nblk;
+  int best = 1;
+  int64_t best_cost = -1;
+  for (int n = 1; n <= 16 && n <= H; ++n) {
+    const int rs = (H + n - 1) / n;
+    const int64_t cost = ((base * ((H + rs - 1) / rs) + slots - 1) / slots) * (rs + 2);
+    if (best_cost < 0 || cost < best_cost) { best = n; best_cost = cost; }
+  }
+  wk.rs = (H + best - 1) / best;
+  wk.nrs = (H + wk.rs - 1) / wk.rs;
+  const int64_t ctas = base * wk.nrs;
+  if (ctas >= (1ll << 31) || (int64_t)W * C * (H + 4) >= (1ll << 31)) return cudaErrorInvalidValue;
+  const T* xs = static_cast<const T*>(x);
+  const T* as = static_cast<const T*>(aux);
+  T* ys = static_cast<T*>(y);
+  if (epi == 1 || epi == 3)
+    dwnhwc_walk3_kernel<T, true><<<(unsigned)ctas, DW_THREADS, 0, stream>>>(xs, as, ys, sg.w[0], sg.b[0], wk, flip, epi, H, W, C);
+  else
+    dwnhwc_walk3_kernel<T, false><<<(unsigned)ctas, DW_THREADS, 0, stream>>>(xs, as, ys, sg.w[0], sg.b[0], wk, flip, epi, H, W, C);
+  return cudaGetLastError();
+}
+
 template <typename T, int VEC>
 static cudaError_t stencil_launch_t(const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B, int H,
                                     int W, int C, cudaStream_t stream) {
@@ -361,6 +518,11 @@ static cudaError_t stencil_launch_v(int vec, const void* x, const void* aux, voi
 cudaError_t dwnhwc_stencil_launch(const void* x, const void* aux, void* y, const DwnSegs& sg, int flip, int epi, int B, int H,
                                   int W, int C, int dt, cudaStream_t stream) {
   const int vec = dwn_vec(C, sg.cbeg, sg.nseg + 1, dt == SS2D_F32 ? 4 : 2, x, aux, y);
+  if (vec == 4 && sg.nseg == 1 && sg.k[0] == 3 && scan_path_policy() != 3) {     // the DWConv of the FFNs: column walker (test hook 3: tiled kernel)
+    if (dt == SS2D_F32) return walk3_launch<float>(x, aux, y, sg, flip, epi, B, H, W, C, stream);
+    if (dt == SS2D_F16) return walk3_launch<__half>(x, aux, y, sg, flip, epi, B, H, W, C, stream);
+    return walk3_launch<__nv_bfloat16>(x, aux, y, sg, flip, epi, B, H, W, C, stream);
+  }
   if (dt == SS2D_F32) return stencil_launch_v<float>(vec, x, aux, y, sg, flip, epi, B, H, W, C, stream);
   if (dt == SS2D_F16) return stencil_launch_v<__half>(vec, x, aux, y, sg, flip, epi, B, H, W, C, stream);
   return stencil_launch_v<__nv_bfloat16>(vec, x, aux, y, sg, flip, epi, B, H, W, C, stream);

@@ -79,6 +79,41 @@ def test_ffn_vs_oracle_live_shapes(ctor, C, hidden, H, W):
     _oracle_case(ctor, C, hidden, H, W, 2, False)
 
 
+def test_ffn_tiled_stencil_kernel_for_the_3x3_case():
+    """The single-segment 3 x 3 passes normally take the column walker; the test hook routes them through the tiled kernel."""
+    from ceigm_unet_b200 import _lib
+    _lib.test_force_path(3)
+    try:
+        _oracle_case("PVT2FFN", 64, 512, 56, 56, 2, False)
+        _oracle_case("PVT2FFN", 32, 128, 7, 9, 3, True)
+    finally:
+        _lib.test_force_path(0)
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (2, 3), (5, 17), (33, 4)])
+def test_walker_small_and_ragged_images(H, W):
+    """Column walker at image sizes around its row-segment / column-tile / 3-fold-unroll boundaries vs F.conv2d."""
+    from ceigm_unet_b200 import ops
+    gen = torch.Generator(device="cuda").manual_seed(H * 100 + W)
+    B, C = 2, 8
+    x = torch.randn(B, H * W, C, device="cuda", generator=gen)
+    a = torch.randn(B, H * W, C, device="cuda", generator=gen)
+    w = torch.randn(C, 1, 3, 3, device="cuda", generator=gen)
+    b = torch.randn(C, device="cuda", generator=gen)
+    img = x.transpose(1, 2).reshape(B, C, H, W)
+    pre = F.conv2d(img, w, b, padding=1, groups=C)
+    def nlc(t):
+        return t.flatten(2).transpose(1, 2)
+    assert rel_err(ops.dwnhwc_stencil(x, (H, W), [(C, 3, w, b)], epi=ops.EPI_NONE), nlc(pre)) < 1e-4
+    assert rel_err(ops.dwnhwc_stencil(x, (H, W), [(C, 3, w, b)], epi=ops.EPI_GELU), nlc(F.gelu(pre))) < 1e-4
+    assert rel_err(ops.dwnhwc_stencil(x, (H, W), [(C, 3, w, b)], epi=ops.EPI_RESIDUAL), nlc(img + pre)) < 1e-4
+    pre_g = pre.detach().clone().requires_grad_(True)
+    F.gelu(pre_g).backward(a.transpose(1, 2).reshape(B, C, H, W))
+    assert rel_err(ops.dwnhwc_stencil(x, (H, W), [(C, 3, w, b)], epi=ops.EPI_DGELU_MUL, aux=a), nlc(pre_g.grad)) < 1e-4
+    flipped = F.conv2d(img, w.flip(2, 3), None, padding=1, groups=C)
+    assert rel_err(ops.dwnhwc_stencil(x, (H, W), [(C, 3, w, None)], flip=True, epi=ops.EPI_NONE), nlc(flipped)) < 1e-4
+
+
 @pytest.mark.parametrize("ctor", ["PVT2FFN", "custom_ffn"])
 def test_ffn_bf16_autocast(ctor):
     _oracle_case(ctor, 128, 1024, 28, 28, 2, True)
