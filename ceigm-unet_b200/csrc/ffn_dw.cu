@@ -231,20 +231,26 @@ __device__ __forceinline__ void dwn_taps(const T* __restrict__ xb, const float* 
       if (ki < 0 || ki >= K) continue;                           // resolved at compile time
 #pragma unroll
       for (int j = 0; j < K; ++j) {
+        float wv[VEC];
         if constexpr (K == 3) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[py][v] = fmaf(wr[ki * 3 + j][v], xv[j][v], acc[py][v]);
+          for (int v = 0; v < VEC; ++v) wv[v] = wr[ki * 3 + j][v];
+        } else if constexpr (VEC == 4) {
+          const float4 t = *reinterpret_cast<const float4*>(wts + (ki * K + j) * CB);
+          wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
         } else {
-          float wv[VEC];
-          if constexpr (VEC == 4) {
-            const float4 t = *reinterpret_cast<const float4*>(wts + (ki * K + j) * CB);
-            wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
-          } else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) wv[v] = wts[(ki * K + j) * CB + v];
+          for (int v = 0; v < VEC; ++v) wv[v] = wts[(ki * K + j) * CB + v];
+        }
+        if constexpr (VEC >= 2) {                                // channel pairs on packed fp32x2 FMAs
+#pragma unroll
+          for (int q = 0; q < VEC / 2; ++q) {
+            const float2 r = __ffma2_rn(make_float2(wv[2 * q], wv[2 * q + 1]), make_float2(xv[j][2 * q], xv[j][2 * q + 1]),
+                                        make_float2(acc[py][2 * q], acc[py][2 * q + 1]));
+            acc[py][2 * q] = r.x; acc[py][2 * q + 1] = r.y;
           }
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[py][v] = fmaf(wv[v], xv[j][v], acc[py][v]);
+        } else {
+          acc[py][0] = fmaf(wv[0], xv[j][0], acc[py][0]);
         }
       }
     }
