@@ -242,16 +242,9 @@ __device__ __forceinline__ void dwn_taps(const T* __restrict__ xb, const float* 
 #pragma unroll
           for (int v = 0; v < VEC; ++v) wv[v] = wts[(ki * K + j) * CB + v];
         }
-        if constexpr (VEC >= 2) {                                // channel pairs on packed fp32x2 FMAs
+        // scalar FMAs: packed fp32x2 pairs (as in the column walker) measured SLOWER in this kernel (multi-scale stage 160 -> 185 us)
 #pragma unroll
-          for (int q = 0; q < VEC / 2; ++q) {
-            const float2 r = __ffma2_rn(make_float2(wv[2 * q], wv[2 * q + 1]), make_float2(xv[j][2 * q], xv[j][2 * q + 1]),
-                                        make_float2(acc[py][2 * q], acc[py][2 * q + 1]));
-            acc[py][2 * q] = r.x; acc[py][2 * q + 1] = r.y;
-          }
-        } else {
-          acc[py][0] = fmaf(wv[0], xv[j][0], acc[py][0]);
-        }
+        for (int v = 0; v < VEC; ++v) acc[py][v] = fmaf(wv[v], xv[j][v], acc[py][v]);
       }
     }
   }
