@@ -164,7 +164,7 @@ def check(rc: int, what: str) -> None:
 
 
 def test_force_path(policy: int) -> None:
-    """TEST HOOK (include/ss2d_b200.h: ss2d_test_force_path): 0 automatic, 1 / 2 lane-owns-row forward (32 / 16-row warps), 3 the 8-row-warp forward."""
+    """TEST HOOK (include/ss2d_b200.h: ss2d_test_force_path): 0 automatic, 1 / 2 lane-owns-row forward (32 / 16-row warps), 3 the 8-row-warp forward (and the tiled FFN stencil), 4 the segmented forward."""
     rc = lib().ss2d_test_force_path(int(policy))
     if rc != 0:
         raise RuntimeError("ss2d_test_force_path(%d) -> %d" % (policy, rc))

@@ -602,7 +602,7 @@ int64_t ss2d_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
 }
 int32_t ss2d_test_force_path(int32_t policy) {
-  if (policy < 0 || policy > 3) return SS2D_ERR_BAD_SHAPE;
+  if (policy < 0 || policy > 4) return SS2D_ERR_BAD_SHAPE;
   g_path_policy.store(policy, std::memory_order_relaxed);
   return SS2D_OK;
 }

@@ -40,9 +40,10 @@ struct FwdrShape {
   static constexpr size_t smem_bytes = (size_t)FR_NW * warp_bytes + FR_NW * FR_STAGES * 8 + 1024;
 };
 
-template <int NS, int R, bool SOFTPLUS>
+template <int NS, int R, bool SOFTPLUS, bool SEG>
 __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams p, const __grid_constant__ FwdrMaps maps,
-                                                               const int nrb, const int nwb) {
+                                                               const int nrb, const int nwb, const int nseg_arg, const int tps) {
+  const int nseg = SEG ? nseg_arg : 1;                     // compile-time 1 in the whole-row instantiation
   using S = FwdrShape<R>;
   constexpr int ROWS = S::ROWS;
   extern __shared__ __align__(16) unsigned char smem_rawfr[];
@@ -50,7 +51,10 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wb = blockIdx.x * FR_NW + warp;                // warp block: (batch, group, row block), row block fastest
   if (wb >= nwb) return;                                   // warps are independent: no CTA-wide barrier anywhere
-  const int rb = wb % nrb, bg = wb / nrb;
+  // warp block = (batch, group, segment of the sequence, row block). nseg > 1 (small calls, SEGMENTED mode): every warp scans
+  // tps tiles from a ZERO state; scan_fwd_fixup_kernel adds the carried-in states afterwards (see scan_fwdr_try).
+  const int rb = wb % nrb, sb = wb / nrb;
+  const int seg = SEG ? sb % nseg : 0, bg = SEG ? sb / nseg : sb;
   const int g = bg % p.G, b = bg / p.G;
   const int q = lane % R, rl = lane / R;
   const int row0 = rb * ROWS;                              // first row of this warp inside the group
@@ -60,7 +64,9 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
   const int L = p.L;
   const int dir = p.layout == SS2D_LAYOUT_NATURAL ? p.dirs[g] : 0;
   const bool rev = dir == 3;
-  const int ntiles = (L + FR_LT - 1) / FR_LT;
+  const int ntiles_row = (L + FR_LT - 1) / FR_LT;
+  const int tb = SEG ? seg * tps : 0;                      // first tile of this warp's segment
+  const int ntiles = SEG ? min(ntiles_row, tb + tps) : ntiles_row;      // one past its last tile
 
   float* wsm = reinterpret_cast<float*>(smem + warp * S::warp_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + FR_NW * S::warp_bytes) + warp * FR_STAGES;
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
 
   const int ug = p.u_mod > 0 ? g % (p.u_mod / p.dpg) : g;  // group coordinate of u when the groups share it
   auto issue = [&](int t) {                                // lane 0 only
-    const int s = t % FR_STAGES;
+    const int s = (t - tb) % FR_STAGES;
     const int l0 = t * FR_LT;
     const int m0 = rev ? L - l0 - FR_LT : l0;              // memory offset of the tile (may be < 0: zero-filled by TMA)
     mbar_arrive_expect_tx(&full[s], (uint32_t)S::stage_bytes);
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
   if (lane == 0) {
     for (int s = 0; s < FR_STAGES; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
-    for (int t = 0; t < FR_STAGES && t < ntiles; ++t) issue(t);
+    for (int t = tb; t < tb + FR_STAGES && t < ntiles; ++t) issue(t);
   }
   __syncwarp();
 
@@ -136,9 +142,9 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
       }
     };
     mbar_wait(&full[0], 0);
-    activate(st_dl(0), st_u(0), 0, min(FR_LT, L));
-    for (int t = 0; t < ntiles; ++t) {
-      const int s = t % FR_STAGES, sn = (t + 1) % FR_STAGES;
+    activate(st_dl(0), st_u(0), 0, min(FR_LT, L - tb * FR_LT));
+    for (int t = tb; t < ntiles; ++t) {
+      const int s = (t - tb) % FR_STAGES, sn = (t + 1 - tb) % FR_STAGES;
       const int l0 = t * FR_LT, len = min(FR_LT, L - l0);
       const float* s_dl = st_dl(s);
       const float* s_u = st_u(s);
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
 #pragma unroll 1
       for (int i4 = 0; i4 < FR_LT / 4; i4 += 2 * R) {
         const bool last_pair = i4 == FR_LT / 4 - 2 * R;
-        if (last_pair && more) mbar_wait(&full[sn], ((t + 1) / FR_STAGES) & 1);    // requested one tile ago: there by now
+        if (last_pair && more) mbar_wait(&full[sn], ((t + 1 - tb) / FR_STAGES) & 1);    // requested one tile ago: there by now
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int ii = i4 + k * R;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(FR_NW * 32) scan_fwdr_kernel(const ScanParams 
   };
   if (rev) body(std::true_type{}); else body(std::false_type{});
 
-  if (p.last_state != nullptr && valid) {
+  if (p.last_state != nullptr && valid && nseg == 1) {     // segmented mode: written by the fix-up kernel
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       const int n = j * R + q;
@@ -247,17 +253,169 @@ static bool fwdr_maps(const ScanParams& p, FwdrMaps* m) {
          make_tmap(&m->B, p.Bm, 4, d4, s4B, 16, R > 1) && make_tmap(&m->C, p.Cm, 4, d4, s4C, 16, R > 1);
 }
 
-template <int NS, int R, bool SOFTPLUS>
-static cudaError_t launch_fwdr(const ScanParams& p, const FwdrMaps& maps, cudaStream_t stream) {
+template <int NS, int R, bool SOFTPLUS, bool SEG>
+static cudaError_t launch_fwdr(const ScanParams& p, const FwdrMaps& maps, cudaStream_t stream, int nseg = 1, int tps = 0) {
   using S = FwdrShape<R>;
-  auto kern = scan_fwdr_kernel<NS, R, SOFTPLUS>;
+  auto kern = scan_fwdr_kernel<NS, R, SOFTPLUS, SEG>;
   static PerDeviceOnce once;
   cudaError_t e = func_attr_once(once, reinterpret_cast<const void*>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem_bytes);
   if (e != cudaSuccess) return e;
+  if (!SEG) nseg = 1;
   const int nrb = (p.dpg + S::ROWS - 1) / S::ROWS;
-  const long long nwb = (long long)nrb * p.G * p.batch;
-  kern<<<(unsigned)((nwb + FR_NW - 1) / FR_NW), FR_NW * 32, S::smem_bytes, stream>>>(p, maps, nrb, (int)nwb);
+  const long long nwb = (long long)nrb * p.G * p.batch * nseg;
+  if (tps <= 0) tps = (p.L + FR_LT - 1) / FR_LT;
+  kern<<<(unsigned)((nwb + FR_NW - 1) / FR_NW), FR_NW * 32, S::smem_bytes, stream>>>(p, maps, nrb, (int)nwb, nseg, tps);
   return cudaGetLastError();
+}
+
+// ---- SEGMENTED mode: the sequence split over several warps (small calls: batch 1 / 2 of the north-star shape give the machine
+// 24 / 48 CTAs of sequential work otherwise). The reference chunks L the same way with a running prefix per 2048 positions
+// (selective_scan_fwd_kernel.cuh:101-158); here a segment is `tps` 32-position tiles:
+//   1. scan_fwdr_kernel with nseg > 1: every (row block, segment) warp scans its tiles from a ZERO state -> local y, local
+//      checkpoints (the segment's last checkpoint = its local end state e_s);
+//   2. scan_fwd_carry_kernel (warp per row): S_s = sum of the activated delta over segment s (the decay of state n across the
+//      whole segment is exp(A_n S_s)), then the true end states h_s = e_s + exp(A S_s) h_(s-1), written over the segments' last
+//      checkpoints (and last_state);
+//   3. scan_fwd_fixup_kernel (warp per (row, segment >= 1)): with c_l the inclusive running sum of delta inside the segment,
+//      y_l += sum_n C_(l,n) exp(A_n c_l) h_in,n and checkpoint_t += exp(A c_(end of t)) h_in.
+// Twice the exponentials of the sequential scan for nseg times its parallelism; exact in exact arithmetic (products of
+// exponentials = exponential of the sum). Needs the checkpoint buffer (it carries e_s); calls without one take scan_fwd.cu.
+constexpr int FX_MAX_SEG = 64;
+
+// 4 consecutive scan positions starting at l of one row (L % 4 == 0, rows 16-byte aligned on this path): one 128-bit access;
+// a reversed traversal reads the mirrored quad and swaps it.
+__device__ __forceinline__ float4 ldq(const float* __restrict__ row, int l, int L, bool rev) {
+  if (!rev) return __ldg(reinterpret_cast<const float4*>(row + l));
+  const float4 v = __ldg(reinterpret_cast<const float4*>(row + (L - 4 - l)));
+  return make_float4(v.w, v.z, v.y, v.x);
+}
+template <bool SOFTPLUS>
+__device__ __forceinline__ float4 activate4(float4 x, float bias) {
+  x.x += bias; x.y += bias; x.z += bias; x.w += bias;
+  if (SOFTPLUS) { x.x = softplus20(x.x); x.y = softplus20(x.y); x.z = softplus20(x.z); x.w = softplus20(x.w); }
+  return x;
+}
+
+// CTA per row: its four warps split the segments for the sums, warp 0 runs the carry chain
+template <bool SOFTPLUS>
+__global__ void __launch_bounds__(128) scan_fwd_carry_kernel(const ScanParams p, const int tps, const int nseg) {
+  __shared__ float s_sum[FX_MAX_SEG];
+  __shared__ float s_e[FX_MAX_SEG][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x;
+  const int b = row / p.dim, d = row - b * p.dim, g = d / p.dpg;
+  const int L = p.L, N = p.N;
+  const bool rev = p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3;
+  const int ntiles = (L + FR_LT - 1) / FR_LT;
+  const float* dl = static_cast<const float*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
+  float* ck = p.ckpt + ((int64_t)b * p.dim + d) * p.nck * N;
+  const float bias = p.bias ? p.bias[d] : 0.f;
+  // phase 1 (independent iterations): S_s = sum of the activated delta over segment s, and the local end states e_s
+#pragma unroll 2
+  for (int s = warp; s < nseg; s += 4) {
+    const int lb = s * tps * FR_LT, le = min(L, lb + tps * FR_LT);
+    float sum = 0.f;
+    for (int l = lb + lane * 4; l < le; l += 128) {
+      const float4 x = activate4<SOFTPLUS>(ldq(dl, l, L, rev), bias);
+      sum += (x.x + x.y) + (x.z + x.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int tl = min(ntiles, (s + 1) * tps) - 1;           // last tile of the segment
+    if (lane == 0) s_sum[s] = sum;
+    if (lane < N) s_e[s][lane] = ck[(int64_t)tl * N + lane];
+  }
+  __syncthreads();
+  // phase 2: h_s = e_s + exp(A S_s) h_(s-1), the true end state of segment s
+  if (warp == 0 && lane < N) {
+    const float A2l = p.A[(int64_t)d * p.A_ld + lane] * kLog2e;
+    float h = 0.f;
+    for (int s = 0; s < nseg; ++s) {
+      h = fmaf(ex2f(A2l * s_sum[s]), h, s_e[s][lane]);
+      const int tl = min(ntiles, (s + 1) * tps) - 1;
+      if (s > 0) ck[(int64_t)tl * N + lane] = h;
+    }
+    if (p.last_state != nullptr) {
+      const int64_t slot = ((int64_t)b * p.dim + d) * p.A_ld + lane;
+      if (p.last_il) { p.last_state[2 * slot] = 0.f; p.last_state[2 * slot + 1] = h; }
+      else p.last_state[slot] = h;
+    }
+  }
+}
+
+// warp per (row, segment >= 1); a lane owns 4 consecutive positions of a 128-position step
+template <bool SOFTPLUS>
+__global__ void __launch_bounds__(128) scan_fwd_fixup_kernel(const ScanParams p, const int tps, const int nseg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wid >= (int64_t)p.batch * p.dim * (nseg - 1)) return;
+  const int row = (int)(wid / (nseg - 1)), seg = 1 + (int)(wid % (nseg - 1));
+  const int b = row / p.dim, d = row - b * p.dim, g = d / p.dpg;
+  const int L = p.L, N = p.N;
+  const bool rev = p.layout == SS2D_LAYOUT_NATURAL && p.dirs[g] == 3;
+  const int ntiles = (L + FR_LT - 1) / FR_LT;
+  const int tb = seg * tps, te = min(ntiles, tb + tps);
+  const int lb = tb * FR_LT, le = min(L, te * FR_LT);
+  const float* dl = static_cast<const float*>(p.delta) + (int64_t)b * p.dl_bs + (int64_t)d * p.dl_ds;
+  const float* Cg = static_cast<const float*>(p.Cm) + (int64_t)b * p.C_bs + (int64_t)g * p.C_gs;
+  float* out = p.out ? static_cast<float*>(p.out) + (int64_t)b * p.out_bs + (int64_t)d * p.out_ds : nullptr;
+  float* ck = p.ckpt + ((int64_t)b * p.dim + d) * p.nck * N;
+  const float bias = p.bias ? p.bias[d] : 0.f;
+  const float A2l = lane < N ? p.A[(int64_t)d * p.A_ld + lane] * kLog2e : 0.f;
+  const float hl = lane < N ? ck[(int64_t)(tb - 1) * N + lane] : 0.f;     // true state entering the segment (carry kernel)
+  float A2[16], hin[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    A2[n] = __shfl_sync(0xffffffffu, A2l, n);
+    hin[n] = __shfl_sync(0xffffffffu, hl, n);
+  }
+  // once A_n * (running sum) is below the flush-to-zero range of ex2 for every state, every further term is EXACTLY zero
+  float amax = -3.0e38f;
+#pragma unroll
+  for (int n = 0; n < 16; ++n) amax = n < N ? fmaxf(amax, A2[n]) : amax;
+  float base = 0.f;
+#pragma unroll 2
+  for (int l0 = lb; l0 < le; l0 += 128) {
+    if (SOFTPLUS && amax * base < -160.f) break;              // (softplus: delta >= 0, the running sum only grows)
+    const int l = l0 + lane * 4;
+    const bool live = l < le;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) x = activate4<SOFTPLUS>(ldq(dl, l, L, rev), bias);
+    x.y += x.x; x.z += x.y; x.w += x.z;                      // inclusive running sum inside the quad
+    float incl = x.w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const float off = base + (incl - x.w);
+    const float4 cum = make_float4(off + x.x, off + x.y, off + x.z, off + x.w);
+    if (live && out != nullptr) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < N) {
+          const float4 cv = ldq(Cg + (int64_t)n * p.C_ns, l, L, rev);
+          acc.x = fmaf(cv.x * ex2f(A2[n] * cum.x), hin[n], acc.x);
+          acc.y = fmaf(cv.y * ex2f(A2[n] * cum.y), hin[n], acc.y);
+          acc.z = fmaf(cv.z * ex2f(A2[n] * cum.z), hin[n], acc.z);
+          acc.w = fmaf(cv.w * ex2f(A2[n] * cum.w), hin[n], acc.w);
+        }
+      float4* op = reinterpret_cast<float4*>(out + (rev ? L - 4 - l : l));
+      float4 o4 = *op;
+      if (rev) { o4.x += acc.w; o4.y += acc.z; o4.z += acc.y; o4.w += acc.x; }
+      else { o4.x += acc.x; o4.y += acc.y; o4.z += acc.z; o4.w += acc.w; }
+      *op = o4;
+    }
+    // the four 32-position tiles of this step end in lanes 7, 15, 23, 31 (flat past the end of the row)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float cend = __shfl_sync(0xffffffffu, cum.w, 8 * j + 7);
+      const int t = l0 / FR_LT + j;
+      if (t < te - 1 && lane < N) ck[(int64_t)t * N + lane] += ex2f(A2l * cend) * hl;   // the segment's last one is already true
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
 }
 
 int scan_path_policy();     // api.cu
@@ -273,21 +431,50 @@ bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   // 128-bit stores of out: rows aligned to 16 bytes
   if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.out_bs & 3) || (p.out_ds & 3))) return false;
   // Variant by machine fill (measured on B200): this mapping needs two warps per scheduler to hide its
-  // latencies. 32-row warps (R = 1) when there are that many, else 16-row warps (R = 2), else scan_fwd.cu (8-row warps).
+  // latencies. 32-row warps (R = 1) when there are that many, else 16-row warps (R = 2), else the sequence is split over
+  // several 16-row warps (SEGMENTED mode above) when that gives at least six segments of at least four tiles, else
+  // scan_fwd.cu (8-row warps).
   const long long wb1 = (long long)((p.dpg + 31) / 32) * p.G * p.batch;
   const long long wb2 = (long long)((p.dpg + 15) / 16) * p.G * p.batch;
-  if (wb2 >= 0x7fffffffLL) return false;
+  if (wb2 >= 0x7fffffffLL / 64) return false;
   const long long need = (long long)sm_count_current_device() * 4 * 2 * 9 / 10;
   const int policy = scan_path_policy();      // 0 unless a parity test forces a path (ss2d_test_force_path)
-  if (policy == 3 || (policy == 0 && wb2 < need)) return false;
-  const bool r1 = policy == 0 ? wb1 >= need : policy == 1;
+  if (policy == 3) return false;
+  const int ntiles = (p.L + FR_LT - 1) / FR_LT;
+  int nseg = 1, tps = ntiles;
+  if (policy == 4 || (policy == 0 && wb2 < need)) {
+    if (p.ckpt == nullptr) return false;
+    const int min_tiles = policy == 4 ? 1 : 4;
+    long long want = policy == 4 ? 3 : (need + wb2 - 1) / wb2;
+    if (want > ntiles / min_tiles) want = ntiles / min_tiles;
+    if (want > FX_MAX_SEG) want = FX_MAX_SEG;
+    if (want < (policy == 4 ? 2 : 6)) return false;       // measured: the fix-up pass costs about one sequential sweep of the call
+                                                             // -> only calls that leave >= 5/6 of the machine idle are split
+    tps = (int)((ntiles + want - 1) / want);
+    nseg = (ntiles + tps - 1) / tps;
+    if (nseg < 2) return false;
+  }
+  const bool r1 = nseg == 1 && (policy == 0 ? wb1 >= need : policy == 1);
   FwdrMaps maps;
   if (r1) {
     if (!fwdr_maps<1>(p, &maps)) return false;
-    *err = p.softplus ? launch_fwdr<16, 1, true>(p, maps, stream) : launch_fwdr<16, 1, false>(p, maps, stream);
-  } else {
-    if (!fwdr_maps<2>(p, &maps)) return false;
-    *err = p.softplus ? launch_fwdr<8, 2, true>(p, maps, stream) : launch_fwdr<8, 2, false>(p, maps, stream);
+    *err = p.softplus ? launch_fwdr<16, 1, true, false>(p, maps, stream) : launch_fwdr<16, 1, false, false>(p, maps, stream);
+    return true;
+  }
+  if (!fwdr_maps<2>(p, &maps)) return false;
+  if (nseg > 1) *err = p.softplus ? launch_fwdr<8, 2, true, true>(p, maps, stream, nseg, tps) : launch_fwdr<8, 2, false, true>(p, maps, stream, nseg, tps);
+  else *err = p.softplus ? launch_fwdr<8, 2, true, false>(p, maps, stream) : launch_fwdr<8, 2, false, false>(p, maps, stream);
+  if (nseg > 1 && *err == cudaSuccess) {
+    const long long rows = (long long)p.batch * p.dim;
+    const unsigned gc = (unsigned)rows, gf = (unsigned)((rows * (nseg - 1) + 3) / 4);
+    if (p.softplus) {
+      scan_fwd_carry_kernel<true><<<gc, 128, 0, stream>>>(p, tps, nseg);
+      scan_fwd_fixup_kernel<true><<<gf, 128, 0, stream>>>(p, tps, nseg);
+    } else {
+      scan_fwd_carry_kernel<false><<<gc, 128, 0, stream>>>(p, tps, nseg);
+      scan_fwd_fixup_kernel<false><<<gf, 128, 0, stream>>>(p, tps, nseg);
+    }
+    *err = cudaGetLastError();
   }
   return true;
 }

@@ -328,7 +328,8 @@ int64_t ss2d_launch_count(int reset);
  * the call gives the machine (csrc/scan_fwdr.cu); parity tests use this to run a small case through a kernel that only
  * large calls would select. policy 0: automatic (the default, the only value a product caller ever needs); 1: lane-owns-row
  * forward with 32-row warps; 2: the same with 16-row warps; 3: the 8-row-warp forward (scan_fwd.cu) — and, for
- * ss2d_dwnhwc_stencil, the tiled kernel where the single-segment 3 x 3 case would take the column walker (csrc/ffn_dw.cu).
+ * ss2d_dwnhwc_stencil, the tiled kernel where the single-segment 3 x 3 case would take the column walker (csrc/ffn_dw.cu);
+ * 4: the segmented forward of small calls (sequence split over several warps + carry + fix-up kernels, csrc/scan_fwdr.cu).
  * Process-wide; returns SS2D_OK or SS2D_ERR_BAD_SHAPE. */
 int32_t ss2d_test_force_path(int32_t policy);
 
