@@ -392,10 +392,13 @@ __global__ void __launch_bounds__(128) scan_fwd_fixup_kernel(const ScanParams p,
     const float4 cum = make_float4(off + x.x, off + x.y, off + x.z, off + x.w);
     if (live && out != nullptr) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* cp = Cg + (rev ? L - 4 - l : l);          // this lane's quad of state row 0; rows are C_ns apart
 #pragma unroll
       for (int n = 0; n < 16; ++n)
         if (n < N) {
-          const float4 cv = ldq(Cg + (int64_t)n * p.C_ns, l, L, rev);
+          float4 cv = __ldg(reinterpret_cast<const float4*>(cp));
+          cp += p.C_ns;
+          if (rev) cv = make_float4(cv.w, cv.z, cv.y, cv.x);
           acc.x = fmaf(cv.x * ex2f(A2[n] * cum.x), hin[n], acc.x);
           acc.y = fmaf(cv.y * ex2f(A2[n] * cum.y), hin[n], acc.y);
           acc.z = fmaf(cv.z * ex2f(A2[n] * cum.z), hin[n], acc.z);
@@ -432,7 +435,7 @@ bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
   if (p.out && ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.out_bs & 3) || (p.out_ds & 3))) return false;
   // Variant by machine fill (measured on B200): this mapping needs two warps per scheduler to hide its
   // latencies. 32-row warps (R = 1) when there are that many, else 16-row warps (R = 2), else the sequence is split over
-  // several 16-row warps (SEGMENTED mode above) when that gives at least six segments of at least four tiles, else
+  // several 16-row warps (SEGMENTED mode above) when that gives at least eight segments of at least four tiles, else
   // scan_fwd.cu (8-row warps).
   const long long wb1 = (long long)((p.dpg + 31) / 32) * p.G * p.batch;
   const long long wb2 = (long long)((p.dpg + 15) / 16) * p.G * p.batch;
@@ -448,9 +451,10 @@ bool scan_fwdr_try(const ScanParams& p, cudaStream_t stream, cudaError_t* err) {
     long long want = policy == 4 ? 3 : (need + wb2 - 1) / wb2;
     if (want > ntiles / min_tiles) want = ntiles / min_tiles;
     if (want > FX_MAX_SEG) want = FX_MAX_SEG;
-    if (want < (policy == 4 ? 2 : 6)) return false;       // measured: the fix-up pass costs about one sequential sweep of the call
-                                                             // -> only calls that leave >= 5/6 of the machine idle are split
+    if (want < (policy == 4 ? 2 : 8)) return false;       // measured: the fix-up pass costs about one sequential sweep of the call
+                                                             // -> only calls that leave >= 7/8 of the machine idle are split
     tps = (int)((ntiles + want - 1) / want);
+    if (policy != 4) tps = tps < 6 ? 4 : (tps + 2) / 4 * 4;  // whole 128-position steps of the fix-up pass (4 tiles each)
     nseg = (ntiles + tps - 1) / tps;
     if (nseg < 2) return false;
   }
