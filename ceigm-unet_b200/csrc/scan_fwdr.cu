@@ -392,18 +392,20 @@ __global__ void __launch_bounds__(128) scan_fwd_fixup_kernel(const ScanParams p,
     const float4 cum = make_float4(off + x.x, off + x.y, off + x.z, off + x.w);
     if (live && out != nullptr) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // all C quads first, without a branch per state (states past N re-read row N - 1 and multiply by h_in = 0): 16
+      // independent 128-bit loads in flight instead of 16 load -> use round trips
       const float* cp = Cg + (rev ? L - 4 - l : l);          // this lane's quad of state row 0; rows are C_ns apart
+      float4 cq[16];
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
-        if (n < N) {
-          float4 cv = __ldg(reinterpret_cast<const float4*>(cp));
-          cp += p.C_ns;
-          if (rev) cv = make_float4(cv.w, cv.z, cv.y, cv.x);
-          acc.x = fmaf(cv.x * ex2f(A2[n] * cum.x), hin[n], acc.x);
-          acc.y = fmaf(cv.y * ex2f(A2[n] * cum.y), hin[n], acc.y);
-          acc.z = fmaf(cv.z * ex2f(A2[n] * cum.z), hin[n], acc.z);
-          acc.w = fmaf(cv.w * ex2f(A2[n] * cum.w), hin[n], acc.w);
-        }
+      for (int n = 0; n < 16; ++n) cq[n] = __ldg(reinterpret_cast<const float4*>(cp + (int64_t)min(n, N - 1) * p.C_ns));
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        const float4 cv = rev ? make_float4(cq[n].w, cq[n].z, cq[n].y, cq[n].x) : cq[n];
+        acc.x = fmaf(cv.x * ex2f(A2[n] * cum.x), hin[n], acc.x);
+        acc.y = fmaf(cv.y * ex2f(A2[n] * cum.y), hin[n], acc.y);
+        acc.z = fmaf(cv.z * ex2f(A2[n] * cum.z), hin[n], acc.z);
+        acc.w = fmaf(cv.w * ex2f(A2[n] * cum.w), hin[n], acc.w);
+      }
       float4* op = reinterpret_cast<float4*>(out + (rev ? L - 4 - l : l));
       float4 o4 = *op;
       if (rev) { o4.x += acc.w; o4.y += acc.z; o4.z += acc.y; o4.w += acc.x; }

@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-for cfg in "8 4" "8 8" "12 12" "6 6" "4 4"; do
-  set -- $cfg
-  timeout 200 python bench.py --steps 20 --warmup 3 --no-model --no-extras --no-cpu-baseline --e2e-chunks $1 --e2e-streams $2 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('chunks/streams', '$1/$2', 'e2e', d['e2e']['value'], 'value', d['value'])"
-done
+timeout 600 python -m pytest tests/test_scan_fast_gpu.py -x -q -m gpu 2>&1 | tail -3 > gpurun_out/s20_tests.log
+cat gpurun_out/s20_tests.log
+timeout 300 python bench.py --steps 20 --warmup 3 --no-model --no-cpu-baseline > gpurun_out/s20_bench.json 2> gpurun_out/s20_bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/s20_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['fwd_ms'], d['bwd_ms'])
+for v in d['other_workloads']:
+    if v['workload'] in ('vm_d192_b1','vm_d192_b2'): print(v['workload'], v['fwd_ms'], v['fwd_bwd_ms'])
+PY
