@@ -229,3 +229,32 @@ def test_reference_autograd_functions_bound_to_dropin():
     assert "ceigm" in (core.__file__ or "") and hasattr(core, "fwd") and hasattr(core, "bwd")
     cs, ss, _ = R.reference_modules()
     assert ss.SelectiveScanCore is cs.SelectiveScanCore       # the reference's own autograd.Function, unmodified
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_harness_min_pool_rebinding_is_bit_identical(dtype):
+    """harness.graph_step.make_capturable() replaces AdaptiveMinPool2d.forward (F.unfold of the whole map + min) by the same
+    min on the flattened view: identical values and identical gradient routing — including ties (post-ReLU zeros)."""
+    import importlib
+    R = _ref()
+    R.load_reference(scan="dropin")
+    from harness import graph_step
+    bd = importlib.import_module("model.best_decoder")
+    pool = bd.AdaptiveMinPool2d()
+    orig = getattr(bd.AdaptiveMinPool2d, "_ss2d_harness_orig_forward", bd.AdaptiveMinPool2d.forward)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.relu(torch.randn(3, 40, 28, 28, device="cuda", generator=gen)).to(dtype)      # many exact ties at 0
+    x[:, ::2] -= 1.0                                                                          # and channels with a unique minimum
+    g = torch.randn(3, 40, 1, 1, device="cuda", generator=gen).to(dtype)
+    xa = x.clone().requires_grad_(True)
+    ya = orig(pool, xa)
+    ya.backward(g)
+    graph_step.make_capturable()
+    assert bd.AdaptiveMinPool2d.forward is graph_step._min_pool_direct
+    xb = x.clone().requires_grad_(True)
+    yb = pool(xb)
+    yb.backward(g)
+    assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad)
+    # non-square maps keep the reference code path
+    xr = torch.randn(1, 4, 6, 6, device="cuda")
+    assert torch.equal(pool(xr), orig(pool, xr))
