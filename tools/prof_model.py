@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-time breakdown of one GM-UNet training step (224^2, batch 24, bf16) by torch.profiler: which kernels the GPU time of
-the graphed step is made of. python tools/prof_model.py [dropin|fused] > profiles/..."""
+the graphed step is made of. python tools/prof_model.py [dropin|fused] [capturable] > profiles/..."""
 import os
 import sys
 from collections import defaultdict
@@ -14,6 +14,9 @@ from harness import workloads as W  # noqa: E402
 level = sys.argv[1] if len(sys.argv) > 1 else "fused"
 dev = torch.device("cuda", 0)
 net = W.build(9, level, dev)
+if "capturable" in sys.argv:      # the graph-mode rebindings of the harness (cached DySample grid, min pool without im2col)
+    from harness import graph_step
+    graph_step.make_capturable()
 step = W.TrainStep(net, 9)
 x, y = W.synthetic_batch(24, 224, 9)
 for _ in range(3):
