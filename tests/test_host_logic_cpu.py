@@ -50,3 +50,25 @@ def test_tensor_core_paths_refuse_cpu_tensors():
         Fn.linear_tc(x, W)
     with pytest.raises(RuntimeError):
         Fn.dwconv3_silu_planes(torch.randn(1, 4, 8, 8), torch.randn(4, 1, 3, 3), None)
+
+
+def test_harness_min_pool_rebinding_matches_reference_on_cpu():
+    """harness.graph_step._min_pool_direct vs the reference's AdaptiveMinPool2d.forward (F.unfold of the whole map + min,
+    model/best_decoder.py:179-191): same values, same gradient routing (ties included). CPU tensors: host logic only."""
+    import importlib
+    import pytest
+    from harness import graph_step, refmodel
+    if not refmodel.available():
+        pytest.skip("reference tree not installed (harness/install_ref.py)")
+    refmodel.load_reference(scan="cpu_fast")
+    bd = importlib.import_module("model.best_decoder")
+    orig = getattr(bd.AdaptiveMinPool2d, "_ss2d_harness_orig_forward", bd.AdaptiveMinPool2d.forward)
+    pool = bd.AdaptiveMinPool2d()
+    gen = torch.Generator().manual_seed(0)
+    x = torch.relu(torch.randn(2, 6, 7, 7, generator=gen))
+    x[:, ::2] -= 1.0
+    g = torch.randn(2, 6, 1, 1, generator=gen)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    orig(pool, xa).backward(g)
+    graph_step._min_pool_direct(pool, xb).backward(g)
+    assert torch.equal(orig(pool, x), graph_step._min_pool_direct(pool, x)) and torch.equal(xa.grad, xb.grad)
