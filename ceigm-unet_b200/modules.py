@@ -337,6 +337,19 @@ class GroupMambaLayer(nn.Module):
         return Fn.linear_ts(xm, self.proj.weight, self.proj.bias)               # :157
 
 
+class LayerNormRows(nn.LayerNorm):
+    """nn.LayerNorm over the last dimension on this package's row kernel (csrc/layernorm.cu, one warp per row): the norm in
+    front of the FFN in the reference's Block_mamba (`self.norm2`, groupmamba.py:200, 225) and the patch-embedding norms.
+    Same parameters and state_dict as nn.LayerNorm (an existing instance can be re-classed in place); rows wider than the
+    kernel's 512 channels, inputs without affine parameters and CPU tensors keep nn.LayerNorm's own forward."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dim() >= 2 and len(self.normalized_shape) == 1 and self.elementwise_affine
+                and self.normalized_shape[0] <= Fn.ops.LN_MAX_C):
+            return Fn.layer_norm_rows(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
 # ---- the GroupMamba FFNs (SURVEY.md §8-f3): same constructors, sub-module names and initialisation as the reference, the
 #      depthwise stack between the two linear layers on this package's channels-last kernels ----
 def _ffn_init_weights(m):

@@ -115,3 +115,19 @@ def load_ref_cuda_ext():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def reclass_layernorms(net):
+    """Level 2 also covers the LayerNorms of the GroupMamba encoder (Block_mamba.norm2 in front of the FFN, the patch-embedding
+    and stage norms: groupmamba.py:200, 225, 231): every plain nn.LayerNorm over <= 512 channels is RE-CLASSED in place to
+    ceigm_unet_b200.LayerNormRows (this repo's row kernel, csrc/layernorm.cu) — same parameters, same state_dict. Returns the
+    number of modules switched."""
+    import torch
+    import ceigm_unet_b200 as pkg
+    n = 0
+    for mod in net.modules():
+        if type(mod) is torch.nn.LayerNorm and len(mod.normalized_shape) == 1 and mod.elementwise_affine \
+                and mod.normalized_shape[0] <= pkg.ops.LN_MAX_C:
+            mod.__class__ = pkg.LayerNormRows
+            n += 1
+    return n

@@ -30,6 +30,8 @@ def build(num_classes: int = 9, level: str = "dropin", device="cuda", seed: int 
     torch.manual_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):           # the reference prints a banner and a checkpoint path
         net = m.build_model(in_channels=3, num_classes=num_classes)
+    if level == "fused":
+        refmodel.reclass_layernorms(net)
     return net.to(device)
 
 

@@ -447,3 +447,32 @@ def test_ss2d_fused_epilogue_and_out_proj_kernel(monkeypatch, mode):
     assert rel_err(dx1, dx0.cpu().numpy()) < tol
     for n in g0:
         assert rel_err(g1[n].float(), g0[n].float().cpu().numpy()) < 2 * tol, n
+
+
+@pytest.mark.parametrize("C,amp", [(64, False), (448, False), (348, True), (600, False)])
+def test_layernorm_rows_module_equals_nn_layernorm(C, amp):
+    """ceigm_unet_b200.LayerNormRows (re-classed nn.LayerNorm, csrc/layernorm.cu; wider than 512 channels: nn.LayerNorm's own
+    forward) against nn.LayerNorm: output, input and parameter gradients; under bf16 autocast both return fp32."""
+    import ceigm_unet_b200 as P
+    torch.manual_seed(C)
+    ref = torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        ref.weight.add_(0.1 * torch.randn_like(ref.weight)); ref.bias.add_(0.1 * torch.randn_like(ref.bias))
+    ours = torch.nn.LayerNorm(C).cuda()
+    ours.load_state_dict(ref.state_dict())
+    ours.__class__ = P.LayerNormRows
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    x = torch.randn(3, 50, C, device="cuda")
+    if amp:
+        x = x.bfloat16()
+    dy = torch.randn(3, 50, C, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        ya, yb = ref(xa), ours(xb)
+    assert ya.dtype == yb.dtype
+    (ya * dy).sum().backward(); (yb * dy).sum().backward()
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+    tol = 2e-2 if amp else 1e-4
+    assert rel(yb, ya) < 1e-4 and rel(xb.grad, xa.grad) < tol
+    assert rel(ours.weight.grad, ref.weight.grad) < 1e-3 and rel(ours.bias.grad, ref.bias.grad) < 1e-3

@@ -196,6 +196,8 @@ def test_build_model_224_forward_backward(level):
     m_gpu = R.load_reference(scan="dropin", fused=(level == "fused"))
     torch.manual_seed(42)
     net = m_gpu.build_model(in_channels=3, num_classes=9)
+    if level == "fused":
+        assert R.reclass_layernorms(net) > 0              # the encoder's LayerNorms on this repo's row kernel (level 2)
     missing, unexpected = net.load_state_dict(sd, strict=True)
     assert not missing and not unexpected
     net = net.cuda().eval()
