@@ -12,7 +12,8 @@ shape, so forward + loss + backward + optimizer are captured ONCE into a CUDA gr
   * `AdaptiveMinPool2d` (model/best_decoder.py:179-191) computes a global minimum through `F.unfold` with a kernel as large
     as the map — an im2col copy of the tensor, 18 % of the step's GPU time; the harness rebinds it to the same `min(dim=2)` on
     `x.flatten(2)` (bit-identical values and gradient routing, tests/test_reference_gpu.py);
-  * AdamW runs with `capturable=True` (step counter on the device);
+  * AdamW runs with `capturable=True` (step counter on the device) and, on one GPU, `fused=True` (the same update in a handful of
+    multi-tensor launches instead of ~200 for-each launches plus their elementwise tails: 14 ms of a 73 ms step);
   * with N > 1 ranks the forward/backward graph writes the gradients into the GradReducer's flat buckets, the NCCL
     all-reduce runs between that graph and the optimizer graph.
 """
@@ -93,7 +94,9 @@ class GraphedTrainStep:
         self.device = next(net.parameters()).device
         self.crit = refmodel.load_losses().DiceCELoss(ce_weight=0.4, dc_weight=0.6)
         self.params = [p for p in net.parameters() if p.requires_grad]
-        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, eps=1e-8, betas=(0.9, 0.999), capturable=True)
+        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, eps=1e-8, betas=(0.9, 0.999), capturable=True,
+                                     fused=(world == 1))      # single-GPU: measured 72.7 -> 59.1 ms per step; the multi-rank path (gradients as
+                                                               # views of the flat all-reduce buffer) keeps the for-each kernels it was verified with
         self.amp_dtype = amp_dtype
         self.world = world
         self.x = torch.zeros(batch, 3, size, size, device=self.device)
