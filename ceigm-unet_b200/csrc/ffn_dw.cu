@@ -12,17 +12,19 @@
 // no split / cat, GELU and the residual never touch HBM on their own. HBM-bound: 2 (epi 0-2) or 3 (epi 3) tensor passes
 // of s bytes per element. Math in fp32 whatever the I/O type (fp32 / fp16 / bf16); erf-based GELU as nn.GELU() (gelu_phi).
 //
-// Machine mapping (second version; the first one — runtime dtype, 2 channels x 4 pixels of a row per thread, one image row
-// per CTA row — ran at 0.3 TB/s, slower than the reference composition):
-//   * a thread owns VEC consecutive channels (one 16-byte access in fp32, 8 bytes in 16-bit types; VEC drops to 2 / 1 when
-//     C or a segment boundary is not a multiple of 4) of DW_PY vertically adjacent pixels; a CTA = 16 channel lanes
-//     (16 VEC channels: whole 128 / 256-byte row pieces per pixel) x 16 pixel columns, so the horizontal neighbours of a
-//     thread are its neighbours' own centre columns (L1 hits) and the K - 1 halo rows are shared by the DW_PY outputs;
-//   * a CTA never straddles a segment: channel blocks are enumerated per segment, the kernel size is CTA-uniform and
-//     dispatched to a fully unrolled body; the block's weights are staged once in shared memory as [tap][channel]
-//     (3 x 3: copied on into registers; 5 x 5 / 7 x 7: one broadcast LDS.128 per tap and 4 VEC FMAs);
-//   * dtype, vector width and "has GELU" are template parameters; all loads of an input row are independent and issued
-//     before the FMAs that use them.
+// Machine mappings (the first version — runtime dtype, 2 channels x 4 pixels of a row per thread, one image row per CTA row —
+// ran at 0.3 TB/s, slower than the reference composition). Common to all kernels: dtype, vector width and "has GELU" are
+// template parameters; a thread owns VEC consecutive channels (one 16-byte access in fp32, 8 bytes in 16-bit types; VEC
+// drops to 2 / 1 when C or a segment boundary is not a multiple of 4); a CTA = 16 channel lanes (whole 128 / 256-byte row
+// pieces per pixel) x 16 pixel lanes; channel block is the fastest grid index.
+//   * dwnhwc_walk3_kernel: the single-segment 3 x 3 case (the DWConv of both FFNs in all its passes) — a column walker with
+//     the neighbourhood in a register window and the next three rows in flight (see the kernel's comment);
+//   * dwnhwc_stencil_kernel: the general tiled kernel (multi-scale stage, narrow vectors): DW_PY vertically adjacent
+//     pixels per thread, the K - 1 halo rows shared by the DW_PY outputs; a CTA never straddles a segment — channel blocks
+//     are enumerated per segment, the kernel size is CTA-uniform and dispatched to a fully unrolled body; 3 x 3 weights go
+//     straight from global memory into registers, 5 x 5 / 7 x 7 weights are staged as [tap][channel] in shared memory (one
+//     broadcast LDS.128 per tap and 4 VEC FMAs);
+//   * dwnhwc_wgrad_kernel: the weight / bias gradient of one segment — a row walker (see its comment).
 #include <type_traits>
 
 #include "common.cuh"
